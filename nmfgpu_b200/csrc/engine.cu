@@ -1,0 +1,593 @@
+// engine.cu -- buffer plan and per-algorithm iteration sequences (see engine.h).
+//
+// Iteration semantics follow SURVEY.md appendix A, which restates the reference:
+//   MU     source/nmf/AlgorithmMultiplicativeFrobenius.h:149-248
+//   GDCLS  source/nmf/AlgorithmGradientDescentConstrainedLeastSquares.h:159-265
+//   ALS    source/nmf/AlgorithmAlternatingLeastSquares.h:145-234
+//   ACLS / AHCLS  source/nmf/AlgorithmAlternatingHoyerConstrainedLeastSquares.h:170-295
+//   nsNMF  source/nmf/AlgorithmNonSmoothNMF.h:173-225
+// What differs from the reference is HOW: one stream, split-K partial products that the update
+// kernels consume directly (no separate numerator/denominator matrices, no multiplyDivide pass,
+// no 8-CTA normalisation kernel), and tensor-core contractions for fp32.
+#include "engine.h"
+
+#include <curand.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+#include "dist.h"
+#include "init_kernels.h"
+#include "kernels.h"
+#include "kmeans.h"
+#include "sparse.h"
+#include "tc_gemm.h"
+
+namespace nmfgpu {
+namespace b200 {
+
+namespace {
+unsigned pickSplits(unsigned tiles, unsigned reduceLen) {
+	// enough CTAs for two waves on 148 SMs, but never slices shorter than 64 reduction steps
+	unsigned s = ceilDiv(2 * 148, std::max(1u, tiles));
+	s = std::min(s, 16u);
+	s = std::min(s, std::max(1u, reduceLen / 64));
+	return std::max(1u, s);
+}
+}  // namespace
+
+template <typename T>
+struct Engine<T>::TcPlan {
+	tc::Plan plan;
+};
+
+template <typename T>
+Engine<T>::Engine(const EngineConfig& cfg) : m_cfg(cfg), m_eps(std::numeric_limits<T>::epsilon()) {
+	CUDA_CHECK(cudaStreamCreateWithFlags(&m_stream, cudaStreamNonBlocking));
+}
+
+template <typename T>
+Engine<T>::~Engine() {
+	if (m_stream) {
+		cudaStreamSynchronize(m_stream);
+		cudaStreamDestroy(m_stream);
+	}
+}
+
+template <typename T>
+void Engine<T>::synchronize() {
+	CUDA_CHECK(cudaStreamSynchronize(m_stream));
+}
+
+template <typename T>
+void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
+	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
+	if (k == 0 || m == 0 || n == 0) throw EngineError(ResultType::ErrorInvalidArgument, "empty problem");
+	// leading dimensions padded to 32 elements, as the reference's DeviceMatrix (Matrix.h:450-452):
+	// keeps cuRAND-initialised factors bit-identical and every column 128-byte aligned for TMA.
+	m_ldW = roundUp(m, 32);
+	m_ldH = roundUp(k, 32);
+
+	if (vOnDevice) {
+		if (V.format != StorageFormat::Dense) throw EngineError(ResultType::ErrorInvalidArgument, "device-resident V must be dense");
+		m_ldV = V.dense.leadingDimension;
+		m_V.adopt(V.dense.values, m_ldV * n);
+	} else {
+		m_ldV = roundUp(m, 32);
+		m_V.allocate(m_ldV * n);
+		if (V.format == StorageFormat::Dense) {
+			if (V.dense.leadingDimension < m) throw EngineError(ResultType::ErrorInvalidArgument, "leading dimension of V too small");
+			CUDA_CHECK(cudaMemcpy2DAsync(m_V.get(), m_ldV * sizeof(T), V.dense.values, (size_t)V.dense.leadingDimension * sizeof(T),
+			                             (size_t)m * sizeof(T), n, cudaMemcpyHostToDevice, m_stream));
+			if (m_ldV != m) sparse::zeroPadRows(m_V.get(), m, n, m_ldV, m_stream);
+		} else {
+			sparse::densify(V, m_V.get(), m_ldV, m_stream);
+		}
+	}
+
+	for (int b = 0; b < 2; ++b) {
+		m_W[b].allocate(m_ldW * k);
+		m_W[b].zero(m_stream);
+		m_H[b].allocate(m_ldH * n);
+		m_H[b].zero(m_stream);
+	}
+	m_G.allocate((size_t)k * k);
+	m_Gsaved.allocate((size_t)k * k);
+	m_B.allocate((size_t)k * k);
+	m_qr.allocate((size_t)k * k + k);
+
+	// tensor-core eligibility: fp32, rank that fits one UMMA N, TMA-compatible strides
+	m_useTC = false;
+	if (std::is_same<T, float>::value && m_cfg.precision != Precision::Exact) {
+		const bool ok = tc::shapeSupported(m, n, k, m_ldV, m_ldW) && (reinterpret_cast<uintptr_t>(m_V.get()) % 16 == 0);
+		if (!ok && (m_cfg.precision == Precision::Tf32x3 || m_cfg.precision == Precision::Tf32x1))
+			throw EngineError(ResultType::ErrorInvalidArgument, "tensor-core precision requested for an unsupported shape");
+		m_useTC = ok;
+	}
+
+	// split-K plans of the two V-sized products and of the Gram products
+	if (m_useTC) {
+		m_tc.reset(new TcPlan());
+		m_ldHt = roundUp(n, 32);
+		m_Whi.allocate(m_ldW * k);
+		m_Wlo.allocate(m_ldW * k);
+		m_HtHi.allocate(m_ldHt * k);
+		m_HtLo.allocate(m_ldHt * k);
+		m_Whi.zero(m_stream);
+		m_Wlo.zero(m_stream);
+		m_HtHi.zero(m_stream);
+		m_HtLo.zero(m_stream);
+		tc::makePlan(m_tc->plan, m, n, k, reinterpret_cast<const float*>(m_V.get()), m_ldV, m_Whi.get(), m_Wlo.get(), m_ldW, m_HtHi.get(),
+		             m_HtLo.get(), m_ldHt, m_cfg.precision == Precision::Tf32x1);
+		m_splitsN = m_tc->plan.splitsWtV;
+		m_splitsP = m_tc->plan.splitsVHt;
+	} else {
+		m_splitsN = kern::effectiveSplits(m, pickSplits(ceilDiv(k, 64) * ceilDiv(n, 64), m));
+		m_splitsP = kern::effectiveSplits(n, pickSplits(ceilDiv(m, 64) * ceilDiv(k, 64), n));
+	}
+	m_splitsGW = kern::effectiveSplits(m, pickSplits(ceilDiv(k, 64) * ceilDiv(k, 64), m));
+	m_splitsGH = kern::effectiveSplits(n, pickSplits(ceilDiv(k, 64) * ceilDiv(k, 64), n));
+	m_strideN = m_ldH * n;
+	m_strideP = m_ldW * k;
+	m_Npart.allocate(m_strideN * m_splitsN);
+	m_Ppart.allocate(m_strideP * (m_splitsP + 1));  // +1: slot for the summed / all-reduced product
+	m_kkScratch.allocate((size_t)k * k * std::max(m_splitsGW, m_splitsGH));
+	m_colSqPartials.allocate((size_t)ceilDiv(m, 128) * k);
+	m_colSq.allocate(k);
+	m_partN.allocate(std::max(n, k));
+	m_partK.allocate(k);
+	m_hostSecond.allocate(std::max(n, k));
+	m_hostThird.allocate(k);
+	if (m_cfg.algorithm == NmfAlgorithm::nsNMF) {
+		m_smoothW.allocate(m_ldW * k);
+		m_smoothH.allocate(m_ldH * n);
+		m_smoothW.zero(m_stream);
+		m_smoothH.zero(m_stream);
+	}
+
+	// tr(V^T V) per column, sorted ascending on the host (MU.h:117-125)
+	kern::columnDots<T>(m, n, m_V.get(), m_ldV, m_V.get(), m_ldV, m_partN.get(), m_stream);
+	m_vtvSorted.resize(n);
+	CUDA_CHECK(cudaMemcpyAsync(m_hostSecond.get(), m_partN.get(), n * sizeof(T), cudaMemcpyDeviceToHost, m_stream));
+	synchronize();
+	std::copy(m_hostSecond.get(), m_hostSecond.get() + n, m_vtvSorted.begin());
+	std::sort(m_vtvSorted.begin(), m_vtvSorted.end());
+}
+
+// ---- initial factors --------------------------------------------------------------------------------
+
+template <typename T>
+void Engine<T>::loadW(const MatrixDescription<T>& hostW) {
+	if (hostW.format != StorageFormat::Dense || hostW.dense.values == nullptr || hostW.dense.leadingDimension < m_cfg.m)
+		throw EngineError(ResultType::ErrorInvalidArgument, "matrix W must be a dense m x k host matrix");
+	CUDA_CHECK(cudaMemcpy2DAsync(m_W[m_wCur].get(), m_ldW * sizeof(T), hostW.dense.values, (size_t)hostW.dense.leadingDimension * sizeof(T),
+	                             (size_t)m_cfg.m * sizeof(T), m_cfg.k, cudaMemcpyHostToDevice, m_stream));
+}
+
+template <typename T>
+void Engine<T>::loadH(const MatrixDescription<T>& hostH) {
+	if (hostH.format != StorageFormat::Dense || hostH.dense.values == nullptr || hostH.dense.leadingDimension < m_cfg.k)
+		throw EngineError(ResultType::ErrorInvalidArgument, "matrix H must be a dense k x n host matrix");
+	CUDA_CHECK(cudaMemcpy2DAsync(m_H[m_hCur].get(), m_ldH * sizeof(T), hostH.dense.values, (size_t)hostH.dense.leadingDimension * sizeof(T),
+	                             (size_t)m_cfg.k * sizeof(T), m_cfg.n, cudaMemcpyHostToDevice, m_stream));
+}
+
+namespace {
+// cuRAND XORWOW over ld x cols elements: the stream the reference draws (RandomValueStrategy.cpp:29-38),
+// so AllRandomValues runs start from the same factors as the reference for the same seed.
+void curandFill(float* p, size_t count, unsigned seed, cudaStream_t stream) {
+	curandGenerator_t gen;
+	if (curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS)
+		throw EngineError(ResultType::ErrorExternalLibrary, "curandCreateGenerator failed");
+	curandSetStream(gen, stream);
+	curandSetPseudoRandomGeneratorSeed(gen, seed);
+	const curandStatus_t st = curandGenerateUniform(gen, p, count);
+	curandDestroyGenerator(gen);
+	if (st != CURAND_STATUS_SUCCESS) throw EngineError(ResultType::ErrorExternalLibrary, "curandGenerateUniform failed");
+}
+void curandFill(double* p, size_t count, unsigned seed, cudaStream_t stream) {
+	curandGenerator_t gen;
+	if (curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS)
+		throw EngineError(ResultType::ErrorExternalLibrary, "curandCreateGenerator failed");
+	curandSetStream(gen, stream);
+	curandSetPseudoRandomGeneratorSeed(gen, seed);
+	const curandStatus_t st = curandGenerateUniformDouble(gen, p, count);
+	curandDestroyGenerator(gen);
+	if (st != CURAND_STATUS_SUCCESS) throw EngineError(ResultType::ErrorExternalLibrary, "curandGenerateUniformDouble failed");
+}
+}  // namespace
+
+template <typename T>
+void Engine<T>::randomW(unsigned seed) {
+	curandFill(m_W[m_wCur].get(), m_ldW * m_cfg.k, seed, m_stream);
+	if (m_ldW != m_cfg.m) sparse::zeroPadRows(m_W[m_wCur].get(), m_cfg.m, m_cfg.k, m_ldW, m_stream);
+}
+
+template <typename T>
+void Engine<T>::randomH(unsigned seed) {
+	// With column shards every rank draws the full-width stream and keeps its own columns, so the
+	// factors do not depend on the number of GPUs.
+	Communicator* comm = m_cfg.comm;
+	if (comm == nullptr || comm->worldSize() == 1) {
+		curandFill(m_H[m_hCur].get(), m_ldH * m_cfg.n, seed, m_stream);
+	} else {
+		DeviceBuffer<T> full;
+		full.allocate(m_ldH * comm->globalColumns());
+		curandFill(full.get(), m_ldH * comm->globalColumns(), seed, m_stream);
+		CUDA_CHECK(cudaMemcpyAsync(m_H[m_hCur].get(), full.get() + m_ldH * comm->columnOffset(), m_ldH * m_cfg.n * sizeof(T),
+		                           cudaMemcpyDeviceToDevice, m_stream));
+		synchronize();
+	}
+	if (m_ldH != m_cfg.k) sparse::zeroPadRows(m_H[m_hCur].get(), m_cfg.k, m_cfg.n, m_ldH, m_stream);
+}
+
+template <typename T>
+void Engine<T>::meanColumnsW(unsigned seed) {
+	init::meanColumns<T>(m_cfg.m, m_cfg.n, m_cfg.k, m_V.get(), m_ldV, m_W[m_wCur].get(), m_ldW, seed, m_stream);
+}
+
+template <typename T>
+void Engine<T>::kmeansW(unsigned seed) {
+	// k-means on the data columns; the centroids become W (KMeansStrategy.cpp:54-58: 100 rounds, 0.5 %)
+	DeviceBuffer<unsigned> membership;
+	membership.allocate(m_cfg.n);
+	kmeans::run<T>(m_cfg.m, m_cfg.n, m_cfg.k, m_V.get(), m_ldV, m_W[m_wCur].get(), m_ldW, membership.get(), seed, 100, 0.005, m_stream,
+	               m_cfg.comm);
+	synchronize();
+}
+
+template <typename T>
+void Engine<T>::hFromWtV(bool absolute) {
+	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
+	const unsigned splits = kern::effectiveSplits(m, std::min(m_splitsN, 16u));
+	// m_Npart has room for m_splitsN slices; reuse them
+	const unsigned use = std::min(splits, m_splitsN);
+	kern::gemmTN<T>(m, k, n, m_W[m_wCur].get(), m_ldW, m_V.get(), m_ldV, m_Npart.get(), m_ldH, use, m_strideN, m_stream);
+	const unsigned eff = kern::effectiveSplits(m, use);
+	kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, eff, m_strideN, m_H[m_hCur].get(), m_ldH, m_stream);
+	if (absolute) kern::absInPlace<T>(k, n, m_H[m_hCur].get(), m_ldH, m_stream);
+	else kern::clampNonNegative<T>(k, n, m_H[m_hCur].get(), m_ldH, m_stream);
+}
+
+template <typename T>
+void Engine<T>::finishInitialisation() {
+	if (!m_useTC) return;
+	float* W = reinterpret_cast<float*>(m_W[m_wCur].get());
+	float* H = reinterpret_cast<float*>(m_H[m_hCur].get());
+	kern::splitTf32(m_cfg.m, m_cfg.k, W, m_ldW, m_Whi.get(), m_Wlo.get(), m_ldW, m_stream);
+	tc::splitTransposeH(m_cfg.k, m_cfg.n, H, m_ldH, m_HtHi.get(), m_HtLo.get(), m_ldHt, m_stream);
+}
+
+// ---- shared building blocks ---------------------------------------------------------------------------
+
+template <typename T>
+void Engine<T>::gramW(const T* W, T* G) {
+	const unsigned k = m_cfg.k;
+	kern::gemmTN<T>(m_cfg.m, k, k, W, m_ldW, W, m_ldW, m_kkScratch.get(), k, m_splitsGW, (size_t)k * k, m_stream);
+	kern::sumSplits<T>(k, k, m_kkScratch.get(), k, m_splitsGW, (size_t)k * k, G, k, m_stream);
+	m_launches += 2;
+}
+
+template <typename T>
+void Engine<T>::gramH(const T* H, size_t ldh, T* B) {
+	const unsigned k = m_cfg.k;
+	kern::gemmNT<T>(k, m_cfg.n, k, H, ldh, H, ldh, m_kkScratch.get(), k, m_splitsGH, (size_t)k * k, m_stream);
+	kern::sumSplits<T>(k, k, m_kkScratch.get(), k, m_splitsGH, (size_t)k * k, B, k, m_stream);
+	m_launches += 2;
+	if (m_cfg.comm && m_cfg.comm->worldSize() > 1) m_cfg.comm->allReduceSum(B, (size_t)k * k, m_stream);
+}
+
+template <typename T>
+void Engine<T>::productWtV(const T* W) {
+	if (m_useTC) {
+		tc::gemmWtV(m_tc->plan, reinterpret_cast<float*>(m_Npart.get()), m_ldH, m_strideN, m_stream);
+	} else {
+		kern::gemmTN<T>(m_cfg.m, m_cfg.k, m_cfg.n, W, m_ldW, m_V.get(), m_ldV, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_stream);
+	}
+	m_launches += 1;
+}
+
+template <typename T>
+void Engine<T>::productVHt(const T* H, size_t ldh) {
+	if (m_useTC) {
+		tc::gemmVHt(m_tc->plan, reinterpret_cast<float*>(m_Ppart.get()), m_ldW, m_strideP, m_stream);
+	} else {
+		kern::gemmNT<T>(m_cfg.m, m_cfg.n, m_cfg.k, m_V.get(), m_ldV, H, ldh, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, m_stream);
+	}
+	m_launches += 1;
+}
+
+template <typename T>
+void Engine<T>::normaliseW(unsigned blocks) {
+	kern::finishColumnNorms<T>(m_cfg.k, blocks, m_colSqPartials.get(), m_colSq.get(), m_stream);
+	kern::scaleColumns<T>(m_cfg.m, m_cfg.k, m_W[m_wCur].get(), m_ldW, m_colSq.get(), m_useTC ? m_Whi.get() : nullptr,
+	                      m_useTC ? m_Wlo.get() : nullptr, m_stream);
+	m_launches += 2;
+}
+
+// W <- W o P / (W B + eps) then unit columns; P is read as split partials, or -- with column shards --
+// summed and all-reduced into the spare slot first.
+template <typename T>
+void Engine<T>::multiplicativeW(const T* B) {
+	const T* P = m_Ppart.get();
+	unsigned splits = m_splitsP;
+	if (m_cfg.comm && m_cfg.comm->worldSize() > 1) {
+		T* sum = m_Ppart.get() + m_strideP * m_splitsP;
+		kern::sumSplits<T>(m_cfg.m, m_cfg.k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, sum, m_ldW, m_stream);
+		m_cfg.comm->allReduceSum(sum, m_strideP, m_stream);
+		m_launches += 1;
+		P = sum;
+		splits = 1;
+	}
+	const unsigned blocks = kern::updateW<T>(m_cfg.m, m_cfg.k, B, m_W[m_wCur].get(), m_W[1 - m_wCur].get(), m_ldW, P, m_ldW, splits, m_strideP,
+	                                         m_eps, m_colSqPartials.get(), m_stream);
+	m_launches += 1;
+	m_wCur = 1 - m_wCur;
+	normaliseW(blocks);
+}
+
+// ---- MU -------------------------------------------------------------------------------------------------
+template <typename T>
+void Engine<T>::iterateMU(bool err) {
+	const unsigned n = m_cfg.n, k = m_cfg.k;
+	float* htHi = m_useTC ? m_HtHi.get() : nullptr;
+	float* htLo = m_useTC ? m_HtLo.get() : nullptr;
+
+	gramW(m_W[m_wCur].get(), m_G.get());                                                    // A = W^T W      MU.h:168/176
+	productWtV(m_W[m_wCur].get());                                                          // N = W^T V      MU.h:187
+	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_eps,
+	                 err ? m_partN.get() : nullptr, htHi, htLo, m_ldHt, m_stream);        // H update       MU.h:181-197
+	m_launches += 1;
+	m_hCur = 1 - m_hCur;
+
+	gramH(m_H[m_hCur].get(), m_ldH, m_B.get());                                             // B = H H^T      MU.h:208/231
+	if (err) {
+		kern::traceKK<T>(k, m_B.get(), m_G.get(), m_partK.get(), m_stream);                 // tr(HH^T W^T W) MU.h:203-216
+		m_launches += 1;
+	}
+	if (!m_cfg.constantW) {
+		productVHt(m_H[m_hCur].get(), m_ldH);                                               // N2 = V H^T     MU.h:240
+		multiplicativeW(m_B.get());                                                         // MU.h:235-247
+	}
+	if (err) resolveError(n);
+}
+
+// ---- nsNMF ------------------------------------------------------------------------------------------------
+template <typename T>
+void Engine<T>::iterateNsNMF(bool err) {
+	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
+	const T theta = (T)m_cfg.params.theta;
+	float* htHi = m_useTC ? m_HtHi.get() : nullptr;
+	float* htLo = m_useTC ? m_HtLo.get() : nullptr;
+
+	kern::smoothRight<T>(m, k, m_W[m_wCur].get(), m_ldW, m_smoothW.get(), m_ldW, theta, m_stream);   // W~ = W S   nsNMF.h:174
+	m_launches += 1;
+	if (m_useTC) {  // the tensor-core product reads the hi/lo split of its left factor
+		kern::splitTf32(m, k, reinterpret_cast<float*>(m_smoothW.get()), m_ldW, m_Whi.get(), m_Wlo.get(), m_ldW, m_stream);
+		m_launches += 1;
+	}
+	gramW(m_smoothW.get(), m_G.get());                                                      // W~^T W~
+	productWtV(m_smoothW.get());                                                            // W~^T V
+	// the H^T split written here is overwritten below by the split of S H (what V H~^T consumes)
+	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_eps,
+	                 err ? m_partN.get() : nullptr, nullptr, nullptr, m_ldHt, m_stream);
+	m_launches += 1;
+	m_hCur = 1 - m_hCur;
+	if (!err && m_cfg.constantW) return;                                                     // nsNMF.h:193-195
+
+	kern::smoothLeft<T>(k, n, m_H[m_hCur].get(), m_ldH, m_smoothH.get(), m_ldH, theta, m_stream);   // H~ = S H   nsNMF.h:197
+	m_launches += 1;
+	gramH(m_smoothH.get(), m_ldH, m_B.get());                                               // H~ H~^T
+	if (err) {
+		gramW(m_W[m_wCur].get(), m_Gsaved.get());                                           // W^T W (unsmoothed) nsNMF.h:202-203
+		kern::traceKK<T>(k, m_B.get(), m_Gsaved.get(), m_partK.get(), m_stream);
+		m_launches += 1;
+	}
+	if (!m_cfg.constantW) {
+		if (m_useTC) {
+			tc::splitTransposeH(k, n, reinterpret_cast<float*>(m_smoothH.get()), m_ldH, htHi, htLo, m_ldHt, m_stream);
+			m_launches += 1;
+		}
+		productVHt(m_smoothH.get(), m_ldH);                                                 // V H~^T     nsNMF.h:211
+		multiplicativeW(m_B.get());                                                         // nsNMF.h:212-217
+	}
+	if (err) resolveError(n);
+}
+
+// ---- GDCLS / ALS / ACLS / AHCLS -------------------------------------------------------------------------------
+template <typename T>
+void Engine<T>::iterateLS(bool err) {
+	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
+	const NmfAlgorithm algo = m_cfg.algorithm;
+	const AlgorithmParams& p = m_cfg.params;
+	const bool multi = m_cfg.comm && m_cfg.comm->worldSize() > 1;
+	T betaW = 0, betaH = 0;
+	if (algo == NmfAlgorithm::AHCLS) {  // AHCLS.h:81-84
+		betaW = (T)((1 - p.alphaW) * std::sqrt((double)k) + p.alphaW); betaW *= betaW;
+		betaH = (T)((1 - p.alphaH) * std::sqrt((double)k) + p.alphaH); betaH *= betaH;
+	}
+
+	// ---- H <- max(0, (W^T W + C_H)^-1 W^T V)
+	gramW(m_W[m_wCur].get(), m_G.get());
+	if (err) CUDA_CHECK(cudaMemcpyAsync(m_Gsaved.get(), m_G.get(), (size_t)k * k * sizeof(T), cudaMemcpyDeviceToDevice, m_stream));
+	if (algo == NmfAlgorithm::GDCLS) kern::addConstraint<T>(k, m_G.get(), T(0), (T)p.lambda, m_stream);
+	else if (algo == NmfAlgorithm::ACLS) kern::addConstraint<T>(k, m_G.get(), T(0), (T)p.lambdaH, m_stream);
+	else if (algo == NmfAlgorithm::AHCLS) kern::addConstraint<T>(k, m_G.get(), -(T)p.lambdaH, (T)p.lambdaH * betaH - (T)p.lambdaH, m_stream);
+	kern::qrFactor<T>(k, m_G.get(), m_qr.get(), m_stream);
+	productWtV(m_W[m_wCur].get());
+	T* H = m_H[m_hCur].get();
+	kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, H, m_ldH, m_stream);
+	kern::qrSolveClamp<T>(k, m_qr.get(), H, m_ldH, n, false, m_stream);
+	m_launches += 4;
+	if (m_useTC) {
+		tc::splitTransposeH(k, n, reinterpret_cast<float*>(H), m_ldH, m_HtHi.get(), m_HtLo.get(), m_ldHt, m_stream);
+		m_launches += 1;
+	}
+
+	gramH(H, m_ldH, m_B.get());
+	if (err) {
+		kern::traceKK<T>(k, m_B.get(), m_Gsaved.get(), m_partK.get(), m_stream);            // GDCLS.h:216-227, AHCLS.h:217-224
+		m_launches += 1;
+	}
+
+	T* Psum = m_Ppart.get() + m_strideP * m_splitsP;
+	if (algo == NmfAlgorithm::GDCLS) {
+		// ---- W by the multiplicative rule; residual term from P and the NEW W (GDCLS.h:236-264)
+		if (!m_cfg.constantW) {
+			productVHt(H, m_ldH);
+			if (err && !multi) {  // multiplicativeW consumes the partials; keep a summed copy for the trace
+				kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, Psum, m_ldW, m_stream);
+				m_launches += 1;
+			}
+			multiplicativeW(m_B.get());
+		}
+		if (err) {
+			kern::columnDots<T>(m, k, Psum, m_ldW, m_W[m_wCur].get(), m_ldW, m_partN.get(), m_stream);
+			m_launches += 1;
+		}
+	} else {
+		// ---- W <- max(0, V H^T (H H^T + C_W)^-1), residual term from W BEFORE the update (AHCLS.h:226-284)
+		if (!m_cfg.constantW) {
+			if (algo == NmfAlgorithm::ACLS) kern::addConstraint<T>(k, m_B.get(), T(0), (T)p.lambdaW, m_stream);
+			else if (algo == NmfAlgorithm::AHCLS) kern::addConstraint<T>(k, m_B.get(), -(T)p.lambdaW, (T)p.lambdaW * betaW - (T)p.lambdaW, m_stream);
+			kern::qrFactor<T>(k, m_B.get(), m_qr.get(), m_stream);
+			productVHt(H, m_ldH);
+			T* Wnext = m_W[1 - m_wCur].get();
+			kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, Wnext, m_ldW, m_stream);
+			m_launches += 2;
+			if (multi) m_cfg.comm->allReduceSum(Wnext, m_strideP, m_stream);
+			if (err) {
+				kern::columnDots<T>(m, k, m_W[m_wCur].get(), m_ldW, Wnext, m_ldW, m_partN.get(), m_stream);
+				m_launches += 1;
+			}
+			kern::qrSolveClamp<T>(k, m_qr.get(), Wnext, m_ldW, m, true, m_stream);
+			m_wCur = 1 - m_wCur;
+			const unsigned blocks = kern::columnSquares<T>(m, k, m_W[m_wCur].get(), m_ldW, m_colSqPartials.get(), m_stream);
+			m_launches += 2;
+			normaliseW(blocks);
+		} else if (err) {
+			// reference quirk (AHCLS.h:259-269 with a constant W): W itself stands in for V H^T
+			kern::columnDots<T>(m, k, m_W[m_wCur].get(), m_ldW, m_W[m_wCur].get(), m_ldW, m_partN.get(), m_stream);
+			m_launches += 1;
+		}
+	}
+	if (err) resolveError(k);
+}
+
+// D2H of the partial sums, then the reference's host-side combine (FrobeniusResolver.cpp:30-51):
+// ascending sort of each array, interleaved accumulation in double, sqrt.
+template <typename T>
+void Engine<T>::resolveError(unsigned secondLen) {
+	const unsigned k = m_cfg.k;
+	const bool multi = m_cfg.comm && m_cfg.comm->worldSize() > 1;
+	CUDA_CHECK(cudaMemcpyAsync(m_hostSecond.get(), m_partN.get(), secondLen * sizeof(T), cudaMemcpyDeviceToHost, m_stream));
+	CUDA_CHECK(cudaMemcpyAsync(m_hostThird.get(), m_partK.get(), k * sizeof(T), cudaMemcpyDeviceToHost, m_stream));
+	synchronize();
+	T* second = m_hostSecond.get();
+	T* third = m_hostThird.get();
+	std::sort(second, second + secondLen);
+	std::sort(third, third + k);
+	double acc = 0.0;
+	if (!multi) {
+		const size_t len = std::max<size_t>(m_vtvSorted.size(), std::max<size_t>(secondLen, k));
+		for (size_t j = 0; j < len; ++j) {
+			if (j < m_vtvSorted.size()) acc += m_vtvSorted[j];
+			if (j < secondLen) acc -= 2.f * second[j];
+			if (j < k) acc += third[j];
+		}
+	} else {
+		// column shards: the per-column terms are local, the k x k trace terms are replicated
+		const bool secondIsLocal = m_cfg.algorithm == NmfAlgorithm::Multiplicative || m_cfg.algorithm == NmfAlgorithm::nsNMF;
+		double local = 0.0;
+		const size_t len = std::max<size_t>(m_vtvSorted.size(), secondIsLocal ? secondLen : 0);
+		for (size_t j = 0; j < len; ++j) {
+			if (j < m_vtvSorted.size()) local += m_vtvSorted[j];
+			if (secondIsLocal && j < secondLen) local -= 2.f * second[j];
+		}
+		acc = m_cfg.comm->allReduceSumHost(local);
+		for (size_t j = 0; j < k; ++j) {
+			if (!secondIsLocal && j < secondLen) acc -= 2.f * second[j];
+			acc += third[j];
+		}
+	}
+	m_frobenius = std::sqrt(acc);
+	const double mn = m_cfg.comm ? (double)m_cfg.m * (double)m_cfg.comm->globalColumns() : (double)m_cfg.m * (double)m_cfg.n;
+	m_rmsd = m_frobenius / std::sqrt(mn);
+}
+
+template <typename T>
+void Engine<T>::iterate(bool computeError) {
+	switch (m_cfg.algorithm) {
+	case NmfAlgorithm::Multiplicative: iterateMU(computeError); break;
+	case NmfAlgorithm::nsNMF: iterateNsNMF(computeError); break;
+	case NmfAlgorithm::GDCLS:
+	case NmfAlgorithm::ALS:
+	case NmfAlgorithm::ACLS:
+	case NmfAlgorithm::AHCLS: iterateLS(computeError); break;
+	default: throw EngineError(ResultType::ErrorInvalidArgument, "unknown algorithm");
+	}
+}
+
+template <typename T>
+void Engine<T>::iterateNoError(unsigned count) {
+	for (unsigned i = 0; i < count; ++i) iterate(false);
+}
+
+template <typename T>
+void Engine<T>::store(const MatrixDescription<T>& hostW, const MatrixDescription<T>& hostH) {
+	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
+	if (hostW.format != StorageFormat::Dense || hostH.format != StorageFormat::Dense)
+		throw EngineError(ResultType::ErrorInvalidArgument, "output matrices must be dense");
+	const T* W = m_W[m_wCur].get();
+	if (m_cfg.algorithm == NmfAlgorithm::nsNMF) {  // the returned basis is W S (nsNMF.h:221-225)
+		kern::smoothRight<T>(m, k, W, m_ldW, m_smoothW.get(), m_ldW, (T)m_cfg.params.theta, m_stream);
+		W = m_smoothW.get();
+	}
+	if (hostW.dense.values != nullptr)
+		CUDA_CHECK(cudaMemcpy2DAsync(hostW.dense.values, (size_t)hostW.dense.leadingDimension * sizeof(T), W, m_ldW * sizeof(T), (size_t)m * sizeof(T), k,
+		                             cudaMemcpyDeviceToHost, m_stream));
+	if (hostH.dense.values != nullptr)
+		CUDA_CHECK(cudaMemcpy2DAsync(hostH.dense.values, (size_t)hostH.dense.leadingDimension * sizeof(T), m_H[m_hCur].get(), m_ldH * sizeof(T),
+		                             (size_t)k * sizeof(T), n, cudaMemcpyDeviceToHost, m_stream));
+	synchronize();
+}
+
+template <typename T>
+void Engine<T>::debugProducts(T* wtv, T* vht, float* msWtV, float* msVHt, cudaEvent_t e0, cudaEvent_t e1) {
+	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
+	if (wtv != nullptr || msWtV != nullptr) {
+		CUDA_CHECK(cudaEventRecord(e0, m_stream));
+		productWtV(m_W[m_wCur].get());
+		CUDA_CHECK(cudaEventRecord(e1, m_stream));
+		CUDA_CHECK(cudaEventSynchronize(e1));
+		if (msWtV) CUDA_CHECK(cudaEventElapsedTime(msWtV, e0, e1));
+		if (wtv) {
+			T* sum = m_H[1 - m_hCur].get();  // spare H buffer as the landing zone
+			kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, sum, m_ldH, m_stream);
+			CUDA_CHECK(cudaMemcpy2DAsync(wtv, (size_t)k * sizeof(T), sum, m_ldH * sizeof(T), (size_t)k * sizeof(T), n, cudaMemcpyDeviceToHost, m_stream));
+			synchronize();
+		}
+	}
+	if (vht != nullptr || msVHt != nullptr) {
+		CUDA_CHECK(cudaEventRecord(e0, m_stream));
+		productVHt(m_H[m_hCur].get(), m_ldH);
+		CUDA_CHECK(cudaEventRecord(e1, m_stream));
+		CUDA_CHECK(cudaEventSynchronize(e1));
+		if (msVHt) CUDA_CHECK(cudaEventElapsedTime(msVHt, e0, e1));
+		if (vht) {
+			T* sum = m_Ppart.get() + m_strideP * m_splitsP;
+			kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, sum, m_ldW, m_stream);
+			CUDA_CHECK(cudaMemcpy2DAsync(vht, (size_t)m * sizeof(T), sum, m_ldW * sizeof(T), (size_t)m * sizeof(T), k, cudaMemcpyDeviceToHost, m_stream));
+			synchronize();
+		}
+	}
+}
+
+template class Engine<float>;
+template class Engine<double>;
+
+}  // namespace b200
+}  // namespace nmfgpu

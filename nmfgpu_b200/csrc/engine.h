@@ -1,0 +1,134 @@
+// engine.h -- device-resident state and iteration sequencing of one factorisation problem.
+//
+// An Engine<T> owns V, W, H and all scratch on one GPU and knows how to run one iteration of each
+// algorithm of include/nmfgpu.h.  It plays the role of the reference's IAlgorithm subclasses
+// (source/nmf/Algorithm*.h) but is one class with one buffer plan, a single stream, fused kernels
+// and -- for fp32 with k <= 128 -- the tcgen05 tensor-core contractions of tc_gemm.cu.
+// The run loop that drives it (error cadence, stop rule, best-run bookkeeping) is driver.cpp.
+#pragma once
+
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <random>
+#include <vector>
+
+#include "common.h"
+
+namespace nmfgpu {
+namespace b200 {
+
+class Communicator;  // dist.h: NCCL all-reduce over the column shards (nullptr = single GPU)
+
+enum class Precision {
+	Auto,     // fp32: tensor cores (3xTF32) when the shape allows, else SIMT; fp64: SIMT
+	Exact,    // SIMT FFMA/DFMA only ("fp32-exact mode")
+	Tf32x3,   // force the tcgen05 3xTF32 path (error if the shape does not allow it)
+	Tf32x1,   // single-pass TF32 (diagnostic: shows why the split is needed)
+};
+
+struct AlgorithmParams {
+	double lambda = 0.0;                    // GDCLS
+	double lambdaW = 0.0, lambdaH = 0.0;    // ACLS / AHCLS
+	double alphaW = 0.0, alphaH = 0.0;      // AHCLS
+	double theta = 0.0;                     // nsNMF
+};
+
+struct EngineConfig {
+	NmfAlgorithm algorithm = NmfAlgorithm::Multiplicative;
+	unsigned m = 0, n = 0, k = 0;           // n = columns held by THIS rank
+	bool constantW = false;
+	AlgorithmParams params;
+	Precision precision = Precision::Auto;
+	Communicator* comm = nullptr;
+};
+
+template <typename T>
+class Engine {
+public:
+	explicit Engine(const EngineConfig& cfg);
+	~Engine();
+
+	// Allocates every buffer and ingests V: host dense / CSR / CSC / COO (reference
+	// source/common/Matrix.h:145-232) or, when vOnDevice, a dense device pointer that is adopted
+	// without a copy.  Also computes the per-column squared norms of V (MU.h:117-125).
+	void setup(const MatrixDescription<T>& V, bool vOnDevice);
+
+	// initial factors ------------------------------------------------------------
+	void loadW(const MatrixDescription<T>& hostW);            // CopyStrategy.h:41-46
+	void loadH(const MatrixDescription<T>& hostH);
+	void randomW(unsigned seed);                              // RandomValueStrategy.cpp:29-70
+	void randomH(unsigned seed);
+	void meanColumnsW(unsigned seed);                         // MeanColumnStrategy.cpp:41-56
+	void kmeansW(unsigned seed);                              // KMeansStrategy.cpp:54-58
+	void hFromWtV(bool absolute);                             // KMeansStrategy.cpp:35-37 (+ documented |W^T V|)
+	void finishInitialisation();                              // derived buffers (TF32 splits) after W/H changed
+
+	// one iteration; if computeError the residual is resolved on the host afterwards
+	void iterate(bool computeError);
+	double frobenius() const { return m_frobenius; }
+	double rmsd() const { return m_rmsd; }
+
+	// enqueue `count` iterations without any error computation (bench / session API)
+	void iterateNoError(unsigned count);
+	void synchronize();
+
+	void store(const MatrixDescription<T>& hostW, const MatrixDescription<T>& hostH);  // MU.h:251-254
+	cudaStream_t stream() const { return m_stream; }
+	const EngineConfig& config() const { return m_cfg; }
+	bool usesTensorCores() const { return m_useTC; }
+	unsigned long long kernelLaunches() const { return m_launches; }
+	unsigned splitsWtV() const { return m_splitsN; }
+	unsigned splitsVHt() const { return m_splitsP; }
+	// test / bench hook: both V-sized products for the current factors, summed over slices, to the host
+	void debugProducts(T* wtv, T* vht, float* msWtV, float* msVHt, cudaEvent_t e0, cudaEvent_t e1);
+
+	T* deviceV() const { return m_V.get(); }
+	size_t ldV() const { return m_ldV; }
+	T* deviceW() const { return m_W[m_wCur].get(); }
+	size_t ldW() const { return m_ldW; }
+	T* deviceH() const { return m_H[m_hCur].get(); }
+	size_t ldH() const { return m_ldH; }
+
+private:
+	void iterateMU(bool err);
+	void iterateNsNMF(bool err);
+	void iterateLS(bool err);
+	void resolveError(unsigned secondLen);
+
+	void gramW(const T* W, T* G);                              // G = W^T W
+	void gramH(const T* H, size_t ldh, T* B);                  // B = H H^T (all-reduced over shards)
+	void productWtV(const T* W);                               // m_Npart / m_splitsN <- W^T V
+	void productVHt(const T* H, size_t ldh);                   // m_Ppart / m_splitsP <- V H^T (all-reduced)
+	void normaliseW(unsigned blocks);
+	void multiplicativeW(const T* B);                          // W <- W o P / (W B + eps), normalise
+
+	EngineConfig m_cfg;
+	T m_eps;
+	cudaStream_t m_stream = nullptr;
+	bool m_useTC = false;
+	unsigned long long m_launches = 0;
+
+	size_t m_ldV = 0, m_ldW = 0, m_ldH = 0;
+	DeviceBuffer<T> m_V, m_W[2], m_H[2];
+	int m_wCur = 0, m_hCur = 0;
+	DeviceBuffer<T> m_G, m_Gsaved, m_B, m_kkScratch, m_qr;
+	DeviceBuffer<T> m_Npart, m_Ppart, m_smoothW, m_smoothH;
+	unsigned m_splitsN = 1, m_splitsP = 1, m_splitsGW = 1, m_splitsGH = 1;
+	size_t m_strideN = 0, m_strideP = 0;
+	DeviceBuffer<T> m_colSqPartials, m_colSq;
+	DeviceBuffer<T> m_partN, m_partK;
+	PinnedBuffer<T> m_hostSecond, m_hostThird;
+	std::vector<T> m_vtvSorted;
+	double m_vtvSum = 0.0;
+	double m_frobenius = 0.0, m_rmsd = 0.0;
+
+	// tensor-core operands (fp32 only): TF32 hi/lo splits of W (m x k) and of H^T (n x k, n contiguous)
+	DeviceBuffer<float> m_Whi, m_Wlo, m_HtHi, m_HtLo;
+	size_t m_ldHt = 0;
+	struct TcPlan;
+	std::unique_ptr<TcPlan> m_tc;
+};
+
+}  // namespace b200
+}  // namespace nmfgpu

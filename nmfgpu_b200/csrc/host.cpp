@@ -1,0 +1,206 @@
+// host.cpp -- logging, summary and the run loop (see host.h).
+#include "host.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <functional>
+#include <limits>
+#include <random>
+
+namespace nmfgpu {
+namespace b200 {
+
+// ---- logging ----------------------------------------------------------------------------------------------
+namespace {
+Verbosity g_verbosity = Verbosity::Summary;  // reference default: the summary table is printed
+}
+Verbosity currentVerbosity() { return g_verbosity; }
+void setCurrentVerbosity(Verbosity v) { g_verbosity = v; }
+
+void logf(Verbosity level, const char* fmt, ...) {
+	if (static_cast<int>(g_verbosity) < static_cast<int>(level)) return;
+	va_list ap;
+	va_start(ap, fmt);
+	vfprintf(stdout, fmt, ap);
+	va_end(ap);
+	fflush(stdout);
+}
+
+void errorf(const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vfprintf(stderr, fmt, ap);
+	va_end(ap);
+	fflush(stderr);
+}
+
+// ---- summary ------------------------------------------------------------------------------------------------
+void Summary::destroy() { delete this; }
+unsigned Summary::bestRun() const { return m_bestRun; }
+void Summary::record(unsigned index, ExecutionRecord& out) const {
+	if (index < m_records.size()) out = m_records[index];
+}
+unsigned Summary::recordCount() const { return static_cast<unsigned>(m_records.size()); }
+void Summary::insert(const ExecutionRecord& rec) {
+	// the newest record becomes the best one only if it is strictly better than all earlier ones
+	const bool better = std::none_of(m_records.begin(), m_records.end(), [&](const ExecutionRecord& r) { return r.frobenius <= rec.frobenius; });
+	m_records.push_back(rec);
+	if (better) m_bestRun = static_cast<unsigned>(m_records.size() - 1);
+}
+void Summary::reset() {
+	m_bestRun = 0;
+	m_records.clear();
+}
+
+// ---- run loop -------------------------------------------------------------------------------------------------
+namespace {
+const char* algorithmName(NmfAlgorithm a) {
+	switch (a) {
+	case NmfAlgorithm::Multiplicative: return "Multiplicative Frobenius";
+	case NmfAlgorithm::GDCLS: return "Gradient Descent Constrained Least Squares";
+	case NmfAlgorithm::ALS: return "Alternating Least Squares";
+	case NmfAlgorithm::ACLS: return "Alternating Constrained Least Squares";
+	case NmfAlgorithm::AHCLS: return "Alternating Hoyer Constrained Least Squares";
+	case NmfAlgorithm::nsNMF: return "non-smooth NMF";
+	}
+	return "?";
+}
+
+void formatDuration(char (&buf)[32], long long ms) {
+	snprintf(buf, sizeof(buf), "%02d:%02d:%02d.%03d", int(ms / 3600000), int(ms / 60000 % 60), int(ms / 1000 % 60), int(ms % 1000));
+}
+
+// per-run initialisation of W and H (reference: IAlgorithm::initialize of each algorithm + InitializationStrategy::create)
+template <typename T>
+void initialiseRun(NmfDescription<T>& desc, Engine<T>& engine, std::function<unsigned()>& nextSeed) {
+	const NmfAlgorithm algo = desc.algorithm;
+	const bool onlyW = algo == NmfAlgorithm::GDCLS || algo == NmfAlgorithm::ACLS || algo == NmfAlgorithm::AHCLS;  // GDCLS.h:147-157, AHCLS.h:158-168
+	const bool gdclsConstant = algo == NmfAlgorithm::GDCLS && desc.useConstantBasisVectors;
+	if (!gdclsConstant) {
+		desc.seed = nextSeed();  // written back to the caller's struct (MU.h:137)
+		switch (desc.initMethod) {
+		case NmfInitializationMethod::CopyExisting:
+			engine.loadW(desc.outputMatrixW);
+			if (!onlyW) engine.loadH(desc.outputMatrixH);
+			break;
+		case NmfInitializationMethod::AllRandomValues:
+			engine.randomW(desc.seed);
+			if (!onlyW) engine.randomH(desc.seed);  // same seed for both factors (RandomValueStrategy.cpp:53-70)
+			break;
+		case NmfInitializationMethod::MeanColumns:
+			engine.meanColumnsW(desc.seed);
+			if (!onlyW) engine.randomH(desc.seed);
+			break;
+		case NmfInitializationMethod::KMeansAndRandomValues:
+			engine.kmeansW(desc.seed);
+			if (!onlyW) engine.randomH(desc.seed + 1);  // KMeansStrategy.cpp:45
+			break;
+		case NmfInitializationMethod::KMeansAndAbsoluteWTV:  // the reference leaves H untouched here (B-10); the header documents |W^T V|
+			engine.kmeansW(desc.seed);
+			if (!onlyW) engine.hFromWtV(true);
+			break;
+		case NmfInitializationMethod::KMeansAndNonNegativeWTV:
+			engine.kmeansW(desc.seed);
+			if (!onlyW) engine.hFromWtV(false);
+			break;
+		case NmfInitializationMethod::EInNMF:
+			throw EngineError(ResultType::ErrorInvalidArgument, "EInNMF initialisation is not provided (reference kernel has undefined warp-shuffle behaviour on sm_70+)");
+		default:
+			throw EngineError(ResultType::ErrorInvalidArgument, "unknown initialisation method");
+		}
+	}
+	if (desc.useConstantBasisVectors) engine.loadW(desc.outputMatrixW);  // MU.h:144-146
+	engine.finishInitialisation();
+}
+}  // namespace
+
+template <typename T>
+bool runFactorisation(NmfDescription<T>& desc, Engine<T>& engine, Summary* summary) {
+	if (summary != nullptr) summary->reset();
+	const unsigned numIterations = desc.numIterations;
+	const unsigned numRuns = desc.numRuns;
+	const bool multi = numRuns > 1;
+	const Context* ctx = currentContext();
+
+	// seed chain: successive outputs of uniform_int<unsigned>(0, UINT_MAX) over mt19937(seed0) (Algorithm.cpp:26-31)
+	std::function<unsigned()> nextSeed =
+	    std::bind(std::uniform_int_distribution<unsigned>(0, std::numeric_limits<unsigned>::max()), std::mt19937(desc.seed));
+
+	logf(Verbosity::Summary, " Executing %u run(s) of the '%s' algorithm on CUDA device #%d%s: \n", numRuns, algorithmName(desc.algorithm),
+	     ctx ? ctx->deviceId : 0, engine.usesTensorCores() ? " (tcgen05 3xTF32)" : " (SIMT)");
+
+	bool interrupted = false;
+	double bestError = std::numeric_limits<double>::max();
+	const char* rule = multi ? " -------------------------------------------------------------------------------------------------------------\n"
+	                         : " ---------------------------------------------------------------------------------------------------\n";
+	for (unsigned run = 1; run <= numRuns; ++run) {
+		if (run == 1) {
+			logf(Verbosity::Summary, "%s", rule);
+			if (multi) logf(Verbosity::Summary, " |   Run   | Iteration |     Frobenius     |       RMSD       |       Delta      | Elapsed Time |   Status   |\n");
+			else logf(Verbosity::Summary, " | Iteration |     Frobenius     |       RMSD       |       Delta      | Elapsed Time |   Status   |\n");
+			logf(Verbosity::Summary, "%s", rule);
+		}
+		initialiseRun(desc, engine, nextSeed);
+		engine.synchronize();
+
+		const auto started = std::chrono::high_resolution_clock::now();
+		long long elapsedMs = 0;
+		double lastError = 0.0, delta = 0.0;
+		unsigned iteration = 1;
+		for (; iteration <= numIterations; ++iteration) {
+			if (desc.callbackUserInterrupt != nullptr && desc.callbackUserInterrupt()) {  // polled before every iteration (Dispatcher.cpp:171)
+				interrupted = true;
+				break;
+			}
+			const bool computeError = iteration % 10 == 0 || iteration == numIterations;  // SingleGpuDispatcher.cpp:173
+			engine.iterate(computeError);
+			if (computeError) {
+				elapsedMs = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - started).count();
+				const double current = desc.thresholdType == NmfThresholdType::Frobenius ? engine.frobenius() : engine.rmsd();
+				delta = current - lastError;
+				if (currentVerbosity() >= Verbosity::Informative) {
+					char t[32];
+					formatDuration(t, elapsedMs);
+					logf(Verbosity::Informative, " | %9u | %17.4f | %16.4f | %16.4f | %s |            |\n", iteration, engine.frobenius(), engine.rmsd(), delta, t);
+				}
+				if (lastError != 0.0 && std::fabs(delta) < desc.thresholdValue) break;  // absolute delta, never on the first check
+				lastError = current;
+			}
+		}
+		iteration = std::min(iteration, numIterations);  // SingleGpuDispatcher.cpp:205
+
+		char t[32];
+		formatDuration(t, elapsedMs);
+		const char* status = "Aborted";
+		if (!interrupted) {
+			const bool stored = engine.frobenius() < bestError;  // always Frobenius, also when thresholding on RMSD (:214)
+			if (stored) {
+				if (summary != nullptr) {
+					ExecutionRecord rec = ExecutionRecord();
+					rec.elapsedTime = elapsedMs / 1000.0;
+					rec.frobenius = engine.frobenius();
+					rec.rmsd = engine.rmsd();
+					rec.numIterations = iteration;
+					summary->insert(rec);
+				}
+				engine.store(desc.outputMatrixW, desc.outputMatrixH);
+				bestError = engine.frobenius();
+			}
+			status = stored ? "Stored" : "Discarded";
+		}
+		if (multi) logf(Verbosity::Summary, " | %7u | %9u | %17.4f | %16.4f | %16.4f | %s | %10s |\n", run, iteration, engine.frobenius(), engine.rmsd(), delta, t, status);
+		else logf(Verbosity::Summary, " | %9u | %17.4f | %16.4f | %16.4f | %s | %10s |\n", iteration, engine.frobenius(), engine.rmsd(), delta, t, status);
+		if (interrupted) break;
+	}
+	logf(Verbosity::Summary, "%s", rule);
+	engine.synchronize();
+	return !interrupted;
+}
+
+template bool runFactorisation<float>(NmfDescription<float>&, Engine<float>&, Summary*);
+template bool runFactorisation<double>(NmfDescription<double>&, Engine<double>&, Summary*);
+
+}  // namespace b200
+}  // namespace nmfgpu

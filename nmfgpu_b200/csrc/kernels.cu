@@ -1,0 +1,817 @@
+// kernels.cu -- SIMT kernels of the NMF iteration (exact fp32 / fp64 arithmetic), sm_100a.
+//
+// See kernels.h for what each launcher replaces in the reference.  Design notes:
+//   * every reduction has a fixed order (split partials + ordered sums, no float atomics), so a run
+//     is bit-reproducible and parity failures are real failures, not noise;
+//   * the elementwise MU rule is `x * num / (den + eps)` -- multiply first, then divide -- exactly as
+//     source/nmf/KernelMultiplyDivide.cu:42 of the reference;
+//   * the fused H/W update kernels keep the k x k Gram matrix in shared memory and one factor
+//     row/column in registers, so each factor is read once and written once per update.
+#include "kernels.h"
+
+#include <cstdint>
+
+#include "common.h"
+
+namespace nmfgpu {
+namespace b200 {
+namespace kern {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// tiled SIMT GEMM:  C[M x N] = sum_K A(a,kk) * B(kk,b)
+//   A_KC: A(a,kk) = A[a*lda + kk]  else A[kk*lda + a]
+//   B_KC: B(kk,b) = B[b*ldb + kk]  else B[kk*ldb + b]
+// C is column-major (a fastest).  grid = (M tiles, N tiles, splits).
+// ---------------------------------------------------------------------------------------------------
+template <typename T, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256) gemm_simt(unsigned M, unsigned N, unsigned K, const T* __restrict__ A, size_t lda,
+                                                const T* __restrict__ B, size_t ldb, T* __restrict__ C, size_t ldc, unsigned kChunk,
+                                                size_t splitStride) {
+	constexpr int BM = 64, BN = 64, BK = 32, TM = 4, TN = 4, PAD = 4;
+	__shared__ T As[BK][BM + PAD];
+	__shared__ T Bs[BK][BN + PAD];
+	const unsigned tid = threadIdx.x;
+	const unsigned tx = tid % 16, ty = tid / 16;  // tx -> M micro tile, ty -> N micro tile
+	const unsigned a0 = blockIdx.x * BM, b0 = blockIdx.y * BN;
+	const unsigned kBegin = blockIdx.z * kChunk;
+	const unsigned kEnd = min(K, kBegin + kChunk);
+
+	T acc[TM][TN];
+#pragma unroll
+	for (int i = 0; i < TM; ++i)
+#pragma unroll
+		for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+
+	for (unsigned k0 = kBegin; k0 < kEnd; k0 += BK) {
+#pragma unroll
+		for (int e = 0; e < (BM * BK) / 256; ++e) {
+			const unsigned idx = tid + e * 256;
+			unsigned a, kk;
+			if (A_KC) { kk = idx % BK; a = idx / BK; } else { a = idx % BM; kk = idx / BM; }
+			const unsigned ga = a0 + a, gk = k0 + kk;
+			T v = T(0);
+			if (ga < M && gk < kEnd) v = A_KC ? A[(size_t)ga * lda + gk] : A[(size_t)gk * lda + ga];
+			As[kk][a] = v;
+		}
+#pragma unroll
+		for (int e = 0; e < (BN * BK) / 256; ++e) {
+			const unsigned idx = tid + e * 256;
+			unsigned b, kk;
+			if (B_KC) { kk = idx % BK; b = idx / BK; } else { b = idx % BN; kk = idx / BN; }
+			const unsigned gb = b0 + b, gk = k0 + kk;
+			T v = T(0);
+			if (gb < N && gk < kEnd) v = B_KC ? B[(size_t)gb * ldb + gk] : B[(size_t)gk * ldb + gb];
+			Bs[kk][b] = v;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int kk = 0; kk < BK; ++kk) {
+			T av[TM], bv[TN];
+#pragma unroll
+			for (int i = 0; i < TM; ++i) av[i] = As[kk][tx * TM + i];
+#pragma unroll
+			for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][ty * TN + j];
+#pragma unroll
+			for (int i = 0; i < TM; ++i)
+#pragma unroll
+				for (int j = 0; j < TN; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+		}
+		__syncthreads();
+	}
+	T* Cs = C + (size_t)blockIdx.z * splitStride;
+#pragma unroll
+	for (int j = 0; j < TN; ++j) {
+		const unsigned gb = b0 + ty * TN + j;
+		if (gb >= N) continue;
+#pragma unroll
+		for (int i = 0; i < TM; ++i) {
+			const unsigned ga = a0 + tx * TM + i;
+			if (ga < M) Cs[(size_t)gb * ldc + ga] = acc[i][j];
+		}
+	}
+}
+
+template <typename T>
+__global__ void sum_splits_kernel(unsigned rows, unsigned cols, const T* __restrict__ src, size_t ldsrc, unsigned splits,
+                                  size_t splitStride, T* __restrict__ dst, size_t lddst) {
+	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned c = blockIdx.y;
+	if (r >= rows || c >= cols) return;
+	T s = T(0);
+	for (unsigned sp = 0; sp < splits; ++sp) s += src[sp * splitStride + (size_t)c * ldsrc + r];
+	dst[(size_t)c * lddst + r] = s;
+}
+
+__device__ __forceinline__ float tf32_hi(float x) {
+	uint32_t u;
+	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+	return __uint_as_float(u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// H update, generic rank: one thread per element, 32 columns per block, double buffered Hin -> Hout.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) update_h_generic(unsigned k, unsigned n, const T* __restrict__ G, const T* __restrict__ Hin,
+                                                       T* __restrict__ Hout, size_t ldh, const T* __restrict__ Npart, size_t ldn,
+                                                       unsigned splits, size_t splitStride, T eps, T* __restrict__ tracePartials,
+                                                       float* __restrict__ HtHi, float* __restrict__ HtLo, size_t ldht) {
+	extern __shared__ unsigned char smem_raw[];
+	T* hcol = reinterpret_cast<T*>(smem_raw);  // [8 warps][k]
+	const unsigned lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+	T* mine = hcol + (size_t)warp * k;
+	for (unsigned cc = 0; cc < 4; ++cc) {
+		const unsigned j = blockIdx.x * 32 + warp * 4 + cc;
+		if (j >= n) break;  // warp-uniform
+		for (unsigned t = lane; t < k; t += 32) mine[t] = Hin[(size_t)j * ldh + t];
+		__syncwarp();
+		T tr = T(0);
+		for (unsigned r = lane; r < k; r += 32) {
+			T d = T(0);
+			for (unsigned t = 0; t < k; ++t) d = fma(G[(size_t)t * k + r], mine[t], d);
+			T num = T(0);
+			for (unsigned s = 0; s < splits; ++s) num += Npart[s * splitStride + (size_t)j * ldn + r];
+			const T hn = mine[r] * num / (d + eps);
+			Hout[(size_t)j * ldh + r] = hn;
+			tr = fma(hn, num, tr);
+			if (HtHi != nullptr) {
+				const float hi = tf32_hi((float)hn);
+				HtHi[(size_t)r * ldht + j] = hi;
+				HtLo[(size_t)r * ldht + j] = (float)hn - hi;
+			}
+		}
+		if (tracePartials != nullptr) {
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+			if (lane == 0) tracePartials[j] = tr;
+		}
+		__syncwarp();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// H update, rank <= KP (fp32): 128 columns per block staged through shared memory, one column per
+// thread in registers, Gram matrix in shared memory read as broadcast float4.
+// ---------------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(128) update_h_reg(unsigned k, unsigned n, const float* __restrict__ G, const float* __restrict__ Hin,
+                                                   float* __restrict__ Hout, size_t ldh, const float* __restrict__ Npart, size_t ldn,
+                                                   unsigned splits, size_t splitStride, float eps, float* __restrict__ tracePartials,
+                                                   float* __restrict__ HtHi, float* __restrict__ HtLo, size_t ldht) {
+	constexpr int COLS = 128, LD = KP + 1;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float* Gs = reinterpret_cast<float*>(smem_raw);  // [KP][KP]: Gs[r*KP + t] = G[r + t*k]
+	float* Ht = Gs + KP * KP;                         // [COLS][LD] old H
+	float* Nt = Ht + COLS * LD;                       // [COLS][LD] numerator, then new H
+	const unsigned tid = threadIdx.x;
+	const unsigned j0 = blockIdx.x * COLS;
+	for (unsigned idx = tid; idx < KP * KP; idx += 128) {
+		const unsigned t = idx % KP, r = idx / KP;
+		Gs[idx] = (r < k && t < k) ? G[(size_t)t * k + r] : 0.f;
+	}
+	for (unsigned idx = tid; idx < COLS * KP; idx += 128) {
+		const unsigned t = idx % KP, col = idx / KP;
+		const unsigned j = j0 + col;
+		float h = 0.f, num = 0.f;
+		if (j < n && t < k) {
+			h = Hin[(size_t)j * ldh + t];
+			for (unsigned s = 0; s < splits; ++s) num += Npart[s * splitStride + (size_t)j * ldn + t];
+		}
+		Ht[col * LD + t] = h;
+		Nt[col * LD + t] = num;
+	}
+	__syncthreads();
+	float h[KP];
+#pragma unroll
+	for (int t = 0; t < KP; ++t) h[t] = Ht[tid * LD + t];
+	float tr = 0.f;
+	for (unsigned r = 0; r < k; ++r) {
+		const float4* g4 = reinterpret_cast<const float4*>(Gs + r * KP);
+		float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+		for (int q = 0; q < KP / 4; ++q) {
+			const float4 g = g4[q];
+			d0 = fmaf(g.x, h[4 * q + 0], d0);
+			d1 = fmaf(g.y, h[4 * q + 1], d1);
+			d2 = fmaf(g.z, h[4 * q + 2], d2);
+			d3 = fmaf(g.w, h[4 * q + 3], d3);
+		}
+		const float d = (d0 + d1) + (d2 + d3);
+		const float num = Nt[tid * LD + r];
+		const float hn = Ht[tid * LD + r] * num / (d + eps);
+		tr = fmaf(hn, num, tr);
+		Nt[tid * LD + r] = hn;
+	}
+	if (tracePartials != nullptr && j0 + tid < n) tracePartials[j0 + tid] = tr;
+	__syncthreads();
+	for (unsigned idx = tid; idx < COLS * KP; idx += 128) {
+		const unsigned t = idx % KP, col = idx / KP;
+		const unsigned j = j0 + col;
+		if (j < n && t < k) Hout[(size_t)j * ldh + t] = Nt[col * LD + t];
+	}
+	if (HtHi != nullptr) {
+		for (unsigned idx = tid; idx < COLS * KP; idx += 128) {
+			const unsigned col = idx % COLS, t = idx / COLS;
+			const unsigned j = j0 + col;
+			if (j < n && t < k) {
+				const float v = Nt[col * LD + t];
+				const float hi = tf32_hi(v);
+				HtHi[(size_t)t * ldht + j] = hi;
+				HtLo[(size_t)t * ldht + j] = v - hi;
+			}
+		}
+	}
+}
+
+template <typename T>
+__global__ void clamp_kernel(unsigned rows, unsigned cols, T* A, size_t lda) {
+	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned c = blockIdx.y;
+	if (r < rows && c < cols) {
+		const T v = A[(size_t)c * lda + r];
+		A[(size_t)c * lda + r] = v > T(0) ? v : T(0);
+	}
+}
+
+template <typename T>
+__global__ void abs_kernel(unsigned rows, unsigned cols, T* A, size_t lda) {
+	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned c = blockIdx.y;
+	if (r < rows && c < cols) {
+		const T v = A[(size_t)c * lda + r];
+		A[(size_t)c * lda + r] = v < T(0) ? -v : v;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// W update, generic rank: one thread per row, Win re-read through L1.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) update_w_generic(unsigned m, unsigned k, const T* __restrict__ B, const T* __restrict__ Win,
+                                                       T* __restrict__ Wout, size_t ldw, const T* __restrict__ Ppart, size_t ldp,
+                                                       unsigned splits, size_t splitStride, T eps, T* __restrict__ colSqPartials) {
+	__shared__ T warpSq[4];
+	const unsigned i = blockIdx.x * 128 + threadIdx.x;
+	const bool valid = i < m;
+	const unsigned lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+	for (unsigned c = 0; c < k; ++c) {
+		T wn = T(0);
+		if (valid) {
+			T d = T(0);
+			for (unsigned t = 0; t < k; ++t) d = fma(Win[(size_t)t * ldw + i], B[(size_t)c * k + t], d);
+			T p = T(0);
+			for (unsigned s = 0; s < splits; ++s) p += Ppart[s * splitStride + (size_t)c * ldp + i];
+			wn = Win[(size_t)c * ldw + i] * p / (d + eps);
+			Wout[(size_t)c * ldw + i] = wn;
+		}
+		T sq = wn * wn;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+		if (lane == 0) warpSq[warp] = sq;
+		__syncthreads();
+		if (threadIdx.x == 0) colSqPartials[(size_t)blockIdx.x * k + c] = (warpSq[0] + warpSq[1]) + (warpSq[2] + warpSq[3]);
+		__syncthreads();
+	}
+}
+
+// W update, rank <= KP (fp32): one row per thread in registers, H H^T in shared memory.
+template <int KP>
+__global__ void __launch_bounds__(128) update_w_reg(unsigned m, unsigned k, const float* __restrict__ B, const float* __restrict__ Win,
+                                                   float* __restrict__ Wout, size_t ldw, const float* __restrict__ Ppart, size_t ldp,
+                                                   unsigned splits, size_t splitStride, float eps, float* __restrict__ colSqPartials) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float* Bs = reinterpret_cast<float*>(smem_raw);  // [KP][KP]: Bs[c*KP + t] = B[t + c*k]
+	float* sq = Bs + KP * KP;                         // [4][KP]
+	const unsigned tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+	for (unsigned idx = tid; idx < KP * KP; idx += 128) {
+		const unsigned t = idx % KP, c = idx / KP;
+		Bs[idx] = (c < k && t < k) ? B[(size_t)c * k + t] : 0.f;
+	}
+	__syncthreads();
+	const unsigned i = blockIdx.x * 128 + tid;
+	const bool valid = i < m;
+	float w[KP];
+#pragma unroll
+	for (int t = 0; t < KP; ++t) w[t] = (valid && t < (int)k) ? Win[(size_t)t * ldw + i] : 0.f;
+	for (unsigned c = 0; c < k; ++c) {
+		const float4* b4 = reinterpret_cast<const float4*>(Bs + c * KP);
+		float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+		for (int q = 0; q < KP / 4; ++q) {
+			const float4 b = b4[q];
+			d0 = fmaf(w[4 * q + 0], b.x, d0);
+			d1 = fmaf(w[4 * q + 1], b.y, d1);
+			d2 = fmaf(w[4 * q + 2], b.z, d2);
+			d3 = fmaf(w[4 * q + 3], b.w, d3);
+		}
+		const float d = (d0 + d1) + (d2 + d3);
+		float wn = 0.f;
+		if (valid) {
+			float p = 0.f;
+			for (unsigned s = 0; s < splits; ++s) p += Ppart[s * splitStride + (size_t)c * ldp + i];
+			wn = Win[(size_t)c * ldw + i] * p / (d + eps);
+			Wout[(size_t)c * ldw + i] = wn;
+		}
+		float s2 = wn * wn;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+		if (lane == 0) sq[warp * KP + c] = s2;
+	}
+	__syncthreads();
+	for (unsigned c = tid; c < k; c += 128)
+		colSqPartials[(size_t)blockIdx.x * k + c] = (sq[c] + sq[KP + c]) + (sq[2 * KP + c] + sq[3 * KP + c]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) column_squares_kernel(unsigned m, unsigned k, const T* __restrict__ W, size_t ldw,
+                                                            T* __restrict__ colSqPartials) {
+	__shared__ T warpSq[4];
+	const unsigned i = blockIdx.x * 128 + threadIdx.x;
+	const unsigned lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+	for (unsigned c = 0; c < k; ++c) {
+		const T v = i < m ? W[(size_t)c * ldw + i] : T(0);
+		T sq = v * v;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+		if (lane == 0) warpSq[warp] = sq;
+		__syncthreads();
+		if (threadIdx.x == 0) colSqPartials[(size_t)blockIdx.x * k + c] = (warpSq[0] + warpSq[1]) + (warpSq[2] + warpSq[3]);
+		__syncthreads();
+	}
+}
+
+// one block per column; fixed-order tree over the row-block partials
+template <typename T>
+__global__ void __launch_bounds__(256) finish_norms_kernel(unsigned k, unsigned blocks, const T* __restrict__ partials, T* __restrict__ colSq) {
+	__shared__ T red[256];
+	const unsigned c = blockIdx.x;
+	T s = T(0);
+	for (unsigned b = threadIdx.x; b < blocks; b += 256) s += partials[(size_t)b * k + c];
+	red[threadIdx.x] = s;
+	__syncthreads();
+	for (unsigned o = 128; o > 0; o >>= 1) {
+		if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) colSq[c] = red[0];
+}
+
+template <typename T>
+__global__ void scale_columns_kernel(unsigned m, unsigned k, T* __restrict__ W, size_t ldw, const T* __restrict__ colSq,
+                                     float* __restrict__ Whi, float* __restrict__ Wlo) {
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned c = blockIdx.y;
+	if (i >= m || c >= k) return;
+	const T s = colSq[c];
+	T v = W[(size_t)c * ldw + i];
+	if (s > T(0)) {
+		v = v / sqrt(s);
+		W[(size_t)c * ldw + i] = v;
+	}
+	if (Whi != nullptr) {
+		const float hi = tf32_hi((float)v);
+		Whi[(size_t)c * ldw + i] = hi;
+		Wlo[(size_t)c * ldw + i] = (float)v - hi;
+	}
+}
+
+__global__ void split_tf32_kernel(unsigned rows, unsigned cols, const float* __restrict__ X, size_t ldx, float* __restrict__ hi,
+                                  float* __restrict__ lo, size_t ldo) {
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned c = blockIdx.y;
+	if (i >= rows || c >= cols) return;
+	const float v = X[(size_t)c * ldx + i];
+	const float h = tf32_hi(v);
+	hi[(size_t)c * ldo + i] = h;
+	lo[(size_t)c * ldo + i] = v - h;
+}
+
+// one warp per column: partial[j] = sum_i A[i,j]*B[i,j]
+template <typename T>
+__global__ void __launch_bounds__(256) column_dots_kernel(unsigned rows, unsigned cols, const T* __restrict__ A, size_t lda,
+                                                         const T* __restrict__ B, size_t ldb, T* __restrict__ partial) {
+	const unsigned j = blockIdx.x * 8 + threadIdx.x / 32;
+	const unsigned lane = threadIdx.x % 32;
+	if (j >= cols) return;
+	const T* a = A + (size_t)j * lda;
+	const T* b = B + (size_t)j * ldb;
+	T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+	unsigned i = lane;
+	for (; i + 96 < rows; i += 128) {
+		s0 = fma(a[i], b[i], s0);
+		s1 = fma(a[i + 32], b[i + 32], s1);
+		s2 = fma(a[i + 64], b[i + 64], s2);
+		s3 = fma(a[i + 96], b[i + 96], s3);
+	}
+	for (; i < rows; i += 32) s0 = fma(a[i], b[i], s0);
+	T s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+	if (lane == 0) partial[j] = s;
+}
+
+template <typename T>
+__global__ void trace_kk_kernel(unsigned k, const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ partial) {
+	const unsigned d = blockIdx.x * blockDim.x + threadIdx.x;
+	if (d >= k) return;
+	T s = T(0);
+	for (unsigned i = 0; i < k; ++i) s = fma(A[(size_t)i * k + d], B[(size_t)d * k + i], s);
+	partial[d] = s;
+}
+
+template <typename T>
+__global__ void add_constraint_kernel(unsigned k, T* G, T offdiag, T diag) {
+	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned c = blockIdx.y;
+	if (r < k && c < k) G[(size_t)c * k + r] += (r == c) ? diag : offdiag;
+}
+
+// X[i,c] = (1-theta) W[i,c] + (theta/k) * sum_t W[i,t]
+template <typename T>
+__global__ void __launch_bounds__(128) smooth_right_kernel(unsigned m, unsigned k, const T* __restrict__ W, size_t ldw, T* __restrict__ X,
+                                                          size_t ldx, T theta) {
+	const unsigned i = blockIdx.x * 128 + threadIdx.x;
+	if (i >= m) return;
+	T rs = T(0);
+	for (unsigned t = 0; t < k; ++t) rs += W[(size_t)t * ldw + i];
+	const T off = theta / T(k);
+	for (unsigned c = 0; c < k; ++c) X[(size_t)c * ldx + i] = (T(1) - theta) * W[(size_t)c * ldw + i] + off * rs;
+}
+
+// Y[r,j] = (1-theta) H[r,j] + (theta/k) * sum_t H[t,j]; one warp per column
+template <typename T>
+__global__ void __launch_bounds__(256) smooth_left_kernel(unsigned k, unsigned n, const T* __restrict__ H, size_t ldh, T* __restrict__ Y,
+                                                         size_t ldy, T theta) {
+	const unsigned j = blockIdx.x * 8 + threadIdx.x / 32;
+	const unsigned lane = threadIdx.x % 32;
+	if (j >= n) return;
+	T cs = T(0);
+	for (unsigned t = lane; t < k; t += 32) cs += H[(size_t)j * ldh + t];
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
+	const T off = theta / T(k);
+	for (unsigned r = lane; r < k; r += 32) Y[(size_t)j * ldy + r] = (T(1) - theta) * H[(size_t)j * ldh + r] + off * cs;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k x k Householder QR in one block (shared memory), then independent solves.
+// factor layout: [k*k] R (upper) + Householder vectors (below the diagonal, unit leading element
+// implied) followed by [k] tau.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) qr_factor_kernel(unsigned k, const T* __restrict__ G, T* __restrict__ factor) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	T* a = reinterpret_cast<T*>(smem_raw);  // [k][k] column-major
+	T* tau = a + (size_t)k * k;
+	__shared__ T s_norm, s_tau, s_scale, s_beta;
+	__shared__ T red[256];
+	const unsigned tid = threadIdx.x;
+	for (unsigned idx = tid; idx < k * k; idx += 256) a[idx] = G[idx];
+	__syncthreads();
+	for (unsigned j = 0; j < k; ++j) {
+		T* col = a + (size_t)j * k;
+		T part = T(0);
+		for (unsigned i = j + tid; i < k; i += 256) part += col[i] * col[i];
+		red[tid] = part;
+		__syncthreads();
+		for (unsigned o = 128; o > 0; o >>= 1) {
+			if (tid < o) red[tid] += red[tid + o];
+			__syncthreads();
+		}
+		if (tid == 0) {
+			const T norm = sqrt(red[0]);
+			s_norm = norm;
+			if (norm == T(0)) {
+				s_tau = T(0);
+				s_scale = T(0);
+				s_beta = T(0);
+			} else {
+				const T alpha = col[j];
+				const T beta = alpha >= T(0) ? -norm : norm;
+				s_tau = (beta - alpha) / beta;
+				s_scale = T(1) / (alpha - beta);
+				s_beta = beta;
+			}
+			tau[j] = s_tau;
+		}
+		__syncthreads();
+		if (s_norm != T(0)) {
+			for (unsigned i = j + 1 + tid; i < k; i += 256) col[i] *= s_scale;
+			__syncthreads();
+			if (tid == 0) col[j] = s_beta;
+			// apply the reflector to the trailing columns: one thread per column
+			for (unsigned c = j + 1 + tid; c < k; c += 256) {
+				T* cc = a + (size_t)c * k;
+				T dot = cc[j];
+				for (unsigned i = j + 1; i < k; ++i) dot = fma(col[i], cc[i], dot);
+				dot *= s_tau;
+				cc[j] -= dot;
+				for (unsigned i = j + 1; i < k; ++i) cc[i] -= dot * col[i];
+			}
+		}
+		__syncthreads();
+	}
+	for (unsigned idx = tid; idx < k * k + k; idx += 256) factor[idx] = a[idx];
+}
+
+// one thread per right-hand side; the vector lives in shared memory (stride k+1, conflict free)
+template <typename T>
+__global__ void __launch_bounds__(64) qr_solve_clamp_kernel(unsigned k, const T* __restrict__ factor, T* __restrict__ R, size_t ldr,
+                                                           unsigned nrhs, bool transposed) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	T* xs = reinterpret_cast<T*>(smem_raw);  // [64][k+1]
+	const unsigned tid = threadIdx.x;
+	const unsigned base = blockIdx.x * 64;
+	const unsigned ld = k + 1;
+	const T* tau = factor + (size_t)k * k;
+	// stage: coalesced along the contiguous direction of R
+	if (transposed) {  // R is nrhs x k: element (q, c) at R[q + c*ldr]
+		for (unsigned c = 0; c < k; ++c) {
+			const unsigned q = base + tid;
+			xs[tid * ld + c] = q < nrhs ? R[(size_t)c * ldr + q] : T(0);
+		}
+	} else {  // R is k x nrhs: element (c, q) at R[c + q*ldr]
+		for (unsigned idx = tid; idx < 64 * k; idx += 64) {
+			const unsigned c = idx % k, qq = idx / k;
+			const unsigned q = base + qq;
+			xs[qq * ld + c] = q < nrhs ? R[(size_t)q * ldr + c] : T(0);
+		}
+	}
+	__syncthreads();
+	T* x = xs + tid * ld;
+	for (unsigned j = 0; j < k; ++j) {  // x <- Q^T x
+		const T tj = tau[j];
+		if (tj == T(0)) continue;
+		const T* col = factor + (size_t)j * k;
+		T dot = x[j];
+		for (unsigned i = j + 1; i < k; ++i) dot = fma(col[i], x[i], dot);
+		dot *= tj;
+		x[j] -= dot;
+		for (unsigned i = j + 1; i < k; ++i) x[i] -= dot * col[i];
+	}
+	for (int j = (int)k - 1; j >= 0; --j) {  // back substitution
+		T s = x[j];
+		for (unsigned c = j + 1; c < k; ++c) s -= factor[(size_t)c * k + j] * x[c];
+		x[j] = s / factor[(size_t)j * k + j];
+	}
+	__syncthreads();
+	if (transposed) {
+		for (unsigned c = 0; c < k; ++c) {
+			const unsigned q = base + tid;
+			if (q < nrhs) {
+				const T v = xs[tid * ld + c];
+				R[(size_t)c * ldr + q] = v > T(0) ? v : T(0);
+			}
+		}
+	} else {
+		for (unsigned idx = tid; idx < 64 * k; idx += 64) {
+			const unsigned c = idx % k, qq = idx / k;
+			const unsigned q = base + qq;
+			if (q < nrhs) {
+				const T v = xs[qq * ld + c];
+				R[(size_t)q * ldr + c] = v > T(0) ? v : T(0);
+			}
+		}
+	}
+}
+
+inline void launchCheck() { CUDA_CHECK(cudaGetLastError()); }
+
+template <typename K>
+void allowSmem(K kernel, size_t bytes) {
+	if (bytes > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+}  // namespace
+
+// ===================================================================================================
+// launchers
+// ===================================================================================================
+
+template <typename T>
+void gemmTN(unsigned rows, unsigned ka, unsigned nb, const T* A, size_t lda, const T* B, size_t ldb, T* C, size_t ldc, unsigned splits,
+            size_t splitStride, cudaStream_t stream) {
+	if (splits == 0) splits = 1;
+	unsigned chunk = (unsigned)roundUp(ceilDiv(rows, splits), 32);
+	splits = ceilDiv(rows, chunk);
+	dim3 grid(ceilDiv(ka, 64), ceilDiv(nb, 64), splits);
+	gemm_simt<T, true, true><<<grid, 256, 0, stream>>>(ka, nb, rows, A, lda, B, ldb, C, ldc, chunk, splitStride);
+	launchCheck();
+}
+
+template <typename T>
+void gemmNT(unsigned ma, unsigned cols, unsigned kb, const T* A, size_t lda, const T* B, size_t ldb, T* C, size_t ldc, unsigned splits,
+            size_t splitStride, cudaStream_t stream) {
+	if (splits == 0) splits = 1;
+	unsigned chunk = (unsigned)roundUp(ceilDiv(cols, splits), 32);
+	splits = ceilDiv(cols, chunk);
+	dim3 grid(ceilDiv(ma, 64), ceilDiv(kb, 64), splits);
+	gemm_simt<T, false, false><<<grid, 256, 0, stream>>>(ma, kb, cols, A, lda, B, ldb, C, ldc, chunk, splitStride);
+	launchCheck();
+}
+
+// number of split partials the two launchers above actually produce for a requested split count
+unsigned effectiveSplits(unsigned reduceLen, unsigned splits) {
+	if (splits == 0) splits = 1;
+	unsigned chunk = (unsigned)roundUp(ceilDiv(reduceLen, splits), 32);
+	return ceilDiv(reduceLen, chunk);
+}
+
+template <typename T>
+void sumSplits(unsigned rows, unsigned cols, const T* src, size_t ldsrc, unsigned splits, size_t splitStride, T* dst, size_t lddst,
+               cudaStream_t stream) {
+	dim3 grid(ceilDiv(rows, 128), cols);
+	sum_splits_kernel<T><<<grid, 128, 0, stream>>>(rows, cols, src, ldsrc, splits, splitStride, dst, lddst);
+	launchCheck();
+}
+
+template <typename T>
+static void updateHGeneric(unsigned k, unsigned n, const T* G, const T* Hin, T* Hout, size_t ldh, const T* Npart, size_t ldn,
+                           unsigned splits, size_t splitStride, T eps, T* tracePartials, float* HtHi, float* HtLo, size_t ldht,
+                           cudaStream_t stream) {
+	const size_t smem = (size_t)8 * k * sizeof(T);
+	allowSmem(update_h_generic<T>, smem);
+	update_h_generic<T><<<ceilDiv(n, 32), 256, smem, stream>>>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps,
+	                                                            tracePartials, HtHi, HtLo, ldht);
+	launchCheck();
+}
+
+template <int KP>
+static void updateHReg(unsigned k, unsigned n, const float* G, const float* Hin, float* Hout, size_t ldh, const float* Npart, size_t ldn,
+                       unsigned splits, size_t splitStride, float eps, float* tracePartials, float* HtHi, float* HtLo, size_t ldht,
+                       cudaStream_t stream) {
+	const size_t smem = sizeof(float) * ((size_t)KP * KP + 2 * 128 * (KP + 1));
+	allowSmem(update_h_reg<KP>, smem);
+	update_h_reg<KP><<<ceilDiv(n, 128), 128, smem, stream>>>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials,
+	                                                          HtHi, HtLo, ldht);
+	launchCheck();
+}
+
+template <>
+void updateH<float>(unsigned k, unsigned n, const float* G, const float* Hin, float* Hout, size_t ldh, const float* Npart, size_t ldn,
+                    unsigned splits, size_t splitStride, float eps, float* tracePartials, float* HtHi, float* HtLo, size_t ldht,
+                    cudaStream_t stream) {
+#define NMF_ARGS k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials, HtHi, HtLo, ldht, stream
+	if (k <= 16) updateHReg<16>(NMF_ARGS);
+	else if (k <= 32) updateHReg<32>(NMF_ARGS);
+	else if (k <= 64) updateHReg<64>(NMF_ARGS);
+	else if (k <= 128) updateHReg<128>(NMF_ARGS);
+	else updateHGeneric<float>(NMF_ARGS);
+#undef NMF_ARGS
+}
+
+template <>
+void updateH<double>(unsigned k, unsigned n, const double* G, const double* Hin, double* Hout, size_t ldh, const double* Npart,
+                     size_t ldn, unsigned splits, size_t splitStride, double eps, double* tracePartials, float* HtHi, float* HtLo,
+                     size_t ldht, cudaStream_t stream) {
+	updateHGeneric<double>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials, HtHi, HtLo, ldht, stream);
+}
+
+template <typename T>
+void clampNonNegative(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream_t stream) {
+	dim3 grid(ceilDiv(rows, 128), cols);
+	clamp_kernel<T><<<grid, 128, 0, stream>>>(rows, cols, A, lda);
+	launchCheck();
+}
+
+template <typename T>
+void absInPlace(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream_t stream) {
+	dim3 grid(ceilDiv(rows, 128), cols);
+	abs_kernel<T><<<grid, 128, 0, stream>>>(rows, cols, A, lda);
+	launchCheck();
+}
+
+template <int KP>
+static unsigned updateWReg(unsigned m, unsigned k, const float* B, const float* Win, float* Wout, size_t ldw, const float* Ppart,
+                           size_t ldp, unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream) {
+	const size_t smem = sizeof(float) * ((size_t)KP * KP + 4 * KP);
+	allowSmem(update_w_reg<KP>, smem);
+	const unsigned blocks = ceilDiv(m, 128);
+	update_w_reg<KP><<<blocks, 128, smem, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials);
+	launchCheck();
+	return blocks;
+}
+
+template <>
+unsigned updateW<float>(unsigned m, unsigned k, const float* B, const float* Win, float* Wout, size_t ldw, const float* Ppart, size_t ldp,
+                        unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream) {
+#define NMF_ARGS m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, stream
+	if (k <= 16) return updateWReg<16>(NMF_ARGS);
+	if (k <= 32) return updateWReg<32>(NMF_ARGS);
+	if (k <= 64) return updateWReg<64>(NMF_ARGS);
+	if (k <= 128) return updateWReg<128>(NMF_ARGS);
+#undef NMF_ARGS
+	const unsigned blocks = ceilDiv(m, 128);
+	update_w_generic<float><<<blocks, 128, 0, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials);
+	launchCheck();
+	return blocks;
+}
+
+template <>
+unsigned updateW<double>(unsigned m, unsigned k, const double* B, const double* Win, double* Wout, size_t ldw, const double* Ppart,
+                         size_t ldp, unsigned splits, size_t splitStride, double eps, double* colSqPartials, cudaStream_t stream) {
+	const unsigned blocks = ceilDiv(m, 128);
+	update_w_generic<double><<<blocks, 128, 0, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials);
+	launchCheck();
+	return blocks;
+}
+
+template <typename T>
+void finishColumnNorms(unsigned k, unsigned blocks, const T* colSqPartials, T* colSq, cudaStream_t stream) {
+	finish_norms_kernel<T><<<k, 256, 0, stream>>>(k, blocks, colSqPartials, colSq);
+	launchCheck();
+}
+
+template <typename T>
+unsigned columnSquares(unsigned m, unsigned k, const T* W, size_t ldw, T* colSqPartials, cudaStream_t stream) {
+	const unsigned blocks = ceilDiv(m, 128);
+	column_squares_kernel<T><<<blocks, 128, 0, stream>>>(m, k, W, ldw, colSqPartials);
+	launchCheck();
+	return blocks;
+}
+
+template <typename T>
+void scaleColumns(unsigned m, unsigned k, T* W, size_t ldw, const T* colSq, float* Whi, float* Wlo, cudaStream_t stream) {
+	dim3 grid(ceilDiv(m, 256), k);
+	scale_columns_kernel<T><<<grid, 256, 0, stream>>>(m, k, W, ldw, colSq, Whi, Wlo);
+	launchCheck();
+}
+
+template <typename T>
+void columnDots(unsigned rows, unsigned cols, const T* A, size_t lda, const T* B, size_t ldb, T* partial, cudaStream_t stream) {
+	column_dots_kernel<T><<<ceilDiv(cols, 8), 256, 0, stream>>>(rows, cols, A, lda, B, ldb, partial);
+	launchCheck();
+}
+
+template <typename T>
+void traceKK(unsigned k, const T* A, const T* B, T* partial, cudaStream_t stream) {
+	trace_kk_kernel<T><<<ceilDiv(k, 128), 128, 0, stream>>>(k, A, B, partial);
+	launchCheck();
+}
+
+template <typename T>
+void addConstraint(unsigned k, T* G, T offdiag, T diag, cudaStream_t stream) {
+	dim3 grid(ceilDiv(k, 128), k);
+	add_constraint_kernel<T><<<grid, 128, 0, stream>>>(k, G, offdiag, diag);
+	launchCheck();
+}
+
+template <typename T>
+void smoothRight(unsigned m, unsigned k, const T* W, size_t ldw, T* X, size_t ldx, T theta, cudaStream_t stream) {
+	smooth_right_kernel<T><<<ceilDiv(m, 128), 128, 0, stream>>>(m, k, W, ldw, X, ldx, theta);
+	launchCheck();
+}
+
+template <typename T>
+void smoothLeft(unsigned k, unsigned n, const T* H, size_t ldh, T* Y, size_t ldy, T theta, cudaStream_t stream) {
+	smooth_left_kernel<T><<<ceilDiv(n, 8), 256, 0, stream>>>(k, n, H, ldh, Y, ldy, theta);
+	launchCheck();
+}
+
+template <typename T>
+void qrFactor(unsigned k, const T* G, T* factor, cudaStream_t stream) {
+	const size_t smem = sizeof(T) * ((size_t)k * k + k);
+	allowSmem(qr_factor_kernel<T>, smem);
+	qr_factor_kernel<T><<<1, 256, smem, stream>>>(k, G, factor);
+	launchCheck();
+}
+
+template <typename T>
+void qrSolveClamp(unsigned k, const T* factor, T* R, size_t ldr, unsigned nrhs, bool transposed, cudaStream_t stream) {
+	const size_t smem = sizeof(T) * 64 * ((size_t)k + 1);
+	allowSmem(qr_solve_clamp_kernel<T>, smem);
+	qr_solve_clamp_kernel<T><<<ceilDiv(nrhs, 64), 64, smem, stream>>>(k, factor, R, ldr, nrhs, transposed);
+	launchCheck();
+}
+
+void splitTf32(unsigned rows, unsigned cols, const float* X, size_t ldx, float* hi, float* lo, size_t ldo, cudaStream_t stream) {
+	dim3 grid(ceilDiv(rows, 256), cols);
+	split_tf32_kernel<<<grid, 256, 0, stream>>>(rows, cols, X, ldx, hi, lo, ldo);
+	launchCheck();
+}
+
+#define NMF_INSTANTIATE(T)                                                                                                             \
+	template void gemmTN<T>(unsigned, unsigned, unsigned, const T*, size_t, const T*, size_t, T*, size_t, unsigned, size_t, cudaStream_t); \
+	template void gemmNT<T>(unsigned, unsigned, unsigned, const T*, size_t, const T*, size_t, T*, size_t, unsigned, size_t, cudaStream_t); \
+	template void sumSplits<T>(unsigned, unsigned, const T*, size_t, unsigned, size_t, T*, size_t, cudaStream_t);                         \
+	template void clampNonNegative<T>(unsigned, unsigned, T*, size_t, cudaStream_t);                                                      \
+	template void absInPlace<T>(unsigned, unsigned, T*, size_t, cudaStream_t);                                                            \
+	template void finishColumnNorms<T>(unsigned, unsigned, const T*, T*, cudaStream_t);                                                   \
+	template unsigned columnSquares<T>(unsigned, unsigned, const T*, size_t, T*, cudaStream_t);                                           \
+	template void scaleColumns<T>(unsigned, unsigned, T*, size_t, const T*, float*, float*, cudaStream_t);                                \
+	template void columnDots<T>(unsigned, unsigned, const T*, size_t, const T*, size_t, T*, cudaStream_t);                                \
+	template void traceKK<T>(unsigned, const T*, const T*, T*, cudaStream_t);                                                             \
+	template void addConstraint<T>(unsigned, T*, T, T, cudaStream_t);                                                                     \
+	template void smoothRight<T>(unsigned, unsigned, const T*, size_t, T*, size_t, T, cudaStream_t);                                      \
+	template void smoothLeft<T>(unsigned, unsigned, const T*, size_t, T*, size_t, T, cudaStream_t);                                       \
+	template void qrFactor<T>(unsigned, const T*, T*, cudaStream_t);                                                                      \
+	template void qrSolveClamp<T>(unsigned, const T*, T*, size_t, unsigned, bool, cudaStream_t);
+NMF_INSTANTIATE(float)
+NMF_INSTANTIATE(double)
+#undef NMF_INSTANTIATE
+
+}  // namespace kern
+}  // namespace b200
+}  // namespace nmfgpu

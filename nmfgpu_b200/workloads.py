@@ -1,8 +1,8 @@
 """Deterministic synthetic inputs shared by tests, bench.py and the reference driver.
 
 One counter-based generator (a splitmix64 finaliser of seed and linear column-major index) is defined
-three times with identical arithmetic: here in numpy, in csrc/workload.cu for device-side generation
-of the 4 GB benchmark matrix (no H2D of V), and in oracle/ref_driver.cpp for the reference run.  Values
+twice with identical arithmetic: here in numpy and in csrc/session.cu for device-side generation of the
+4 GB benchmark matrix (no H2D of V).  Values
 are k * 2^-24 for k in [1, 2^24], i.e. strictly positive and exactly representable in fp32.
 """
 import numpy as np

@@ -22,7 +22,7 @@ def build(force=False):
     srcs = [s for s in _SRCS if os.path.exists(s)]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
         return _SO
-    cmd = ["g++", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", "-o", _SO] + srcs
+    cmd = ["g++", "-O3", "-march=x86-64-v3", "-fopenmp", "-shared", "-fPIC", "-o", _SO] + srcs
     subprocess.run(cmd, check=True)
     return _SO
 
@@ -151,3 +151,21 @@ def time_mu_iterations(V32, W0, H0, iters):
     if rc != 0:
         raise RuntimeError("oracle_mu_iterations failed")
     return t1 - t0
+
+
+def run_kmeans(X, k, seed=0, maxiter=100, threshold=0.0, reference_row_coverage=True):
+    """CPU k-means with the reference's arithmetic order.  X: (m, n) float32/float64."""
+    X = np.asfortranarray(X)
+    m, n = X.shape
+    C = np.zeros((m, k), dtype=X.dtype, order="F")
+    memb = np.zeros(n, dtype=np.uint32)
+    rounds = ctypes.c_uint(0)
+    fn = lib().oracle_kmeans_f32 if X.dtype == np.float32 else lib().oracle_kmeans_f64
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_long,
+                   ctypes.c_void_p, ctypes.c_uint, ctypes.c_uint, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_uint)]
+    rc = fn(m, n, k, X.ctypes.data, X.strides[1] // X.itemsize if n > 1 else m, C.ctypes.data, m, memb.ctypes.data, seed, maxiter,
+            threshold, int(reference_row_coverage), ctypes.byref(rounds))
+    if rc != 0:
+        raise RuntimeError("oracle_kmeans failed: %d" % rc)
+    return dict(centroids=C, memberships=memb, rounds=rounds.value)

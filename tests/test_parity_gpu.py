@@ -1,0 +1,340 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle, the golden inputs, and -- when
+oracle/_ref/libnmfgpu64_ref.so (the shim-compiled reference) is present -- against the reference itself run
+from the same CopyExisting W0/H0.
+
+Tolerances (fp32 product vs fp64 oracle; SURVEY.md 8c "self-calibrating"):
+  * per-check residual:   |res - res_oracle| / res_oracle <= max(2 * e_ref, RES_TOL)   RES_TOL = 2e-5
+  * final factors:        ||X - X_oracle||_F / ||X_oracle||_F <= max(2 * e_ref, FAC_TOL)  FAC_TOL = 2e-4
+  * V-sized products:     relative Frobenius error <= 2e-6 (3xTF32 and exact fp32 alike)
+  * k-means memberships:  bit-exact
+"""
+import os
+
+import numpy as np
+import pytest
+
+from nmfgpu_b200 import api
+from nmfgpu_b200.api import NmfInitializationMethod, ResultType
+from oracle import binding as orc
+from tests.test_oracle import PARAMS
+from tests.workloads import cfg1_inputs, dense_inputs, planted_inputs, uniform_block
+
+pytestmark = pytest.mark.gpu
+
+RES_TOL = 2e-5
+FAC_TOL = 2e-4
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libnmfgpu64_ref.so")
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / np.linalg.norm(b))
+
+
+@pytest.fixture(scope="module")
+def L():
+    lib = api.Library()
+    lib.set_verbosity(api.Verbosity.NoOutput)
+    assert lib.initialize() == ResultType.Success
+    yield lib
+    lib.finalize()
+
+
+@pytest.fixture(scope="module")
+def REF():
+    if not os.path.exists(REF_SO):
+        pytest.skip("reference build oracle/_ref/libnmfgpu64_ref.so not present")
+    try:
+        lib = api.Library(REF_SO)
+    except OSError as e:
+        pytest.skip("reference build does not load: %s" % e)
+    lib.set_verbosity(api.Verbosity.NoOutput)
+    assert lib.initialize() == ResultType.Success
+    yield lib
+    lib.finalize()
+
+
+def _trace(L, algo, V, W0, H0, checks, params, precision):
+    """residual at each of `checks` iterations through nmfgpu_compute_single (one call per check, as a C caller would)."""
+    L.set_precision(precision)
+    out = []
+    for it in checks:
+        r = L.compute(V, W0.shape[1], algorithm=algo, W0=W0, H0=H0, iterations=it, params=params)
+        assert r["rc"] == ResultType.Success, r["rc"]
+        assert r["iterations"] == it
+        out.append(r)
+    L.set_precision("auto")
+    return out
+
+
+@pytest.mark.parametrize("precision", ["auto", "fp32"])
+def test_mu_cfg1_matches_oracle(L, precision):
+    """BASELINE.json configs[0]: dense 1000x500, k=10, Lee-Seung MU, 100 iterations, fixed init."""
+    V, W0, H0 = cfg1_inputs()
+    o = orc.run_nmf("mu", V, W0, H0, 100)
+    runs = _trace(L, "mu", V, W0, H0, [10, 50, 100], {}, precision)
+    for r, idx in zip(runs, [0, 4, 9]):
+        e = abs(r["frobenius"] - o["frob"][idx]) / o["frob"][idx]
+        assert e <= RES_TOL, (precision, r["iterations"], e)
+    final = runs[-1]
+    assert rel(final["W"], o["W"]) <= FAC_TOL and rel(final["H"], o["H"]) <= FAC_TOL
+    # identities: unit columns (MU.h:247), non-negativity, trace-identity residual vs explicit ||V - W_99 H_100||
+    np.testing.assert_allclose((final["W"].astype(np.float64) ** 2).sum(axis=0), 1.0, rtol=1e-5)
+    assert (final["W"] >= 0).all() and (final["H"] >= 0).all()
+    assert abs(final["rmsd"] - final["frobenius"] / np.sqrt(V.size)) < 1e-9
+
+
+@pytest.mark.parametrize("algo", list(PARAMS))
+def test_every_algorithm_matches_oracle(L, algo):
+    V, W0, H0 = planted_inputs(700, 450, 12, seed=31)
+    o = orc.run_nmf(algo, V, W0, H0, 30, params=PARAMS[algo])
+    runs = _trace(L, algo, V, W0, H0, [10, 30], PARAMS[algo], "auto")
+    for r, idx in zip(runs, [0, 2]):
+        e = abs(r["frobenius"] - o["frob"][idx]) / o["frob"][idx]
+        assert e <= 5 * RES_TOL, (algo, r["iterations"], e)   # LS solves amplify fp32 rounding of the Gram matrix
+    assert rel(runs[-1]["W"], o["W"]) <= 5 * FAC_TOL, algo
+    assert rel(runs[-1]["H"], o["H"]) <= 5 * FAC_TOL, algo
+
+
+def test_golden_traces(L):
+    """the committed golden vectors (tests/golden/nmf_traces.json, made by the numpy restatement)"""
+    import json
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "nmf_traces.json")))
+    for algo, g in gold.items():
+        V, W0, H0 = planted_inputs(g["m"], g["n"], g["k"], seed=g["seed"])
+        r = L.compute(V, g["k"], algorithm=algo, W0=W0, H0=H0, iterations=g["iterations"], params=PARAMS[algo])
+        assert r["rc"] == ResultType.Success
+        assert abs(r["frobenius"] - g["frob"][-1]) / g["frob"][-1] <= 5 * RES_TOL, algo
+        np.testing.assert_allclose(np.abs(r["W"]).sum(axis=0), g["w_colsum"], rtol=2e-3)
+        np.testing.assert_allclose(r["H"].sum(axis=1), g["h_rowsum"], rtol=2e-3)
+
+
+@pytest.mark.parametrize("shape", [(1000, 500, 10), (777, 333, 64), (4100, 1300, 128), (260, 130, 7), (2048, 4096, 32)])
+@pytest.mark.parametrize("precision", ["auto", "fp32"])
+def test_v_sized_products(L, shape, precision):
+    """W^T V and V H^T (the two hot kernels) against numpy fp64, ragged shapes included."""
+    m, n, k = shape
+    V, W0, H0 = dense_inputs(m, n, k, seed=11)
+    L.set_precision(precision)
+    s = api.Session(L, "mu", m, n, k, V=V)
+    try:
+        s.set_factors(W0, H0)
+        wtv, vht, _, _ = s.products()
+        if precision == "auto":
+            assert s.info().uses_tensor_cores == 1, "tensor-core path not taken for %s" % (shape,)
+    finally:
+        s.close()
+        L.set_precision("auto")
+    V64, W64, H64 = V.astype(np.float64), W0.astype(np.float64), H0.astype(np.float64)
+    assert rel(wtv, W64.T @ V64) <= 2e-6
+    assert rel(vht, V64 @ H64.T) <= 2e-6
+
+
+def test_single_pass_tf32_is_not_enough(L):
+    """documents why the 3xTF32 split exists: plain TF32 misses the fp32 tolerance by orders of magnitude"""
+    m, n, k = 2048, 1024, 64
+    V, W0, H0 = dense_inputs(m, n, k, seed=5)
+    L.set_precision("tf32")
+    s = api.Session(L, "mu", m, n, k, V=V)
+    try:
+        s.set_factors(W0, H0)
+        wtv, _, _, _ = s.products(want_vht=False)
+    finally:
+        s.close()
+        L.set_precision("auto")
+    e = rel(wtv, W0.astype(np.float64).T @ V.astype(np.float64))
+    assert 2e-6 < e < 5e-3
+
+
+def test_session_trace_and_driver_agree(L):
+    V, W0, H0 = planted_inputs(600, 400, 16, seed=3)
+    s = api.Session(L, "mu", 600, 400, 16, V=V)
+    try:
+        s.set_factors(W0, H0)
+        s.iterate(9)
+        f10, _ = s.iterate_with_error()
+        s.iterate(9)
+        f20, r20 = s.iterate_with_error()
+        W, H = s.get_factors()
+    finally:
+        s.close()
+    r = L.compute(V, 16, W0=W0, H0=H0, iterations=20)
+    assert abs(r["frobenius"] - f20) <= 1e-6 * f20 and f20 < f10
+    np.testing.assert_array_equal(r["W"], W)
+    np.testing.assert_array_equal(r["H"], H)
+
+
+def test_stop_rule_and_runs(L):
+    V, W0, H0 = planted_inputs(300, 200, 5, seed=8)
+    r = L.compute(V, 5, W0=W0, H0=H0, iterations=100, threshold_value=1e9)
+    assert r["iterations"] == 20          # never on the first check, then |delta| < threshold (Dispatcher.cpp:184-200)
+    r = L.compute(V, 5, init=NmfInitializationMethod.AllRandomValues, iterations=20, runs=3, seed=123)
+    assert r["rc"] == ResultType.Success and 1 <= r["record_count"] <= 3 and r["seed"] != 123
+    hits = []
+    r = L.compute(V, 5, W0=W0, H0=H0, iterations=50, callback=lambda: (hits.append(1), len(hits) > 7)[1])
+    assert r["rc"] == ResultType.ErrorUserInterrupt and len(hits) == 8
+
+
+def test_constant_basis_vectors(L):
+    V, W0, H0 = planted_inputs(300, 200, 5, seed=8)
+    r = L.compute(V, 5, W0=W0, H0=H0, iterations=20, constant_w=True)
+    o = orc.run_nmf("mu", V, W0, H0, 20, use_constant_w=True)
+    np.testing.assert_array_equal(r["W"], W0)
+    assert rel(r["H"], o["H"]) <= FAC_TOL
+    assert abs(r["frobenius"] - o["frob"][-1]) / o["frob"][-1] <= RES_TOL
+
+
+def test_double_precision_entry_point(L):
+    V, W0, H0 = planted_inputs(300, 200, 6, seed=4, dtype=np.float64)
+    r = L.compute(V, 6, W0=W0, H0=H0, iterations=30)
+    o = orc.run_nmf("mu", V, W0, H0, 30)
+    assert r["rc"] == ResultType.Success
+    assert abs(r["frobenius"] - o["frob"][-1]) / o["frob"][-1] <= 1e-10
+    assert rel(r["W"], o["W"]) <= 1e-9 and rel(r["H"], o["H"]) <= 1e-9
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csc", "coo"])
+@pytest.mark.parametrize("base", [0, 1])
+def test_sparse_input_formats(L, fmt, base):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(2)
+    m, n, k = 200, 150, 4
+    D = (rng.random((m, n)) < 0.1) * rng.random((m, n))
+    D = D.astype(np.float32)
+    _, W0, H0 = planted_inputs(m, n, k, seed=2)
+    if fmt == "csr":
+        S = sp.csr_matrix(D)
+        a, b = S.indptr.astype(np.int32) + base, S.indices.astype(np.int32) + base
+        desc = api.sparse_description(api.StorageFormat.CSR, m, n, S.data.astype(np.float32), a, b, base)
+    elif fmt == "csc":
+        S = sp.csc_matrix(D)
+        a, b = S.indptr.astype(np.int32) + base, S.indices.astype(np.int32) + base
+        desc = api.sparse_description(api.StorageFormat.CSC, m, n, S.data.astype(np.float32), a, b, base)
+    else:
+        S = sp.coo_matrix(D)
+        a, b = S.row.astype(np.int32) + base, S.col.astype(np.int32) + base
+        desc = api.sparse_description(api.StorageFormat.COO, m, n, S.data.astype(np.float32), a, b, base)
+    r = L.compute(None, k, W0=W0, H0=H0, iterations=20, sparse=(desc, np.dtype(np.float32)))
+    d = L.compute(D, k, W0=W0, H0=H0, iterations=20)
+    assert r["rc"] == ResultType.Success
+    np.testing.assert_array_equal(r["W"], d["W"])
+    np.testing.assert_array_equal(r["H"], d["H"])
+
+
+def test_kmeans_bit_exact_vs_oracle(L):
+    rng = np.random.default_rng(7)
+    m, n, k = 1000, 600, 8     # ceil(1000/32)=32 even: full row coverage
+    X = (rng.random((m, k)).astype(np.float32)[:, rng.integers(0, k, n)] + 0.3 * rng.random((m, n)).astype(np.float32))
+    g = L.compute_kmeans(X, k, iterations=50, seed=9, threshold=0.0)
+    o = orc.run_kmeans(X, k, seed=9, maxiter=50, threshold=0.0)
+    assert g["rc"] == ResultType.Success
+    np.testing.assert_array_equal(g["memberships"], o["memberships"])
+    np.testing.assert_array_equal(g["centroids"], o["centroids"])
+
+
+def test_kmeans_odd_row_blocks_reference_quirk(L):
+    """m with an odd number of 32-row blocks: the last block keeps its Forgy values"""
+    rng = np.random.default_rng(8)
+    m, n, k = 2016, 300, 5     # ceil(2016/32) = 63 (odd) -> rows 1984..2015 never updated
+    X = (rng.random((m, k)).astype(np.float32)[:, rng.integers(0, k, n)] + 0.3 * rng.random((m, n)).astype(np.float32))
+    g = L.compute_kmeans(X, k, iterations=30, seed=1, threshold=0.0)
+    o = orc.run_kmeans(X, k, seed=1, maxiter=30, threshold=0.0)
+    np.testing.assert_array_equal(g["memberships"], o["memberships"])
+    np.testing.assert_array_equal(g["centroids"], o["centroids"])
+
+
+def test_kmeans_initialised_nmf_runs(L):
+    V, _, _ = planted_inputs(512, 300, 6, seed=12)
+    for init in (NmfInitializationMethod.KMeansAndRandomValues, NmfInitializationMethod.KMeansAndNonNegativeWTV,
+                 NmfInitializationMethod.KMeansAndAbsoluteWTV, NmfInitializationMethod.MeanColumns):
+        r = L.compute(V, 6, init=init, iterations=30, seed=5)
+        assert r["rc"] == ResultType.Success and np.isfinite(r["frobenius"])
+        assert r["frobenius"] < np.linalg.norm(V)
+
+
+# ---- against the reference itself ---------------------------------------------------------------------------------
+
+def test_reference_mu_cfg1_side_by_side(L, REF):
+    V, W0, H0 = cfg1_inputs()
+    o = orc.run_nmf("mu", V, W0, H0, 100)
+    for it, idx in [(10, 0), (100, 9)]:
+        ref = REF.compute(V, 10, W0=W0, H0=H0, iterations=it)
+        new = L.compute(V, 10, W0=W0, H0=H0, iterations=it)
+        assert ref["rc"] == ResultType.Success and new["rc"] == ResultType.Success
+        e_ref = abs(ref["frobenius"] - o["frob"][idx]) / o["frob"][idx]
+        e_new = abs(new["frobenius"] - o["frob"][idx]) / o["frob"][idx]
+        assert e_new <= max(2 * e_ref, 1e-5), (it, e_new, e_ref)
+        # the oracle itself is pinned by the reference here
+        assert e_ref <= RES_TOL, (it, e_ref)
+    for key in ("W", "H"):
+        assert rel(new[key], o[key]) <= max(2 * rel(ref[key], o[key]), 1e-4), key
+
+
+@pytest.mark.parametrize("algo", ["gdcls", "als", "acls", "ahcls", "nsnmf"])
+def test_reference_other_algorithms_side_by_side(L, REF, algo):
+    V, W0, H0 = planted_inputs(700, 450, 12, seed=31)
+    o = orc.run_nmf(algo, V, W0, H0, 30, params=PARAMS[algo])
+    ref = REF.compute(V, 12, algorithm=algo, W0=W0, H0=H0, iterations=30, params=PARAMS[algo])
+    new = L.compute(V, 12, algorithm=algo, W0=W0, H0=H0, iterations=30, params=PARAMS[algo])
+    assert ref["rc"] == ResultType.Success and new["rc"] == ResultType.Success
+    e_ref = abs(ref["frobenius"] - o["frob"][-1]) / o["frob"][-1]
+    e_new = abs(new["frobenius"] - o["frob"][-1]) / o["frob"][-1]
+    assert e_ref <= 20 * RES_TOL, (algo, e_ref)           # pins the oracle's restatement of this algorithm
+    assert e_new <= max(2 * e_ref, 5 * RES_TOL), (algo, e_new, e_ref)
+
+
+def test_reference_random_init_same_stream(L, REF):
+    """AllRandomValues draws the same cuRAND XORWOW stream over the same padded shape as the reference"""
+    V, _, _ = planted_inputs(640, 320, 8, seed=13)
+    ref = REF.compute(V, 8, init=NmfInitializationMethod.AllRandomValues, iterations=20, seed=77)
+    new = L.compute(V, 8, init=NmfInitializationMethod.AllRandomValues, iterations=20, seed=77)
+    assert ref["seed"] == new["seed"]
+    assert abs(ref["frobenius"] - new["frobenius"]) / ref["frobenius"] <= RES_TOL
+    assert rel(new["W"], ref["W"].astype(np.float64)) <= FAC_TOL
+
+
+def test_kmeans_matches_reference(L, REF):
+    rng = np.random.default_rng(17)
+    m, n, k = 1000, 500, 6
+    X = (rng.random((m, k)).astype(np.float32)[:, rng.integers(0, k, n)] + 0.3 * rng.random((m, n)).astype(np.float32))
+    ref = REF.compute_kmeans(X, k, iterations=40, seed=4, threshold=0.0)
+    new = L.compute_kmeans(X, k, iterations=40, seed=4, threshold=0.0)
+    assert ref["rc"] == ResultType.Success and new["rc"] == ResultType.Success
+    np.testing.assert_array_equal(new["memberships"], ref["memberships"])
+    np.testing.assert_array_equal(new["centroids"], ref["centroids"])
+
+
+# ---- full-size properties (BASELINE configs[1]) -----------------------------------------------------------------------
+
+def test_full_size_properties(L):
+    """100k x 10k, k=64 on the device: size-independent properties instead of an oracle run."""
+    m, n, k = 100_000, 10_000, 64
+    ld = m
+    dev = L.lib.nmfgpu_b200_device_alloc(ld * n * 4)
+    assert dev
+    try:
+        assert L.lib.nmfgpu_b200_device_uniform_f32(dev, m, n, ld, 42, m, 0, 0) == 0
+        s = api.Session(L, "mu", m, n, k, device_ptr=dev, ld_v=ld)
+        try:
+            s.set_factors(uniform_block(43, m, k), uniform_block(44, k, n))
+            s.iterate(4)
+            f5, _ = s.iterate_with_error()
+            s.iterate(4)
+            f10, r10 = s.iterate_with_error()
+            W, H = s.get_factors()
+            wtv, vht, _, _ = s.products()
+        finally:
+            s.close()
+    finally:
+        L.lib.nmfgpu_b200_device_free(dev)
+    assert np.isfinite(f10) and f10 < f5                                  # Lee-Seung monotonicity
+    np.testing.assert_allclose((W.astype(np.float64) ** 2).sum(axis=0), 1.0, rtol=1e-5)
+    assert (W >= 0).all() and (H >= 0).all()
+    assert abs(r10 - f10 / np.sqrt(float(m) * n)) < 1e-9
+    # linearity check of the products on a slice: rows/columns regenerated on the host
+    cols = slice(5000, 5016)
+    Vc = uniform_block(42, m, 16, total_rows=m, col0=5000).astype(np.float64)
+    assert rel(wtv[:, cols], W.astype(np.float64).T @ Vc) <= 2e-6
+    rows = slice(70_000, 70_016)
+    Vr = uniform_block(42, 16, n, total_rows=m, row0=70_000).astype(np.float64)
+    assert rel(vht[rows, :], Vr @ H.astype(np.float64).T) <= 2e-6
