@@ -71,7 +71,13 @@ void nmfgpu_b200_device_free(void* p);
 /* u[i, j] = f(seed, (col0 + j) * total_rows + row0 + i), the generator of nmfgpu_b200/workloads.py */
 int nmfgpu_b200_device_uniform_f32(float* dev, unsigned rows, unsigned cols, size_t ld, unsigned long long seed,
                                    unsigned long long total_rows, unsigned long long row0, unsigned long long col0);
-/* write `bytes` bytes to a scratch buffer larger than L2 (flush between timed iterations) */
+/* plain copies between a host buffer and a device buffer obtained from nmfgpu_b200_device_alloc */
+int nmfgpu_b200_device_download(void* host, const void* dev, size_t bytes);
+int nmfgpu_b200_device_upload(void* dev, const void* host, size_t bytes);
+/* page-locked host memory (so nmfgpu_compute_single's H2D of the input runs at full PCIe speed) */
+void* nmfgpu_b200_host_alloc(size_t bytes);
+void nmfgpu_b200_host_free(void* p);
+/* overwrite a 256 MB scratch buffer (twice the L2) to flush the cache between timed iterations */
 int nmfgpu_b200_flush_l2(void);
 
 #ifdef __cplusplus

@@ -147,7 +147,8 @@ EXT_SYMBOLS = ["nmfgpu_b200_set_precision", "nmfgpu_b200_dist_unique_id", "nmfgp
                "nmfgpu_b200_session_time_iterations", "nmfgpu_b200_session_products_f32",
                "nmfgpu_b200_session_synchronize", "nmfgpu_b200_session_get_info", "nmfgpu_b200_session_destroy",
                "nmfgpu_b200_device_alloc", "nmfgpu_b200_device_free", "nmfgpu_b200_device_uniform_f32",
-               "nmfgpu_b200_flush_l2"]
+               "nmfgpu_b200_flush_l2", "nmfgpu_b200_device_download", "nmfgpu_b200_device_upload", "nmfgpu_b200_host_alloc",
+               "nmfgpu_b200_host_free"]
 
 
 class SummaryHandle:
@@ -244,6 +245,12 @@ class Library:
             L.nmfgpu_b200_dist_init.argtypes = [c_int, c_int, c_void_p]
             L.nmfgpu_b200_dist_set_shard.argtypes = [c_uint, c_uint]
             L.nmfgpu_b200_set_precision.argtypes = [c_int]
+            L.nmfgpu_b200_device_download.argtypes = [c_void_p, c_void_p, c_size_t]
+            L.nmfgpu_b200_device_upload.argtypes = [c_void_p, c_void_p, c_size_t]
+            L.nmfgpu_b200_host_alloc.restype = c_void_p
+            L.nmfgpu_b200_host_alloc.argtypes = [c_size_t]
+            L.nmfgpu_b200_host_free.argtypes = [c_void_p]
+            L.nmfgpu_b200_host_free.restype = None
 
     # -- reference API ------------------------------------------------------------------------------------
     def initialize(self):

@@ -251,6 +251,29 @@ NMFGPU_EXPORT int nmfgpu_b200_device_uniform_f32(float* dev, unsigned rows, unsi
 	});
 }
 
+NMFGPU_EXPORT int nmfgpu_b200_device_download(void* host, const void* dev, size_t bytes) {
+	if (host == nullptr || dev == nullptr) return static_cast<int>(ResultType::ErrorInvalidArgument);
+	return guarded([&] { CUDA_CHECK(cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost)); });
+}
+
+NMFGPU_EXPORT int nmfgpu_b200_device_upload(void* dev, const void* host, size_t bytes) {
+	if (host == nullptr || dev == nullptr) return static_cast<int>(ResultType::ErrorInvalidArgument);
+	return guarded([&] { CUDA_CHECK(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice)); });
+}
+
+NMFGPU_EXPORT void* nmfgpu_b200_host_alloc(size_t bytes) {
+	void* p = nullptr;
+	if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
+NMFGPU_EXPORT void nmfgpu_b200_host_free(void* p) {
+	if (p) cudaFreeHost(p);
+}
+
 NMFGPU_EXPORT int nmfgpu_b200_flush_l2(void) {
 	return guarded([&] {
 		if (g_flushBuffer == nullptr) CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&g_flushBuffer), kFlushBytes));
