@@ -122,8 +122,10 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 		m_HtLo.zero(m_stream);
 		tc::makePlan(m_tc->plan, m, n, k, reinterpret_cast<const float*>(m_V.get()), m_ldV, m_Whi.get(), m_Wlo.get(), m_ldW, m_HtHi.get(),
 		             m_HtLo.get(), m_ldHt, m_cfg.precision == Precision::Tf32x1);
-		m_splitsN = m_tc->plan.splitsWtV;
-		m_splitsP = m_tc->plan.splitsVHt;
+		m_splitsN = m_tc->plan.wtv.maxSlots;
+		m_splitsP = m_tc->plan.vht.maxSlots;
+		m_slotsN = m_tc->plan.wtv.slotCount;
+		m_slotsP = m_tc->plan.vht.slotCount;
 	} else {
 		m_splitsN = kern::effectiveSplits(m, pickSplits(ceilDiv(k, 64) * ceilDiv(n, 64), m));
 		m_splitsP = kern::effectiveSplits(n, pickSplits(ceilDiv(m, 64) * ceilDiv(k, 64), n));
@@ -314,16 +316,18 @@ template <typename T>
 void Engine<T>::multiplicativeW(const T* B) {
 	const T* P = m_Ppart.get();
 	unsigned splits = m_splitsP;
+	const unsigned char* slots = m_slotsP;
 	if (m_cfg.comm && m_cfg.comm->worldSize() > 1) {
 		T* sum = m_Ppart.get() + m_strideP * m_splitsP;
-		kern::sumSplits<T>(m_cfg.m, m_cfg.k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, sum, m_ldW, m_stream);
+		kern::sumSplits<T>(m_cfg.m, m_cfg.k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, sum, m_ldW, m_stream, m_slotsP, true);
 		m_cfg.comm->allReduceSum(sum, m_strideP, m_stream);
 		m_launches += 1;
 		P = sum;
 		splits = 1;
+		slots = nullptr;
 	}
 	const unsigned blocks = kern::updateW<T>(m_cfg.m, m_cfg.k, B, m_W[m_wCur].get(), m_W[1 - m_wCur].get(), m_ldW, P, m_ldW, splits, m_strideP,
-	                                         m_eps, m_colSqPartials.get(), m_stream);
+	                                         m_eps, m_colSqPartials.get(), m_stream, slots);
 	m_launches += 1;
 	m_wCur = 1 - m_wCur;
 	normaliseW(blocks);
@@ -339,7 +343,7 @@ void Engine<T>::iterateMU(bool err) {
 	gramW(m_W[m_wCur].get(), m_G.get());                                                    // A = W^T W      MU.h:168/176
 	productWtV(m_W[m_wCur].get());                                                          // N = W^T V      MU.h:187
 	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_eps,
-	                 err ? m_partN.get() : nullptr, htHi, htLo, m_ldHt, m_stream);        // H update       MU.h:181-197
+	                 err ? m_partN.get() : nullptr, htHi, htLo, m_ldHt, m_stream, m_slotsN);   // H update  MU.h:181-197
 	m_launches += 1;
 	m_hCur = 1 - m_hCur;
 
@@ -373,7 +377,7 @@ void Engine<T>::iterateNsNMF(bool err) {
 	productWtV(m_smoothW.get());                                                            // W~^T V
 	// the H^T split written here is overwritten below by the split of S H (what V H~^T consumes)
 	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_eps,
-	                 err ? m_partN.get() : nullptr, nullptr, nullptr, m_ldHt, m_stream);
+	                 err ? m_partN.get() : nullptr, nullptr, nullptr, m_ldHt, m_stream, m_slotsN);
 	m_launches += 1;
 	m_hCur = 1 - m_hCur;
 	if (!err && m_cfg.constantW) return;                                                     // nsNMF.h:193-195
@@ -419,7 +423,7 @@ void Engine<T>::iterateLS(bool err) {
 	kern::qrFactor<T>(k, m_G.get(), m_qr.get(), m_stream);
 	productWtV(m_W[m_wCur].get());
 	T* H = m_H[m_hCur].get();
-	kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, H, m_ldH, m_stream);
+	kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, H, m_ldH, m_stream, m_slotsN, false);
 	kern::qrSolveClamp<T>(k, m_qr.get(), H, m_ldH, n, false, m_stream);
 	m_launches += 4;
 	if (m_useTC) {
@@ -439,7 +443,7 @@ void Engine<T>::iterateLS(bool err) {
 		if (!m_cfg.constantW) {
 			productVHt(H, m_ldH);
 			if (err && !multi) {  // multiplicativeW consumes the partials; keep a summed copy for the trace
-				kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, Psum, m_ldW, m_stream);
+				kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, Psum, m_ldW, m_stream, m_slotsP, true);
 				m_launches += 1;
 			}
 			multiplicativeW(m_B.get());
@@ -456,7 +460,7 @@ void Engine<T>::iterateLS(bool err) {
 			kern::qrFactor<T>(k, m_B.get(), m_qr.get(), m_stream);
 			productVHt(H, m_ldH);
 			T* Wnext = m_W[1 - m_wCur].get();
-			kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, Wnext, m_ldW, m_stream);
+			kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, Wnext, m_ldW, m_stream, m_slotsP, true);
 			m_launches += 2;
 			if (multi) m_cfg.comm->allReduceSum(Wnext, m_strideP, m_stream);
 			if (err) {
@@ -566,7 +570,7 @@ void Engine<T>::debugProducts(T* wtv, T* vht, float* msWtV, float* msVHt, cudaEv
 		if (msWtV) CUDA_CHECK(cudaEventElapsedTime(msWtV, e0, e1));
 		if (wtv) {
 			T* sum = m_H[1 - m_hCur].get();  // spare H buffer as the landing zone
-			kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, sum, m_ldH, m_stream);
+			kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, sum, m_ldH, m_stream, m_slotsN, false);
 			CUDA_CHECK(cudaMemcpy2DAsync(wtv, (size_t)k * sizeof(T), sum, m_ldH * sizeof(T), (size_t)k * sizeof(T), n, cudaMemcpyDeviceToHost, m_stream));
 			synchronize();
 		}
@@ -579,7 +583,7 @@ void Engine<T>::debugProducts(T* wtv, T* vht, float* msWtV, float* msVHt, cudaEv
 		if (msVHt) CUDA_CHECK(cudaEventElapsedTime(msVHt, e0, e1));
 		if (vht) {
 			T* sum = m_Ppart.get() + m_strideP * m_splitsP;
-			kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, sum, m_ldW, m_stream);
+			kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, sum, m_ldW, m_stream, m_slotsP, true);
 			CUDA_CHECK(cudaMemcpy2DAsync(vht, (size_t)m * sizeof(T), sum, m_ldW * sizeof(T), (size_t)m * sizeof(T), k, cudaMemcpyDeviceToHost, m_stream));
 			synchronize();
 		}

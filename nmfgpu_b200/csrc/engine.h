@@ -116,6 +116,8 @@ private:
 	DeviceBuffer<T> m_Npart, m_Ppart, m_smoothW, m_smoothH;
 	unsigned m_splitsN = 1, m_splitsP = 1, m_splitsGW = 1, m_splitsGH = 1;
 	size_t m_strideN = 0, m_strideP = 0;
+	const unsigned char* m_slotsN = nullptr;   // per-tile partial counts of the stream-K tensor-core products (tc_gemm.h)
+	const unsigned char* m_slotsP = nullptr;
 	DeviceBuffer<T> m_colSqPartials, m_colSq;
 	DeviceBuffer<T> m_partN, m_partK;
 	PinnedBuffer<T> m_hostSecond, m_hostThird;

@@ -95,10 +95,12 @@ __global__ void __launch_bounds__(256) gemm_simt(unsigned M, unsigned N, unsigne
 
 template <typename T>
 __global__ void sum_splits_kernel(unsigned rows, unsigned cols, const T* __restrict__ src, size_t ldsrc, unsigned splits,
-                                  size_t splitStride, T* __restrict__ dst, size_t lddst) {
+                                  size_t splitStride, T* __restrict__ dst, size_t lddst, const unsigned char* __restrict__ tileSlots,
+                                  bool tilesAlongRows) {
 	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned c = blockIdx.y;
 	if (r >= rows || c >= cols) return;
+	if (tileSlots != nullptr) splits = tileSlots[(tilesAlongRows ? r : c) >> 7];
 	T s = T(0);
 	for (unsigned sp = 0; sp < splits; ++sp) s += src[sp * splitStride + (size_t)c * ldsrc + r];
 	dst[(size_t)c * lddst + r] = s;
@@ -117,7 +119,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) update_h_generic(unsigned k, unsigned n, const T* __restrict__ G, const T* __restrict__ Hin,
                                                        T* __restrict__ Hout, size_t ldh, const T* __restrict__ Npart, size_t ldn,
                                                        unsigned splits, size_t splitStride, T eps, T* __restrict__ tracePartials,
-                                                       float* __restrict__ HtHi, float* __restrict__ HtLo, size_t ldht) {
+                                                       float* __restrict__ HtHi, float* __restrict__ HtLo, size_t ldht,
+                                                       const unsigned char* __restrict__ tileSlots) {
 	extern __shared__ unsigned char smem_raw[];
 	T* hcol = reinterpret_cast<T*>(smem_raw);  // [8 warps][k]
 	const unsigned lane = threadIdx.x % 32, warp = threadIdx.x / 32;
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(256) update_h_generic(unsigned k, unsigned n, 
 	for (unsigned cc = 0; cc < 4; ++cc) {
 		const unsigned j = blockIdx.x * 32 + warp * 4 + cc;
 		if (j >= n) break;  // warp-uniform
+		if (tileSlots != nullptr) splits = tileSlots[j >> 7];
 		for (unsigned t = lane; t < k; t += 32) mine[t] = Hin[(size_t)j * ldh + t];
 		__syncwarp();
 		T tr = T(0);
@@ -159,8 +163,10 @@ template <int KP>
 __global__ void __launch_bounds__(128) update_h_reg(unsigned k, unsigned n, const float* __restrict__ G, const float* __restrict__ Hin,
                                                    float* __restrict__ Hout, size_t ldh, const float* __restrict__ Npart, size_t ldn,
                                                    unsigned splits, size_t splitStride, float eps, float* __restrict__ tracePartials,
-                                                   float* __restrict__ HtHi, float* __restrict__ HtLo, size_t ldht) {
+                                                   float* __restrict__ HtHi, float* __restrict__ HtLo, size_t ldht,
+                                                   const unsigned char* __restrict__ tileSlots) {
 	constexpr int COLS = 128, LD = KP + 1;
+	if (tileSlots != nullptr) splits = tileSlots[blockIdx.x];
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	float* Gs = reinterpret_cast<float*>(smem_raw);  // [KP][KP]: Gs[r*KP + t] = G[r + t*k]
 	float* Ht = Gs + KP * KP;                         // [COLS][LD] old H
@@ -251,8 +257,10 @@ __global__ void abs_kernel(unsigned rows, unsigned cols, T* A, size_t lda) {
 template <typename T>
 __global__ void __launch_bounds__(128) update_w_generic(unsigned m, unsigned k, const T* __restrict__ B, const T* __restrict__ Win,
                                                        T* __restrict__ Wout, size_t ldw, const T* __restrict__ Ppart, size_t ldp,
-                                                       unsigned splits, size_t splitStride, T eps, T* __restrict__ colSqPartials) {
+                                                       unsigned splits, size_t splitStride, T eps, T* __restrict__ colSqPartials,
+                                                       const unsigned char* __restrict__ tileSlots) {
 	__shared__ T warpSq[4];
+	if (tileSlots != nullptr) splits = tileSlots[blockIdx.x];
 	const unsigned i = blockIdx.x * 128 + threadIdx.x;
 	const bool valid = i < m;
 	const unsigned lane = threadIdx.x % 32, warp = threadIdx.x / 32;
@@ -280,7 +288,9 @@ __global__ void __launch_bounds__(128) update_w_generic(unsigned m, unsigned k, 
 template <int KP>
 __global__ void __launch_bounds__(128) update_w_reg(unsigned m, unsigned k, const float* __restrict__ B, const float* __restrict__ Win,
                                                    float* __restrict__ Wout, size_t ldw, const float* __restrict__ Ppart, size_t ldp,
-                                                   unsigned splits, size_t splitStride, float eps, float* __restrict__ colSqPartials) {
+                                                   unsigned splits, size_t splitStride, float eps, float* __restrict__ colSqPartials,
+                                                   const unsigned char* __restrict__ tileSlots) {
+	if (tileSlots != nullptr) splits = tileSlots[blockIdx.x];
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	float* Bs = reinterpret_cast<float*>(smem_raw);  // [KP][KP]: Bs[c*KP + t] = B[t + c*k]
 	float* sq = Bs + KP * KP;                         // [4][KP]
@@ -621,39 +631,39 @@ unsigned effectiveSplits(unsigned reduceLen, unsigned splits) {
 
 template <typename T>
 void sumSplits(unsigned rows, unsigned cols, const T* src, size_t ldsrc, unsigned splits, size_t splitStride, T* dst, size_t lddst,
-               cudaStream_t stream) {
+               cudaStream_t stream, const unsigned char* tileSlots, bool tilesAlongRows) {
 	dim3 grid(ceilDiv(rows, 128), cols);
-	sum_splits_kernel<T><<<grid, 128, 0, stream>>>(rows, cols, src, ldsrc, splits, splitStride, dst, lddst);
+	sum_splits_kernel<T><<<grid, 128, 0, stream>>>(rows, cols, src, ldsrc, splits, splitStride, dst, lddst, tileSlots, tilesAlongRows);
 	launchCheck();
 }
 
 template <typename T>
 static void updateHGeneric(unsigned k, unsigned n, const T* G, const T* Hin, T* Hout, size_t ldh, const T* Npart, size_t ldn,
                            unsigned splits, size_t splitStride, T eps, T* tracePartials, float* HtHi, float* HtLo, size_t ldht,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const unsigned char* tileSlots) {
 	const size_t smem = (size_t)8 * k * sizeof(T);
 	allowSmem(update_h_generic<T>, smem);
 	update_h_generic<T><<<ceilDiv(n, 32), 256, smem, stream>>>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps,
-	                                                            tracePartials, HtHi, HtLo, ldht);
+	                                                            tracePartials, HtHi, HtLo, ldht, tileSlots);
 	launchCheck();
 }
 
 template <int KP>
 static void updateHReg(unsigned k, unsigned n, const float* G, const float* Hin, float* Hout, size_t ldh, const float* Npart, size_t ldn,
                        unsigned splits, size_t splitStride, float eps, float* tracePartials, float* HtHi, float* HtLo, size_t ldht,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const unsigned char* tileSlots) {
 	const size_t smem = sizeof(float) * ((size_t)KP * KP + 2 * 128 * (KP + 1));
 	allowSmem(update_h_reg<KP>, smem);
 	update_h_reg<KP><<<ceilDiv(n, 128), 128, smem, stream>>>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials,
-	                                                          HtHi, HtLo, ldht);
+	                                                          HtHi, HtLo, ldht, tileSlots);
 	launchCheck();
 }
 
 template <>
 void updateH<float>(unsigned k, unsigned n, const float* G, const float* Hin, float* Hout, size_t ldh, const float* Npart, size_t ldn,
                     unsigned splits, size_t splitStride, float eps, float* tracePartials, float* HtHi, float* HtLo, size_t ldht,
-                    cudaStream_t stream) {
-#define NMF_ARGS k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials, HtHi, HtLo, ldht, stream
+                    cudaStream_t stream, const unsigned char* tileSlots) {
+#define NMF_ARGS k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials, HtHi, HtLo, ldht, stream, tileSlots
 	if (k <= 16) updateHReg<16>(NMF_ARGS);
 	else if (k <= 32) updateHReg<32>(NMF_ARGS);
 	else if (k <= 64) updateHReg<64>(NMF_ARGS);
@@ -665,8 +675,8 @@ void updateH<float>(unsigned k, unsigned n, const float* G, const float* Hin, fl
 template <>
 void updateH<double>(unsigned k, unsigned n, const double* G, const double* Hin, double* Hout, size_t ldh, const double* Npart,
                      size_t ldn, unsigned splits, size_t splitStride, double eps, double* tracePartials, float* HtHi, float* HtLo,
-                     size_t ldht, cudaStream_t stream) {
-	updateHGeneric<double>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials, HtHi, HtLo, ldht, stream);
+                     size_t ldht, cudaStream_t stream, const unsigned char* tileSlots) {
+	updateHGeneric<double>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials, HtHi, HtLo, ldht, stream, tileSlots);
 }
 
 template <typename T>
@@ -685,35 +695,37 @@ void absInPlace(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream_t str
 
 template <int KP>
 static unsigned updateWReg(unsigned m, unsigned k, const float* B, const float* Win, float* Wout, size_t ldw, const float* Ppart,
-                           size_t ldp, unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream) {
+                           size_t ldp, unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream,
+                           const unsigned char* tileSlots) {
 	const size_t smem = sizeof(float) * ((size_t)KP * KP + 4 * KP);
 	allowSmem(update_w_reg<KP>, smem);
 	const unsigned blocks = ceilDiv(m, 128);
-	update_w_reg<KP><<<blocks, 128, smem, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials);
+	update_w_reg<KP><<<blocks, 128, smem, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots);
 	launchCheck();
 	return blocks;
 }
 
 template <>
 unsigned updateW<float>(unsigned m, unsigned k, const float* B, const float* Win, float* Wout, size_t ldw, const float* Ppart, size_t ldp,
-                        unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream) {
-#define NMF_ARGS m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, stream
+                        unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream, const unsigned char* tileSlots) {
+#define NMF_ARGS m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, stream, tileSlots
 	if (k <= 16) return updateWReg<16>(NMF_ARGS);
 	if (k <= 32) return updateWReg<32>(NMF_ARGS);
 	if (k <= 64) return updateWReg<64>(NMF_ARGS);
 	if (k <= 128) return updateWReg<128>(NMF_ARGS);
 #undef NMF_ARGS
 	const unsigned blocks = ceilDiv(m, 128);
-	update_w_generic<float><<<blocks, 128, 0, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials);
+	update_w_generic<float><<<blocks, 128, 0, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots);
 	launchCheck();
 	return blocks;
 }
 
 template <>
 unsigned updateW<double>(unsigned m, unsigned k, const double* B, const double* Win, double* Wout, size_t ldw, const double* Ppart,
-                         size_t ldp, unsigned splits, size_t splitStride, double eps, double* colSqPartials, cudaStream_t stream) {
+                         size_t ldp, unsigned splits, size_t splitStride, double eps, double* colSqPartials, cudaStream_t stream,
+                         const unsigned char* tileSlots) {
 	const unsigned blocks = ceilDiv(m, 128);
-	update_w_generic<double><<<blocks, 128, 0, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials);
+	update_w_generic<double><<<blocks, 128, 0, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots);
 	launchCheck();
 	return blocks;
 }
@@ -795,7 +807,7 @@ void splitTf32(unsigned rows, unsigned cols, const float* X, size_t ldx, float* 
 #define NMF_INSTANTIATE(T)                                                                                                             \
 	template void gemmTN<T>(unsigned, unsigned, unsigned, const T*, size_t, const T*, size_t, T*, size_t, unsigned, size_t, cudaStream_t); \
 	template void gemmNT<T>(unsigned, unsigned, unsigned, const T*, size_t, const T*, size_t, T*, size_t, unsigned, size_t, cudaStream_t); \
-	template void sumSplits<T>(unsigned, unsigned, const T*, size_t, unsigned, size_t, T*, size_t, cudaStream_t);                         \
+	template void sumSplits<T>(unsigned, unsigned, const T*, size_t, unsigned, size_t, T*, size_t, cudaStream_t, const unsigned char*, bool); \
 	template void clampNonNegative<T>(unsigned, unsigned, T*, size_t, cudaStream_t);                                                      \
 	template void absInPlace<T>(unsigned, unsigned, T*, size_t, cudaStream_t);                                                            \
 	template void finishColumnNorms<T>(unsigned, unsigned, const T*, T*, cudaStream_t);                                                   \

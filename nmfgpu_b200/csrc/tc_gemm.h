@@ -5,7 +5,7 @@
 //
 // Both stream the 4 GB matrix V exactly once per call and are HBM-bound by design (k/2 FLOP per byte
 // of V).  To stay within fp32 tolerance on TF32 tensor cores they run the 3xTF32 scheme
-//   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi,   x_hi = rn_tf32(x), x_lo = x - x_hi
+//   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo,   x_hi = rna_tf32(x), x_lo = x - x_hi
 // with the split of the big operand (V) done on the fly in registers and handed to the tensor core
 // through TENSOR MEMORY (tcgen05.mma with the A operand in TMEM), so V costs one TMA write and one
 // shared-memory read per element and nothing else.  The small operands (W, H^T) are pre-split in
@@ -19,23 +19,29 @@ namespace nmfgpu {
 namespace b200 {
 namespace tc {
 
+// One of the two products, decomposed stream-K style: the (tile, reduction-stage) space is cut into
+// equal contiguous ranges, one per CTA of a persistent grid.  A tile (128 columns of V for W^T V,
+// 128 rows of V for V H^T) that is covered by several CTAs receives one partial product per CTA, in
+// consecutive "slots" of the output; slotCount[tile] says how many.  Everything is static (a function
+// of the shape only), so the summation order is deterministic.
+struct Product {
+	unsigned tiles = 0;            // 128-row tiles of the A operand
+	unsigned stagesPerTile = 0;    // reduction stages (32 elements) per tile
+	unsigned grid = 0;             // persistent CTAs
+	unsigned maxSlots = 1;         // partial products a consumer may have to add per tile
+	unsigned char* slotCount = nullptr;   // device, [tiles]
+	alignas(64) unsigned char mapV[128];  // TMA descriptors (CUtensorMap)
+	alignas(64) unsigned char mapBhi[128];
+	alignas(64) unsigned char mapBlo[128];
+};
+
 struct Plan {
 	unsigned m = 0, n = 0, k = 0;
-	unsigned kp = 0;               // rank padded to the UMMA N granularity (16, 32, 64 or 128)
-	unsigned splitsWtV = 1;        // partial products written by gemmWtV (one per reduction slice)
-	unsigned splitsVHt = 1;
-	bool singlePass = false;       // 1xTF32 diagnostic mode
-	// work decomposition (filled by makePlan)
-	unsigned wtvTilesN = 0, wtvChunksPerSplit = 0;
-	unsigned vhtTilesM = 0, vhtChunksPerSplit = 0;
-	unsigned gridWtV = 0, gridVHt = 0;
-	// TMA descriptors (CUtensorMap, 128 bytes each, 64-byte aligned)
-	alignas(64) unsigned char mapV_wtv[128];   // V as [32 rows x 128 cols] boxes, 128B swizzle
-	alignas(64) unsigned char mapV_vht[128];   // V as [128 rows x 32 cols] boxes, no swizzle
-	alignas(64) unsigned char mapWhi[128];     // W hi/lo: [32 rows x kp cols] boxes, 128B swizzle (K-major B operand)
-	alignas(64) unsigned char mapWlo[128];
-	alignas(64) unsigned char mapHtHi[128];    // H^T hi/lo (n x k, n contiguous): [32 x kp] boxes, 128B swizzle
-	alignas(64) unsigned char mapHtLo[128];
+	unsigned kp = 0;               // rank padded to the UMMA N granularity (multiple of 16, <= 128)
+	unsigned passes = 3;           // 3 = 3xTF32, 1 = single-pass TF32 (diagnostic)
+	unsigned flushStages = 8;      // reduction stages accumulated inside the tensor core before the fp32 flush
+	Product wtv, vht;
+	~Plan();
 };
 
 // fp32 problem shapes the tensor-core path covers (others run the SIMT kernels)
@@ -44,10 +50,10 @@ bool shapeSupported(unsigned m, unsigned n, unsigned k, size_t ldV, size_t ldW);
 void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, size_t ldV, const float* Whi, const float* Wlo, size_t ldW,
               const float* HtHi, const float* HtLo, size_t ldHt, bool singlePass);
 
-// Npart + s*splitStride (k x n, leading dimension ldn) receives the partial product of reduction slice s
-void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t splitStride, cudaStream_t stream);
-// Ppart + s*splitStride (m x k, leading dimension ldp)
-void gemmVHt(const Plan& plan, float* Ppart, size_t ldp, size_t splitStride, cudaStream_t stream);
+// Npart + slot*slotStride (k x n, leading dimension ldn) receives the partial products of W^T V
+void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream);
+// Ppart + slot*slotStride (m x k, leading dimension ldp)
+void gemmVHt(const Plan& plan, float* Ppart, size_t ldp, size_t slotStride, cudaStream_t stream);
 
 // hi/lo TF32 split of H (k x n, column-major) written transposed: Ht[c * ldht + j] = H[c + j * ldh]
 void splitTransposeH(unsigned k, unsigned n, const float* H, size_t ldh, float* hi, float* lo, size_t ldht, cudaStream_t stream);
