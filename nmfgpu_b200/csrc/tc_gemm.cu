@@ -22,6 +22,7 @@
 
 #include <cuda.h>
 
+#include <cstddef>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -38,7 +39,8 @@ namespace {
 constexpr int TILE_ROWS = 128;        // A rows per tile (= TMEM lanes)
 constexpr int STAGE_K = 32;           // reduction elements per stage (128 bytes of fp32: one swizzle row)
 constexpr int V_STAGE_BYTES = TILE_ROWS * STAGE_K * 4;
-constexpr int A_SLOTS = 4;            // TMEM A operand ring (64 columns each: 32 hi + 32 lo)
+constexpr int SLOTS = 4;              // operand slots: TMEM A ring (64 columns each: 32 hi + 32 lo) + smem B ring
+constexpr int SLOTS_SHIFT = 2;
 constexpr int ACC_COLS = 128;         // TMEM columns reserved per accumulator buffer
 constexpr int A_BASE_COL = 2 * ACC_COLS;
 constexpr int NUM_THREADS = 384;
@@ -47,8 +49,8 @@ constexpr uint64_t POLICY_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t POLICY_EVICT_LAST = 0x14F0000000000000ull;
 
 template <int KPM> struct Rings;
-template <> struct Rings<64> { static constexpr int SV = 6, SB = 4; };
-template <> struct Rings<128> { static constexpr int SV = 5, SB = 3; };
+template <> struct Rings<64> { static constexpr int SV = 8; };    // V tile ring depth (16 KB each)
+template <> struct Rings<128> { static constexpr int SV = 4; };
 
 struct KParams {
 	alignas(64) CUtensorMap mapV;
@@ -128,6 +130,11 @@ __device__ __forceinline__ void tmaLoad2D(uint32_t dst, const CUtensorMap* map, 
 	    "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
 	    : "memory");
 }
+__device__ __forceinline__ bool electOne() {
+	uint32_t pred;
+	asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+	return pred != 0;
+}
 __device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcCommit(uint32_t bar) {
@@ -181,7 +188,9 @@ __device__ __forceinline__ void splitValue(float v, uint32_t& hi, uint32_t& lo) 
 }
 
 struct __align__(8) Barriers {
-	uint64_t vFull[8], vEmpty[8], bFull[4], bEmpty[4], aFull[A_SLOTS], aEmpty[A_SLOTS], accFull[2], accEmpty[2];
+	uint64_t vFull[8], vEmpty[8];          // V tile ring: TMA -> workers
+	uint64_t full[SLOTS], empty[SLOTS];    // operand slots: A (tensor memory, written by the workers) + B (shared memory, TMA) -> MMA
+	uint64_t accFull[2], accEmpty[2];      // accumulator buffers: MMA -> flushing warpgroup
 	uint32_t tmemBase;
 };
 
@@ -190,13 +199,14 @@ struct __align__(8) Barriers {
 //                 = false: V H^T (A rows are rows of V;    V tile in smem is [32 cols][128 rows], linear)
 template <int KPM, bool V_COLS_ARE_ROWS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_constant__ KParams p) {
-	constexpr int SV = Rings<KPM>::SV, SB = Rings<KPM>::SB;
+	constexpr int SV = Rings<KPM>::SV;                 // power of two
+	constexpr int SV_SHIFT = SV == 8 ? 3 : 2;
 	constexpr int B_HALF_BYTES = KPM * STAGE_K * 4;
 	extern __shared__ unsigned char smemRaw[];
 	unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~(uintptr_t)1023);
 	unsigned char* vRing = smem;
 	unsigned char* bRing = smem + SV * V_STAGE_BYTES;
-	Barriers* bars = reinterpret_cast<Barriers*>(bRing + SB * 2 * B_HALF_BYTES);
+	Barriers* bars = reinterpret_cast<Barriers*>(bRing + SLOTS * 2 * B_HALF_BYTES);
 
 	const unsigned warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 	const unsigned F = p.flushStages;
@@ -206,13 +216,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 			mbarInit(smemAddr(&bars->vFull[i]), 1);
 			mbarInit(smemAddr(&bars->vEmpty[i]), 128);
 		}
-		for (int i = 0; i < SB; ++i) {
-			mbarInit(smemAddr(&bars->bFull[i]), 1);
-			mbarInit(smemAddr(&bars->bEmpty[i]), 1);
-		}
-		for (int i = 0; i < A_SLOTS; ++i) {
-			mbarInit(smemAddr(&bars->aFull[i]), 128);
-			mbarInit(smemAddr(&bars->aEmpty[i]), 1);
+		for (int i = 0; i < SLOTS; ++i) {
+			mbarInit(smemAddr(&bars->full[i]), 128 + 1);     // 128 worker threads (A slot written) + the B producer (expect_tx)
+			mbarInit(smemAddr(&bars->empty[i]), 1);          // tcgen05.commit of the stage's MMAs
 		}
 		for (int i = 0; i < 2; ++i) {
 			mbarInit(smemAddr(&bars->accFull[i]), 1);
@@ -228,6 +234,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 	__syncthreads();
 	tcFenceAfter();
 	const uint32_t tmem = bars->tmemBase;
+	const uint32_t barBase = smemAddr(bars);
+	const uint32_t vFullBar = barBase + offsetof(Barriers, vFull), vEmptyBar = barBase + offsetof(Barriers, vEmpty);
+	const uint32_t fullBar = barBase + offsetof(Barriers, full), emptyBar = barBase + offsetof(Barriers, empty);
+	const uint32_t accFullBar = barBase + offsetof(Barriers, accFull), accEmptyBar = barBase + offsetof(Barriers, accEmpty);
 
 	if (warp == 0) {
 		// ===== V producer =====
@@ -235,34 +245,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 			SegmentWalker walk(p, blockIdx.x);
 			Segment s;
 			unsigned g = 0;
+			const uint32_t vBase = smemAddr(vRing);
 			while (walk.next(s)) {
-				for (unsigned ls = 0; ls < s.len; ++ls, ++g) {
-					const unsigned sv = g % SV;
-					mbarWait(smemAddr(&bars->vEmpty[sv]), ((g / SV) & 1) ^ 1);
-					const uint32_t full = smemAddr(&bars->vFull[sv]);
+				const int rIdx = (int)(s.tile * TILE_ROWS);
+				int kIdx = (int)(s.stage0 * STAGE_K);
+				for (unsigned ls = 0; ls < s.len; ++ls, ++g, kIdx += STAGE_K) {
+					const unsigned sv = g & (SV - 1);
+					mbarWait(vEmptyBar + sv * 8, ((g >> SV_SHIFT) & 1) ^ 1);
+					const uint32_t full = vFullBar + sv * 8;
 					mbarArriveExpectTx(full, V_STAGE_BYTES);
-					const int kIdx = (int)((s.stage0 + ls) * STAGE_K);
-					const int rIdx = (int)(s.tile * TILE_ROWS);
-					if (V_COLS_ARE_ROWS) tmaLoad2D(smemAddr(vRing + sv * V_STAGE_BYTES), &p.mapV, full, kIdx, rIdx, POLICY_EVICT_FIRST);
-					else tmaLoad2D(smemAddr(vRing + sv * V_STAGE_BYTES), &p.mapV, full, rIdx, kIdx, POLICY_EVICT_FIRST);
+					if (V_COLS_ARE_ROWS) tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, kIdx, rIdx, POLICY_EVICT_FIRST);
+					else tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, rIdx, kIdx, POLICY_EVICT_FIRST);
 				}
 			}
 		}
 	} else if (warp == 2) {
-		// ===== B producer (hi and lo tiles of W resp. H^T) =====
+		// ===== B producer (hi and lo tiles of W resp. H^T): lands on the same barrier the workers arrive on =====
 		if (lane == 0) {
 			SegmentWalker walk(p, blockIdx.x);
 			Segment s;
 			unsigned g = 0;
 			const uint32_t bytes = 2u * p.kp * STAGE_K * 4u;
+			const uint32_t bBase = smemAddr(bRing);
 			while (walk.next(s)) {
-				for (unsigned ls = 0; ls < s.len; ++ls, ++g) {
-					const unsigned sb = g % SB;
-					mbarWait(smemAddr(&bars->bEmpty[sb]), ((g / SB) & 1) ^ 1);
-					const uint32_t full = smemAddr(&bars->bFull[sb]);
+				int kIdx = (int)(s.stage0 * STAGE_K);
+				for (unsigned ls = 0; ls < s.len; ++ls, ++g, kIdx += STAGE_K) {
+					const unsigned sl = g & (SLOTS - 1);
+					mbarWait(emptyBar + sl * 8, ((g >> SLOTS_SHIFT) & 1) ^ 1);
+					const uint32_t full = fullBar + sl * 8;
 					mbarArriveExpectTx(full, bytes);
-					const int kIdx = (int)((s.stage0 + ls) * STAGE_K);
-					const uint32_t dst = smemAddr(bRing + sb * 2 * B_HALF_BYTES);
+					const uint32_t dst = bBase + sl * 2 * B_HALF_BYTES;
 					tmaLoad2D(dst, &p.mapBhi, full, kIdx, 0, POLICY_EVICT_LAST);
 					tmaLoad2D(dst + B_HALF_BYTES, &p.mapBlo, full, kIdx, 0, POLICY_EVICT_LAST);
 				}
@@ -270,45 +282,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 		}
 	} else if (warp == 1) {
 		// ===== MMA issuer =====
-		if (lane == 0) {
-			// instruction descriptor: D fp32, A/B tf32, both K-major, N = kp, M = 128
-			const uint32_t iDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((p.kp >> 3) << 17) | ((TILE_ROWS >> 4) << 24);
-			SegmentWalker walk(p, blockIdx.x);
-			Segment s;
-			unsigned g = 0, gc = 0;
-			while (walk.next(s)) {
-				unsigned inChunk = 0;
-				uint32_t acc = 0;
-				for (unsigned ls = 0; ls < s.len; ++ls, ++g) {
-					if (inChunk == 0) {
-						const unsigned b = gc & 1;
-						mbarWait(smemAddr(&bars->accEmpty[b]), ((gc >> 1) & 1) ^ 1);
-						acc = tmem + b * ACC_COLS;
-					}
-					const unsigned sa = g % A_SLOTS, sb = g % SB;
-					mbarWait(smemAddr(&bars->bFull[sb]), (g / SB) & 1);
-					mbarWait(smemAddr(&bars->aFull[sa]), (g / A_SLOTS) & 1);
-					tcFenceAfter();
-					const uint32_t aHi = tmem + A_BASE_COL + sa * 64, aLo = aHi + 32;
-					const uint32_t bHi = smemAddr(bRing + sb * 2 * B_HALF_BYTES), bLo = bHi + B_HALF_BYTES;
-#pragma unroll
-					for (int q = 0; q < STAGE_K / 8; ++q) {
-						const uint64_t dHi = smemDescSw128(bHi + q * 32), dLo = smemDescSw128(bLo + q * 32);
-						mmaTf32(acc, aHi + q * 8, dHi, iDesc, (inChunk | q) != 0);
-						if (p.passes == 3) {
-							mmaTf32(acc, aLo + q * 8, dHi, iDesc, 1);
-							mmaTf32(acc, aHi + q * 8, dLo, iDesc, 1);
-						}
-					}
-					tcCommit(smemAddr(&bars->bEmpty[sb]));
-					tcCommit(smemAddr(&bars->aEmpty[sa]));
-					++inChunk;
-					if (inChunk == F || ls + 1 == s.len) {
-						tcCommit(smemAddr(&bars->accFull[gc & 1]));
-						++gc;
-						inChunk = 0;
-					}
+		// The whole warp walks the loop convergently so that every address and descriptor lives in uniform
+		// registers; one elected lane issues the 12 MMAs of a stage back to back (a divergent single-thread
+		// loop costs ~140 cycles per MMA in R2UR traffic; this form issues at the tensor pipe's 32 cycles).
+		const bool leader = electOne();
+		// instruction descriptor: D fp32, A/B tf32, both K-major, N = kp, M = 128
+		const uint32_t iDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((p.kp >> 3) << 17) | ((TILE_ROWS >> 4) << 24);
+		const uint64_t bDesc0 = smemDescSw128(smemAddr(bRing));
+		const bool threePass = p.passes == 3;
+		SegmentWalker walk(p, blockIdx.x);
+		Segment s;
+		unsigned g = 0, gc = 0;
+		while (walk.next(s)) {
+			unsigned inChunk = 0;
+			uint32_t acc = 0;
+			for (unsigned ls = 0; ls < s.len; ++ls, ++g) {
+				if (inChunk == 0) {
+					const unsigned b = gc & 1;
+					mbarWait(accEmptyBar + b * 8, ((gc >> 1) & 1) ^ 1);
+					acc = tmem + b * ACC_COLS;
 				}
+				const unsigned sl = g & (SLOTS - 1);
+				mbarWait(fullBar + sl * 8, (g >> SLOTS_SHIFT) & 1);
+				tcFenceAfter();
+				if (leader) {
+					const uint32_t aHi = tmem + A_BASE_COL + sl * 64, aLo = aHi + 32;
+					const uint64_t dHi = bDesc0 + (uint64_t)((sl * 2 * B_HALF_BYTES) >> 4), dLo = dHi + (B_HALF_BYTES >> 4);
+					if (threePass) {
+#pragma unroll
+						for (int q = 0; q < STAGE_K / 8; ++q) {
+							mmaTf32(acc, aHi + q * 8, dHi + q * 2, iDesc, q == 0 ? (uint32_t)(inChunk != 0) : 1u);
+							mmaTf32(acc, aLo + q * 8, dHi + q * 2, iDesc, 1);
+							mmaTf32(acc, aHi + q * 8, dLo + q * 2, iDesc, 1);
+						}
+					} else {
+#pragma unroll
+						for (int q = 0; q < STAGE_K / 8; ++q) mmaTf32(acc, aHi + q * 8, dHi + q * 2, iDesc, q == 0 ? (uint32_t)(inChunk != 0) : 1u);
+					}
+					tcCommit(emptyBar + sl * 8);
+				}
+				++inChunk;
+				if (inChunk == F || ls + 1 == s.len) {
+					if (leader) tcCommit(accFullBar + (gc & 1) * 8);
+					++gc;
+					inChunk = 0;
+				}
+				__syncwarp();
 			}
 		}
 	} else if (warp >= 4) {
@@ -316,13 +335,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 		const unsigned wg = (warp - 4) / 4;                 // 0 or 1
 		const unsigned row = (warp % 4) * 32 + lane;        // A row = TMEM lane owned by this thread
 		const uint32_t laneBase = ((warp % 4) * 32) << 16;
+		const unsigned kp = p.kp;
 		float sum[KPM];
 #pragma unroll
 		for (int c = 0; c < KPM; ++c) sum[c] = 0.f;
 
 		auto split = [&](unsigned g) {
-			const unsigned sv = g % SV, sa = g % A_SLOTS;
-			mbarWait(smemAddr(&bars->vFull[sv]), (g / SV) & 1);
+			const unsigned sv = g & (SV - 1), sl = g & (SLOTS - 1);
+			mbarWait(vFullBar + sv * 8, (g >> SV_SHIFT) & 1);
 			const unsigned char* tile = vRing + sv * V_STAGE_BYTES;
 			float v[STAGE_K];
 			if (V_COLS_ARE_ROWS) {
@@ -338,59 +358,65 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 #pragma unroll
 				for (int j = 0; j < STAGE_K; ++j) v[j] = base[j * TILE_ROWS];
 			}
-			mbarArrive(smemAddr(&bars->vEmpty[sv]));           // the tile is in registers: release the slot
-			mbarWait(smemAddr(&bars->aEmpty[sa]), ((g / A_SLOTS) & 1) ^ 1);
+			mbarArrive(vEmptyBar + sv * 8);                     // the tile is in registers: release the slot
+			uint32_t hi[STAGE_K], lo[STAGE_K];
+#pragma unroll
+			for (int e = 0; e < STAGE_K; ++e) splitValue(v[e], hi[e], lo[e]);
+			mbarWait(emptyBar + sl * 8, ((g >> SLOTS_SHIFT) & 1) ^ 1);
 			tcFenceAfter();
-			const uint32_t aSlot = tmem + laneBase + A_BASE_COL + sa * 64;
-#pragma unroll
-			for (int h = 0; h < 2; ++h) {
-				uint32_t hi[16], lo[16];
-#pragma unroll
-				for (int e = 0; e < 16; ++e) splitValue(v[16 * h + e], hi[e], lo[e]);
-				tmemStore16(aSlot + 16 * h, hi);
-				tmemStore16(aSlot + 32 + 16 * h, lo);
-			}
+			const uint32_t aSlot = tmem + laneBase + A_BASE_COL + sl * 64;
+			tmemStore16(aSlot, hi);
+			tmemStore16(aSlot + 16, hi + 16);
+			tmemStore16(aSlot + 32, lo);
+			tmemStore16(aSlot + 48, lo + 16);
 			tmemWaitStore();
 			tcFenceBefore();
-			mbarArrive(smemAddr(&bars->aFull[sa]));
+			mbarArrive(fullBar + sl * 8);
 		};
 
 		auto flush = [&](unsigned gc) {
 			const unsigned b = gc & 1;
-			mbarWait(smemAddr(&bars->accFull[b]), (gc >> 1) & 1);
+			mbarWait(accFullBar + b * 8, (gc >> 1) & 1);
 			tcFenceAfter();
 			const uint32_t acc = tmem + laneBase + b * ACC_COLS;
 #pragma unroll
-			for (int q = 0; q < KPM / 16; ++q) {
-				if (q * 16 < (int)p.kp) {
-					uint32_t r[16];
-					tmemLoad16(acc + q * 16, r);
+			for (int q = 0; q < KPM / 32; ++q) {
+				if (q * 32 < (int)kp) {
+					uint32_t r[32];
+					tmemLoad16(acc + q * 32, r);
+					if (q * 32 + 16 < (int)kp) tmemLoad16(acc + q * 32 + 16, r + 16);
 					tmemWaitLoad();
 #pragma unroll
-					for (int e = 0; e < 16; ++e) sum[q * 16 + e] += __uint_as_float(r[e]);
+					for (int e = 0; e < 16; ++e) sum[q * 32 + e] += __uint_as_float(r[e]);
+					if (q * 32 + 16 < (int)kp) {
+#pragma unroll
+						for (int e = 16; e < 32; ++e) sum[q * 32 + e] += __uint_as_float(r[e]);
+					}
 				}
 			}
 			tcFenceBefore();
-			mbarArrive(smemAddr(&bars->accEmpty[b]));
+			mbarArrive(accEmptyBar + b * 8);
 		};
 
 		SegmentWalker walk(p, blockIdx.x);
 		Segment s;
-		unsigned g = 0, gcBase = 0;
+		unsigned gBase = 0, gcBase = 0;
 		while (walk.next(s)) {
+			// chunk c of this segment covers local stages [c F, (c+1) F); global chunk gcBase + c is flushed by
+			// warpgroup (gcBase + c) & 1 once that warpgroup has split past the chunk's end
 			const unsigned nChunks = (s.len + F - 1) / F;
-			unsigned flushed = 0;
-			for (unsigned ls = 0; ls < s.len; ++ls, ++g) {
-				if ((g & 1) == wg) split(g);
-				while (flushed < nChunks) {
-					const unsigned chunkEnd = min((flushed + 1) * F, s.len) - 1;
-					if (chunkEnd + FLUSH_LOOKAHEAD > ls) break;
-					if (((gcBase + flushed) & 1) == wg) flush(gcBase + flushed);
-					++flushed;
+			unsigned nextChunk = (gcBase & 1) == wg ? 0u : 1u;          // my first chunk of this segment
+			unsigned flushAt = (nextChunk + 1) * F + FLUSH_LOOKAHEAD;    // local stage index from which it may be flushed
+			for (unsigned ls = (gBase & 1) == wg ? 0u : 1u; ls < s.len; ls += 2) {
+				split(gBase + ls);
+				if (ls >= flushAt && nextChunk + 1 < nChunks) {
+					flush(gcBase + nextChunk);
+					nextChunk += 2;
+					flushAt += 2 * F;
 				}
 			}
-			for (; flushed < nChunks; ++flushed)
-				if (((gcBase + flushed) & 1) == wg) flush(gcBase + flushed);
+			for (; nextChunk < nChunks; nextChunk += 2) flush(gcBase + nextChunk);
+			gBase += s.len;
 			gcBase += nChunks;
 
 			// ---- output of this segment's partial product: warpgroup 0 stores, warpgroup 1 adds its share
@@ -402,7 +428,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 						float4* dst = reinterpret_cast<float4*>(out + (size_t)r * p.ldOut);     // column r of N: kp contiguous values
 #pragma unroll
 						for (int c = 0; c < KPM / 4; ++c) {
-							if (c * 4 < (int)p.kp) {
+							if (c * 4 < (int)kp) {
 								float4 x = make_float4(sum[4 * c], sum[4 * c + 1], sum[4 * c + 2], sum[4 * c + 3]);
 								if (phase == 1) {
 									const float4 y = dst[c];
@@ -438,7 +464,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 
 template <int KPM>
 size_t smemBytes() {
-	return 1024 + (size_t)Rings<KPM>::SV * V_STAGE_BYTES + (size_t)Rings<KPM>::SB * 2 * KPM * STAGE_K * 4 + sizeof(Barriers);
+	return 1024 + (size_t)Rings<KPM>::SV * V_STAGE_BYTES + (size_t)SLOTS * 2 * KPM * STAGE_K * 4 + sizeof(Barriers);
 }
 
 // ---- H -> H^T hi/lo ----------------------------------------------------------------------------------
