@@ -1,29 +1,33 @@
 // tc_gemm.cu -- W^T V and V H^T on the Blackwell tensor cores (tcgen05 / TMEM / TMA), 3xTF32.
 //
-// Both products are the same machine:   D[128 x kp] += A[128 x 32] * B[kp x 32]^T   per reduction stage,
-//   W^T V :  A rows = 128 columns of V, reduction over the rows of V (contiguous in memory),  B = W      (hi, lo)
-//   V H^T :  A rows = 128 rows of V,    reduction over the columns of V,                     B = H^T    (hi, lo)
-// computing N^T resp. N2 so that the big operand V is always the 128-row A operand (UMMA M = 128 runs
-// the tensor pipe at full rate, M = 64 at half) and the rank k is the UMMA N dimension.
+// Both products are the same machine:   D[256 x kp] += A[256 x 32] * B[kp x 32]^T   per reduction stage,
+//   W^T V :  A rows = 256 columns of V, reduction over the rows of V (contiguous in memory),  B = W      (hi, lo)
+//   V H^T :  A rows = 256 rows of V,    reduction over the columns of V,                     B = H^T    (hi, lo)
+// computing N^T resp. N2 so that the big operand V is always the A operand in two 128-row UMMA tiles
+// (M = 128 runs the tensor pipe at full rate, M = 64 at half) and the rank k is the UMMA N dimension.
+// Two A tiles share every B tile: B comes out of L2, and its traffic and its latency -- not HBM -- bound
+// the one-tile version of this kernel (profiles/r01_notes.md).
 //
 // Kernel anatomy (one persistent CTA per SM, 384 threads, stream-K work split, see tc_gemm.h):
-//   warp 0      TMA producer of the V tiles (16 KB per stage, EVICT_FIRST: V is streamed once per product)
+//   warp 0      TMA producer of the V tiles (16 KB each, two per stage, EVICT_FIRST: V is streamed once per product)
 //   warp 2      TMEM allocation, then TMA producer of the B tiles (hi and lo, kp x 32 each, EVICT_LAST)
-//   warp 1      MMA issuer: per stage 4 k-steps x {A_hi B_hi, A_lo B_hi, A_hi B_lo}, tcgen05.mma kind::tf32 with
+//   warps 1, 3  MMA issuers, one per A tile: 4 k-steps x {A_hi B_hi, A_lo B_hi, A_hi B_lo}, tcgen05.mma kind::tf32 with
 //               A in TENSOR MEMORY and B in shared memory (128B swizzle); accumulators in TMEM
-//   warps 4-7, 8-11   two worker warpgroups taking alternate stages: read the fp32 V tile from shared memory
-//               (each thread owns one A row = one TMEM lane), split every value into TF32 hi/lo in registers
-//               and tcgen05.st both halves into an A slot of TMEM.  V is never written back anywhere.
-// The tensor core accumulates only `flushStages` stages at a time; the workers then tcgen05.ld the
-// accumulator and add it to fp32 running sums in registers with round-to-nearest (two accumulator
-// buffers, one per warpgroup, so the flush overlaps the next chunk's MMAs).  That keeps the rounding of
-// a 100 000-term reduction at fp32 level regardless of how the tensor core rounds its accumulator.
+//   warps 4-7, 8-11   two worker warpgroups, one per A tile: read the fp32 V tile from shared memory (each
+//               thread owns one A row = one TMEM lane), split every value into TF32 hi/lo in registers and
+//               tcgen05.st both halves into an A slot of TMEM.  V is never written back anywhere.
+// The tensor core accumulates only `flushStages` stages at a time; each warpgroup then tcgen05.ld's its
+// tile's accumulator and adds it to fp32 running sums in registers with round-to-nearest (double-buffered
+// accumulators for kp <= 64, so the flush overlaps the next chunk's MMAs).  The tensor core truncates its
+// fp32 accumulator after every MMA (measured: bias of -2.4e-7 per accumulated stage), so a 100 000-term
+// reduction kept in TMEM would be off by 4e-4; chunked it stays at fp32 level.
 #include "tc_gemm.h"
 
 #include <cuda.h>
 
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -39,24 +43,41 @@ namespace {
 constexpr int TILE_ROWS = 128;        // A rows per tile (= TMEM lanes)
 constexpr int STAGE_K = 32;           // reduction elements per stage (128 bytes of fp32: one swizzle row)
 constexpr int V_STAGE_BYTES = TILE_ROWS * STAGE_K * 4;
-constexpr int SLOTS = 4;              // operand slots: TMEM A ring (64 columns each: 32 hi + 32 lo) + smem B ring
+constexpr int PAIR_ROWS = 2 * TILE_ROWS;   // A rows per stream-K tile: two UMMA tiles that share their B tiles
+constexpr int SLOTS = 4;              // TMEM A operand ring, in tiles (64 columns each: 32 hi + 32 lo)
 constexpr int SLOTS_SHIFT = 2;
-constexpr int ACC_COLS = 128;         // TMEM columns reserved per accumulator buffer
-constexpr int A_BASE_COL = 2 * ACC_COLS;
+constexpr int SV = 8;                 // shared-memory ring of V tiles (16 KB each): 4 stages of 2 tiles
+constexpr int SV_SHIFT = 3;
+constexpr int A_BASE_COL = 256;       // TMEM columns [0, 256): accumulators, [256, 512): A slots
 constexpr int NUM_THREADS = 384;
-constexpr int FLUSH_LOOKAHEAD = 2;    // stages a worker keeps splitting past a chunk end before it flushes
+constexpr int HELPER_REGS = 72, WORKER_REGS = 216;   // 128 * 72 + 256 * 216 = 64512 <= 384 * 168
 constexpr uint64_t POLICY_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t POLICY_EVICT_LAST = 0x14F0000000000000ull;
 
 template <int KPM> struct Rings;
-template <> struct Rings<64> { static constexpr int SV = 8; };    // V tile ring depth (16 KB each)
-template <> struct Rings<128> { static constexpr int SV = 4; };
+// shared-memory rings: SV tiles of V (16 KB each) and SB tile pairs of B (hi + lo, KPM x 32 fp32 each).  Both
+// must cover the loaded TMA latency (~2700 cycles measured under full HBM traffic) at one stage per 400-650 cycles.
+// SB: shared-memory ring of B tile pairs (hi + lo, KPM x 32 fp32 each); ACC_BUFS: accumulator buffers per A tile
+template <> struct Rings<64> { static constexpr int SB = 4, ACC_BUFS = 2; };
+template <> struct Rings<128> { static constexpr int SB = 2, ACC_BUFS = 1; };
+
+// position in a ring of arbitrary depth: slot index plus the parity of the number of completed laps
+struct RingPos {
+	unsigned idx = 0, lap = 0;
+	__device__ __forceinline__ void advance(unsigned depth) {
+		if (++idx == depth) {
+			idx = 0;
+			lap ^= 1;
+		}
+	}
+};
 
 struct KParams {
 	alignas(64) CUtensorMap mapV;
 	alignas(64) CUtensorMap mapBhi;
 	alignas(64) CUtensorMap mapBlo;
 	float* out;
+	unsigned long long* trace;   // optional timeline of CTA 0 (NMFGPU_TC_TRACE), nullptr otherwise
 	unsigned long long ldOut, slotStride, units;
 	unsigned rowsA, k, kp, tiles, stagesPerTile, flushStages, passes, grid;
 };
@@ -187,26 +208,33 @@ __device__ __forceinline__ void splitValue(float v, uint32_t& hi, uint32_t& lo) 
 	lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
+constexpr unsigned TRACE_STAGES = 512, TRACE_EVENTS = 16;
+__device__ __forceinline__ void traceEvent(unsigned long long* trace, unsigned g, unsigned ev) {
+	if (trace != nullptr && blockIdx.x == 0 && g < TRACE_STAGES) trace[g * TRACE_EVENTS + ev] = clock64();
+}
+
 struct __align__(8) Barriers {
-	uint64_t vFull[8], vEmpty[8];          // V tile ring: TMA -> workers
-	uint64_t full[SLOTS], empty[SLOTS];    // operand slots: A (tensor memory, written by the workers) + B (shared memory, TMA) -> MMA
-	uint64_t accFull[2], accEmpty[2];      // accumulator buffers: MMA -> flushing warpgroup
+	uint64_t vFull[SV], vEmpty[SV];        // V tile ring: TMA -> workers
+	uint64_t bFull[4], bEmpty[4];          // B tile ring: TMA -> MMA
+	uint64_t full[SLOTS], empty[SLOTS];    // A operand slots in tensor memory: workers -> MMA
+	uint64_t accFull[2], accEmpty[2];      // accumulator buffers: MMA -> workers
 	uint32_t tmemBase;
 };
 
 // ---- the kernel ----------------------------------------------------------------------------------------
 // V_COLS_ARE_ROWS = true : W^T V (A rows are columns of V; V tile in smem is [128 cols][32 rows], 128B swizzle)
 //                 = false: V H^T (A rows are rows of V;    V tile in smem is [32 cols][128 rows], linear)
+// Counters: g = stage of this CTA (a stage = 32 reduction elements of one 256-row pair tile), tile step
+// t = 2 g + w for the A tile w of that stage; V ring slot = t mod 8, A slot = t mod 4, B slot = g mod SB.
 template <int KPM, bool V_COLS_ARE_ROWS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_constant__ KParams p) {
-	constexpr int SV = Rings<KPM>::SV;                 // power of two
-	constexpr int SV_SHIFT = SV == 8 ? 3 : 2;
+	constexpr int SB = Rings<KPM>::SB, ACC_BUFS = Rings<KPM>::ACC_BUFS;
 	constexpr int B_HALF_BYTES = KPM * STAGE_K * 4;
 	extern __shared__ unsigned char smemRaw[];
 	unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~(uintptr_t)1023);
 	unsigned char* vRing = smem;
 	unsigned char* bRing = smem + SV * V_STAGE_BYTES;
-	Barriers* bars = reinterpret_cast<Barriers*>(bRing + SLOTS * 2 * B_HALF_BYTES);
+	Barriers* bars = reinterpret_cast<Barriers*>(bRing + SB * 2 * B_HALF_BYTES);
 
 	const unsigned warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 	const unsigned F = p.flushStages;
@@ -214,15 +242,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 	if (threadIdx.x == 0) {
 		for (int i = 0; i < SV; ++i) {
 			mbarInit(smemAddr(&bars->vFull[i]), 1);
-			mbarInit(smemAddr(&bars->vEmpty[i]), 128);
+			mbarInit(smemAddr(&bars->vEmpty[i]), 4);         // one arrival per warp of the warpgroup that read the tile
+		}
+		for (int i = 0; i < SB; ++i) {
+			mbarInit(smemAddr(&bars->bFull[i]), 1);
+			mbarInit(smemAddr(&bars->bEmpty[i]), 2);         // tcgen05.commit of both issuers' MMAs of the stage
 		}
 		for (int i = 0; i < SLOTS; ++i) {
-			mbarInit(smemAddr(&bars->full[i]), 128 + 1);     // 128 worker threads (A slot written) + the B producer (expect_tx)
-			mbarInit(smemAddr(&bars->empty[i]), 1);          // tcgen05.commit of the stage's MMAs
+			mbarInit(smemAddr(&bars->full[i]), 4);           // one arrival per warp once its 32 lanes of the A slot are written
+			mbarInit(smemAddr(&bars->empty[i]), 1);          // tcgen05.commit of the tile's MMAs
 		}
 		for (int i = 0; i < 2; ++i) {
-			mbarInit(smemAddr(&bars->accFull[i]), 1);
-			mbarInit(smemAddr(&bars->accEmpty[i]), 128);
+			mbarInit(smemAddr(&bars->accFull[i]), 2);        // tcgen05.commit of both issuers' last MMAs of the chunk
+			mbarInit(smemAddr(&bars->accEmpty[i]), 8);       // the 8 worker warps have read their tiles' accumulators
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -236,79 +268,106 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 	const uint32_t tmem = bars->tmemBase;
 	const uint32_t barBase = smemAddr(bars);
 	const uint32_t vFullBar = barBase + offsetof(Barriers, vFull), vEmptyBar = barBase + offsetof(Barriers, vEmpty);
+	const uint32_t bFullBar = barBase + offsetof(Barriers, bFull), bEmptyBar = barBase + offsetof(Barriers, bEmpty);
 	const uint32_t fullBar = barBase + offsetof(Barriers, full), emptyBar = barBase + offsetof(Barriers, empty);
 	const uint32_t accFullBar = barBase + offsetof(Barriers, accFull), accEmptyBar = barBase + offsetof(Barriers, accEmpty);
 
+	// register budget: 384 threads x 168; the four helper warps keep HELPER_REGS each and hand the rest to the workers
 	if (warp == 0) {
 		// ===== V producer =====
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS));
 		if (lane == 0) {
 			SegmentWalker walk(p, blockIdx.x);
 			Segment s;
-			unsigned g = 0;
+			unsigned t = 0;
 			const uint32_t vBase = smemAddr(vRing);
 			while (walk.next(s)) {
-				const int rIdx = (int)(s.tile * TILE_ROWS);
+				const int rIdx = (int)(s.tile * PAIR_ROWS);
 				int kIdx = (int)(s.stage0 * STAGE_K);
-				for (unsigned ls = 0; ls < s.len; ++ls, ++g, kIdx += STAGE_K) {
-					const unsigned sv = g & (SV - 1);
-					mbarWait(vEmptyBar + sv * 8, ((g >> SV_SHIFT) & 1) ^ 1);
-					const uint32_t full = vFullBar + sv * 8;
-					mbarArriveExpectTx(full, V_STAGE_BYTES);
-					if (V_COLS_ARE_ROWS) tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, kIdx, rIdx, POLICY_EVICT_FIRST);
-					else tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, rIdx, kIdx, POLICY_EVICT_FIRST);
+				for (unsigned ls = 0; ls < s.len; ++ls, kIdx += STAGE_K) {
+#pragma unroll
+					for (int w = 0; w < 2; ++w, ++t) {
+						const unsigned sv = t & (SV - 1);
+						mbarWait(vEmptyBar + sv * 8, ((t >> SV_SHIFT) & 1) ^ 1);
+						if (w == 0) traceEvent(p.trace, t >> 1, 8);
+						const uint32_t full = vFullBar + sv * 8;
+						if (p.passes & 0x2000) {
+							mbarArrive(full);
+							continue;
+						}
+						mbarArriveExpectTx(full, V_STAGE_BYTES);
+						if (V_COLS_ARE_ROWS) tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, kIdx, rIdx + w * TILE_ROWS, POLICY_EVICT_FIRST);
+						else tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, rIdx + w * TILE_ROWS, kIdx, POLICY_EVICT_FIRST);
+					}
 				}
 			}
 		}
 	} else if (warp == 2) {
-		// ===== B producer (hi and lo tiles of W resp. H^T): lands on the same barrier the workers arrive on =====
+		// ===== B producer (hi and lo tiles of W resp. H^T) =====
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS));
 		if (lane == 0) {
 			SegmentWalker walk(p, blockIdx.x);
 			Segment s;
+			RingPos b;
 			unsigned g = 0;
 			const uint32_t bytes = 2u * p.kp * STAGE_K * 4u;
 			const uint32_t bBase = smemAddr(bRing);
 			while (walk.next(s)) {
 				int kIdx = (int)(s.stage0 * STAGE_K);
-				for (unsigned ls = 0; ls < s.len; ++ls, ++g, kIdx += STAGE_K) {
-					const unsigned sl = g & (SLOTS - 1);
-					mbarWait(emptyBar + sl * 8, ((g >> SLOTS_SHIFT) & 1) ^ 1);
-					const uint32_t full = fullBar + sl * 8;
+				for (unsigned ls = 0; ls < s.len; ++ls, kIdx += STAGE_K, b.advance(SB), ++g) {
+					mbarWait(bEmptyBar + b.idx * 8, b.lap ^ 1);
+					traceEvent(p.trace, g, 7);
+					const uint32_t full = bFullBar + b.idx * 8;
+					if (p.passes & 0x1000) {
+						mbarArrive(full);
+						continue;
+					}
 					mbarArriveExpectTx(full, bytes);
-					const uint32_t dst = bBase + sl * 2 * B_HALF_BYTES;
+					const uint32_t dst = bBase + b.idx * 2 * B_HALF_BYTES;
 					tmaLoad2D(dst, &p.mapBhi, full, kIdx, 0, POLICY_EVICT_LAST);
 					tmaLoad2D(dst + B_HALF_BYTES, &p.mapBlo, full, kIdx, 0, POLICY_EVICT_LAST);
 				}
 			}
 		}
-	} else if (warp == 1) {
-		// ===== MMA issuer =====
-		// The whole warp walks the loop convergently so that every address and descriptor lives in uniform
-		// registers; one elected lane issues the 12 MMAs of a stage back to back (a divergent single-thread
-		// loop costs ~140 cycles per MMA in R2UR traffic; this form issues at the tensor pipe's 32 cycles).
+	} else if (warp == 1 || warp == 3) {
+		// ===== MMA issuers: warp 1 feeds A tile 0 of every stage, warp 3 A tile 1 (separate accumulators) =====
+		// Each warp walks its loop convergently so that every address and descriptor lives in uniform registers
+		// (a divergent single-thread loop costs ~140 cycles per MMA in R2UR traffic); one elected lane issues the
+		// 12 MMAs of a tile back to back.  Issuing blocks for about as long as the MMAs execute and every barrier
+		// probe costs ~100 cycles, so one issuer leaves the tensor pipe idle during its waits (measured: 2000
+		// cycles per stage for 768 cycles of MMA); two issuers cover each other's waits.
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS));
+		const unsigned w = warp == 1 ? 0u : 1u;
 		const bool leader = electOne();
 		// instruction descriptor: D fp32, A/B tf32, both K-major, N = kp, M = 128
 		const uint32_t iDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((p.kp >> 3) << 17) | ((TILE_ROWS >> 4) << 24);
 		const uint64_t bDesc0 = smemDescSw128(smemAddr(bRing));
-		const bool threePass = p.passes == 3;
+		const bool threePass = (p.passes & 0xFF) == 3;
+		const bool skipMma = (p.passes & 0x100) != 0;
+		const bool tracing = leader && w == 0;
 		SegmentWalker walk(p, blockIdx.x);
 		Segment s;
 		unsigned g = 0, gc = 0;
+		RingPos b;
 		while (walk.next(s)) {
-			unsigned inChunk = 0;
-			uint32_t acc = 0;
-			for (unsigned ls = 0; ls < s.len; ++ls, ++g) {
+			unsigned inChunk = 0, buf = 0;
+			for (unsigned ls = 0; ls < s.len; ++ls, ++g, b.advance(SB)) {
 				if (inChunk == 0) {
-					const unsigned b = gc & 1;
-					mbarWait(accEmptyBar + b * 8, ((gc >> 1) & 1) ^ 1);
-					acc = tmem + b * ACC_COLS;
+					buf = gc % ACC_BUFS;
+					mbarWait(accEmptyBar + buf * 8, (((gc / ACC_BUFS) & 1) ^ 1));
 				}
-				const unsigned sl = g & (SLOTS - 1);
-				mbarWait(fullBar + sl * 8, (g >> SLOTS_SHIFT) & 1);
+				const unsigned t = 2 * g + w, sl = t & (SLOTS - 1);
+				mbarWait(bFullBar + b.idx * 8, b.lap);
+				if (tracing) traceEvent(p.trace, g, 6);
+				mbarWait(fullBar + sl * 8, (t >> SLOTS_SHIFT) & 1);
 				tcFenceAfter();
 				if (leader) {
+					if (tracing) traceEvent(p.trace, g, 4);
+					const uint64_t dHi = bDesc0 + (uint64_t)((b.idx * 2 * B_HALF_BYTES) >> 4), dLo = dHi + (B_HALF_BYTES >> 4);
+					const uint32_t acc = tmem + (w * ACC_BUFS + buf) * KPM;
 					const uint32_t aHi = tmem + A_BASE_COL + sl * 64, aLo = aHi + 32;
-					const uint64_t dHi = bDesc0 + (uint64_t)((sl * 2 * B_HALF_BYTES) >> 4), dLo = dHi + (B_HALF_BYTES >> 4);
-					if (threePass) {
+					if (skipMma) {
+					} else if (threePass) {
 #pragma unroll
 						for (int q = 0; q < STAGE_K / 8; ++q) {
 							mmaTf32(acc, aHi + q * 8, dHi + q * 2, iDesc, q == 0 ? (uint32_t)(inChunk != 0) : 1u);
@@ -320,10 +379,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 						for (int q = 0; q < STAGE_K / 8; ++q) mmaTf32(acc, aHi + q * 8, dHi + q * 2, iDesc, q == 0 ? (uint32_t)(inChunk != 0) : 1u);
 					}
 					tcCommit(emptyBar + sl * 8);
+					tcCommit(bEmptyBar + b.idx * 8);
+					if (tracing) traceEvent(p.trace, g, 5);
 				}
 				++inChunk;
 				if (inChunk == F || ls + 1 == s.len) {
-					if (leader) tcCommit(accFullBar + (gc & 1) * 8);
+					if (leader) tcCommit(accFullBar + buf * 8);
 					++gc;
 					inChunk = 0;
 				}
@@ -332,20 +393,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 		}
 	} else if (warp >= 4) {
 		// ===== workers: V tile -> TF32 hi/lo -> TMEM A slot; accumulator flush; output =====
-		const unsigned wg = (warp - 4) / 4;                 // 0 or 1
+		asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WORKER_REGS));
+		const unsigned wg = (warp - 4) / 4;                 // 0 or 1: the A tile of every stage this warpgroup owns
 		const unsigned row = (warp % 4) * 32 + lane;        // A row = TMEM lane owned by this thread
 		const uint32_t laneBase = ((warp % 4) * 32) << 16;
 		const unsigned kp = p.kp;
+		const bool skipStore = (p.passes & 0x200) != 0, skipRead = (p.passes & 0x400) != 0, skipFlush = (p.passes & 0x800) != 0;
+		const bool tracing = row == 1 && wg == 0;   // not lane 0: its mbarrier arrivals would wait for the trace stores
 		float sum[KPM];
 #pragma unroll
 		for (int c = 0; c < KPM; ++c) sum[c] = 0.f;
 
-		auto split = [&](unsigned g) {
-			const unsigned sv = g & (SV - 1), sl = g & (SLOTS - 1);
-			mbarWait(vFullBar + sv * 8, (g >> SV_SHIFT) & 1);
+		// The worker loop is software pipelined: while the tcgen05.st of tile t drain, the V tile of this
+		// warpgroup's next stage is already read from shared memory into v[], so neither the shared-memory
+		// latency nor the TMEM store latency sits on the per-tile critical path.
+		float v[STAGE_K];
+		auto loadTile = [&](unsigned g) {
+			const unsigned t = 2 * g + wg, sv = t & (SV - 1);
+			mbarWait(vFullBar + sv * 8, (t >> SV_SHIFT) & 1);
+			if (tracing) traceEvent(p.trace, g, 0);
 			const unsigned char* tile = vRing + sv * V_STAGE_BYTES;
-			float v[STAGE_K];
-			if (V_COLS_ARE_ROWS) {
+			if (skipRead) {
+#pragma unroll
+				for (int j = 0; j < STAGE_K; ++j) v[j] = 1.f;
+			} else if (V_COLS_ARE_ROWS) {
 				// row `row` of the [128][32] tile; 16-byte chunk c lives at chunk c ^ (row & 7)
 				const unsigned char* base = tile + row * 128;
 #pragma unroll
@@ -358,30 +429,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 #pragma unroll
 				for (int j = 0; j < STAGE_K; ++j) v[j] = base[j * TILE_ROWS];
 			}
-			mbarArrive(vEmptyBar + sv * 8);                     // the tile is in registers: release the slot
+			// the tile is in registers: release the slot (one arrival per warp: 128 per-thread arrivals on one
+			// mbarrier serialise in the barrier unit and delay the TMA completions that share it)
+			if (tracing) traceEvent(p.trace, g, 12);
+			__syncwarp();
+			if (lane == 0) mbarArrive(vEmptyBar + sv * 8);
+			if (tracing) traceEvent(p.trace, g, 13);
+		};
+		// split v[] (tile of stage g), store it to its A slot, prefetch the tile of stage g + 1, publish the slot
+		auto splitAndStore = [&](unsigned g, bool prefetchNext) {
+			const unsigned t = 2 * g + wg, sl = t & (SLOTS - 1);
 			uint32_t hi[STAGE_K], lo[STAGE_K];
 #pragma unroll
 			for (int e = 0; e < STAGE_K; ++e) splitValue(v[e], hi[e], lo[e]);
-			mbarWait(emptyBar + sl * 8, ((g >> SLOTS_SHIFT) & 1) ^ 1);
+			if (tracing) traceEvent(p.trace, g, 1);
+			mbarWait(emptyBar + sl * 8, ((t >> SLOTS_SHIFT) & 1) ^ 1);
 			tcFenceAfter();
+			if (tracing) traceEvent(p.trace, g, 2);
 			const uint32_t aSlot = tmem + laneBase + A_BASE_COL + sl * 64;
-			tmemStore16(aSlot, hi);
-			tmemStore16(aSlot + 16, hi + 16);
-			tmemStore16(aSlot + 32, lo);
-			tmemStore16(aSlot + 48, lo + 16);
-			tmemWaitStore();
+			if (!skipStore) {
+				tmemStore16(aSlot, hi);
+				tmemStore16(aSlot + 16, hi + 16);
+				tmemStore16(aSlot + 32, lo);
+				tmemStore16(aSlot + 48, lo + 16);
+			}
+			if (tracing) traceEvent(p.trace, g, 9);
+			if (prefetchNext) loadTile(g + 1);
+			if (tracing) traceEvent(p.trace, g, 10);
+			if (!skipStore) tmemWaitStore();
+			if (tracing) traceEvent(p.trace, g, 11);
 			tcFenceBefore();
-			mbarArrive(fullBar + sl * 8);
+			__syncwarp();
+			if (lane == 0) mbarArrive(fullBar + sl * 8);
+			if (tracing) traceEvent(p.trace, g, 3);
 		};
 
 		auto flush = [&](unsigned gc) {
-			const unsigned b = gc & 1;
-			mbarWait(accFullBar + b * 8, (gc >> 1) & 1);
+			const unsigned buf = gc % ACC_BUFS;
+			mbarWait(accFullBar + buf * 8, (gc / ACC_BUFS) & 1);
 			tcFenceAfter();
-			const uint32_t acc = tmem + laneBase + b * ACC_COLS;
+			const uint32_t acc = tmem + laneBase + (wg * ACC_BUFS + buf) * KPM;
 #pragma unroll
 			for (int q = 0; q < KPM / 32; ++q) {
-				if (q * 32 < (int)kp) {
+				if (q * 32 < (int)kp && !skipFlush) {
 					uint32_t r[32];
 					tmemLoad16(acc + q * 32, r);
 					if (q * 32 + 16 < (int)kp) tmemLoad16(acc + q * 32 + 16, r + 16);
@@ -395,59 +485,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 				}
 			}
 			tcFenceBefore();
-			mbarArrive(accEmptyBar + b * 8);
+			__syncwarp();
+			if (lane == 0) mbarArrive(accEmptyBar + buf * 8);
 		};
 
 		SegmentWalker walk(p, blockIdx.x);
 		Segment s;
 		unsigned gBase = 0, gcBase = 0;
+		const unsigned totalStages = (unsigned)(walk.uEnd - walk.u);
+		if (totalStages > 0) loadTile(0);
 		while (walk.next(s)) {
-			// chunk c of this segment covers local stages [c F, (c+1) F); global chunk gcBase + c is flushed by
-			// warpgroup (gcBase + c) & 1 once that warpgroup has split past the chunk's end
+			// chunk c of this segment covers local stages [c F, (c+1) F); both warpgroups flush every chunk
+			// (each its own tile) once they have split LOOKAHEAD stages past the chunk's end
+			// The A ring holds two stages, so a worker can get at most two stages past a chunk end while the MMA
+			// warp waits for a single-buffered accumulator: the look-ahead must stay below that or both sides block.
+			constexpr unsigned LOOKAHEAD = ACC_BUFS == 2 ? 2 : 1;
 			const unsigned nChunks = (s.len + F - 1) / F;
-			unsigned nextChunk = (gcBase & 1) == wg ? 0u : 1u;          // my first chunk of this segment
-			unsigned flushAt = (nextChunk + 1) * F + FLUSH_LOOKAHEAD;    // local stage index from which it may be flushed
-			for (unsigned ls = (gBase & 1) == wg ? 0u : 1u; ls < s.len; ls += 2) {
-				split(gBase + ls);
+			unsigned nextChunk = 0;
+			unsigned flushAt = F - 1 + LOOKAHEAD;
+			for (unsigned ls = 0; ls < s.len; ++ls) {
+				splitAndStore(gBase + ls, gBase + ls + 1 < totalStages);
 				if (ls >= flushAt && nextChunk + 1 < nChunks) {
 					flush(gcBase + nextChunk);
-					nextChunk += 2;
-					flushAt += 2 * F;
+					++nextChunk;
+					flushAt += F;
 				}
 			}
-			for (; nextChunk < nChunks; nextChunk += 2) flush(gcBase + nextChunk);
+			for (; nextChunk < nChunks; ++nextChunk) flush(gcBase + nextChunk);
 			gBase += s.len;
 			gcBase += nChunks;
 
-			// ---- output of this segment's partial product: warpgroup 0 stores, warpgroup 1 adds its share
+			// ---- output of this segment's partial product: every warpgroup owns the rows of its tile
 			float* out = p.out + (size_t)s.slot * p.slotStride;
-			const unsigned r = s.tile * TILE_ROWS + row;
-			for (unsigned phase = 0; phase < 2; ++phase) {
-				if (phase == wg && r < p.rowsA) {
-					if (V_COLS_ARE_ROWS) {
-						float4* dst = reinterpret_cast<float4*>(out + (size_t)r * p.ldOut);     // column r of N: kp contiguous values
+			const unsigned r = s.tile * PAIR_ROWS + wg * TILE_ROWS + row;
+			if (r < p.rowsA) {
+				if (V_COLS_ARE_ROWS) {
+					float4* dst = reinterpret_cast<float4*>(out + (size_t)r * p.ldOut);     // column r of N: kp contiguous values
 #pragma unroll
-						for (int c = 0; c < KPM / 4; ++c) {
-							if (c * 4 < (int)kp) {
-								float4 x = make_float4(sum[4 * c], sum[4 * c + 1], sum[4 * c + 2], sum[4 * c + 3]);
-								if (phase == 1) {
-									const float4 y = dst[c];
-									x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
-								}
-								dst[c] = x;
-							}
-						}
-					} else {
+					for (int c = 0; c < KPM / 4; ++c)
+						if (c * 4 < (int)kp) dst[c] = make_float4(sum[4 * c], sum[4 * c + 1], sum[4 * c + 2], sum[4 * c + 3]);
+				} else {
 #pragma unroll
-						for (int c = 0; c < KPM; ++c) {
-							if (c < (int)p.k) {
-								float* dst = out + (size_t)c * p.ldOut + r;                      // row r of N2: coalesced across the warp
-								*dst = phase == 1 ? *dst + sum[c] : sum[c];
-							}
-						}
-					}
+					for (int c = 0; c < KPM; ++c)
+						if (c < (int)p.k) out[(size_t)c * p.ldOut + r] = sum[c];             // row r of N2: coalesced across the warp
 				}
-				if (phase == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
 			}
 #pragma unroll
 			for (int c = 0; c < KPM; ++c) sum[c] = 0.f;
@@ -464,7 +545,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 
 template <int KPM>
 size_t smemBytes() {
-	return 1024 + (size_t)Rings<KPM>::SV * V_STAGE_BYTES + (size_t)SLOTS * 2 * KPM * STAGE_K * 4 + sizeof(Barriers);
+	return 1024 + (size_t)SV * V_STAGE_BYTES + (size_t)Rings<KPM>::SB * 2 * KPM * STAGE_K * 4 + sizeof(Barriers);
 }
 
 // ---- H -> H^T hi/lo ----------------------------------------------------------------------------------
@@ -507,7 +588,8 @@ EncodeTiledFn encodeTiled() {
 }
 
 // 2-D fp32 tensor map over a column-major matrix: dim0 = rows (contiguous), dim1 = columns (stride ld)
-void makeMap(unsigned char* out, const float* base, unsigned rows, unsigned cols, size_t ld, unsigned boxRows, unsigned boxCols, bool swizzle128) {
+void makeMap(unsigned char* out, const float* base, unsigned rows, unsigned cols, size_t ld, unsigned boxRows, unsigned boxCols, bool swizzle128,
+             bool promote256 = true) {
 	CUtensorMap map;
 	const cuuint64_t dims[2] = {rows, cols};
 	const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
@@ -515,7 +597,7 @@ void makeMap(unsigned char* out, const float* base, unsigned rows, unsigned cols
 	const cuuint32_t elem[2] = {1, 1};
 	const CUresult r = encodeTiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, elem,
 	                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-	                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	                                 promote256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		char buf[160];
 		snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d) for a %u x %u matrix, ld %zu, box %u x %u", (int)r, rows, cols, ld, boxRows, boxCols);
@@ -533,21 +615,24 @@ int smCount() {
 }
 
 void planProduct(Product& prod, unsigned rowsA, unsigned kdim) {
-	prod.tiles = ceilDiv(rowsA, TILE_ROWS);
+	prod.tiles = ceilDiv(rowsA, PAIR_ROWS);
 	prod.stagesPerTile = ceilDiv(kdim, STAGE_K);
 	const unsigned long long units = (unsigned long long)prod.tiles * prod.stagesPerTile;
 	prod.grid = (unsigned)std::min<unsigned long long>(units, (unsigned long long)smCount());
-	std::vector<unsigned char> counts(prod.tiles);
+	// consumers index the counts by 128-wide tile (kernels.h), the stream-K tiles are 256 wide
+	const unsigned tiles128 = ceilDiv(rowsA, TILE_ROWS);
+	std::vector<unsigned char> counts(tiles128);
 	prod.maxSlots = 1;
 	for (unsigned t = 0; t < prod.tiles; ++t) {
 		const unsigned first = ctaOfUnit((unsigned long long)t * prod.stagesPerTile, prod.grid, units);
 		const unsigned last = ctaOfUnit((unsigned long long)(t + 1) * prod.stagesPerTile - 1, prod.grid, units);
-		counts[t] = (unsigned char)(last - first + 1);
+		for (unsigned h = 0; h < 2; ++h)
+			if (2 * t + h < tiles128) counts[2 * t + h] = (unsigned char)(last - first + 1);
 		prod.maxSlots = std::max(prod.maxSlots, last - first + 1);
 	}
 	if (prod.slotCount) cudaFree(prod.slotCount);
-	CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&prod.slotCount), prod.tiles));
-	CUDA_CHECK(cudaMemcpy(prod.slotCount, counts.data(), prod.tiles, cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&prod.slotCount), tiles128));
+	CUDA_CHECK(cudaMemcpy(prod.slotCount, counts.data(), tiles128, cudaMemcpyHostToDevice));
 }
 
 template <int KPM, bool VC>
@@ -563,6 +648,7 @@ void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, s
 	memcpy(&p.mapBhi, prod.mapBhi, 128);
 	memcpy(&p.mapBlo, prod.mapBlo, 128);
 	p.out = out;
+	p.trace = plan.trace;
 	p.ldOut = ldOut;
 	p.slotStride = slotStride;
 	p.units = (unsigned long long)prod.tiles * prod.stagesPerTile;
@@ -581,6 +667,24 @@ void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, s
 }  // namespace
 
 Plan::~Plan() {
+	if (trace != nullptr) {
+		// diagnostic timeline of CTA 0 of the LAST product launched: one line per stage with the clock64 stamps
+		// worker{tile landed, split done, slot free, slot published}, MMA{operands ready, stage issued}
+		std::vector<unsigned long long> host(TRACE_STAGES * TRACE_EVENTS);
+		if (cudaMemcpy(host.data(), trace, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+			if (FILE* f = fopen(getenv("NMFGPU_TC_TRACE"), "w")) {
+				unsigned long long t0 = ~0ull;
+				for (unsigned long long v : host) if (v != 0 && v < t0) t0 = v;
+				for (unsigned g = 0; g < TRACE_STAGES; ++g) {
+					fprintf(f, "%u", g);
+					for (unsigned e = 0; e < 14; ++e) fprintf(f, " %lld", host[g * TRACE_EVENTS + e] ? (long long)(host[g * TRACE_EVENTS + e] - t0) : -1ll);
+					fprintf(f, "\n");
+				}
+				fclose(f);
+			}
+		}
+		cudaFree(trace);
+	}
 	if (wtv.slotCount) cudaFree(wtv.slotCount);
 	if (vht.slotCount) cudaFree(vht.slotCount);
 }
@@ -600,10 +704,15 @@ void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, si
 	plan.k = k;
 	plan.kp = (unsigned)roundUp(k, 16);
 	plan.passes = singlePass ? 1 : 3;
+	if (const char* e = getenv("NMFGPU_TC_ABLATE")) plan.passes |= (unsigned)strtol(e, nullptr, 0) & 0xFF00;   // timing experiments only: results are garbage
 	plan.flushStages = 8;
 	if (const char* e = getenv("NMFGPU_TC_FLUSH_STAGES")) {   // tuning knob: 0 = accumulate whole segments inside the tensor core
 		const long v = strtol(e, nullptr, 10);
 		plan.flushStages = v <= 0 ? 0x40000000u : (unsigned)v;
+	}
+	if (getenv("NMFGPU_TC_TRACE") != nullptr && plan.trace == nullptr) {
+		CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&plan.trace), TRACE_STAGES * TRACE_EVENTS * sizeof(unsigned long long)));
+		CUDA_CHECK(cudaMemset(plan.trace, 0, TRACE_STAGES * TRACE_EVENTS * sizeof(unsigned long long)));
 	}
 	// W^T V: A rows = columns of V, reduction over m
 	planProduct(plan.wtv, n, m);
@@ -612,7 +721,7 @@ void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, si
 	makeMap(plan.wtv.mapBlo, Wlo, m, k, ldW, STAGE_K, plan.kp, true);
 	// V H^T: A rows = rows of V, reduction over n
 	planProduct(plan.vht, m, n);
-	makeMap(plan.vht.mapV, V, m, n, ldV, TILE_ROWS, STAGE_K, false);
+	makeMap(plan.vht.mapV, V, m, n, ldV, TILE_ROWS, STAGE_K, false, false);   // 512-byte rows: promotion only costs bandwidth (tools/tma_stream_bench)
 	makeMap(plan.vht.mapBhi, HtHi, n, k, ldHt, STAGE_K, plan.kp, true);
 	makeMap(plan.vht.mapBlo, HtLo, n, k, ldHt, STAGE_K, plan.kp, true);
 }

@@ -41,6 +41,7 @@ struct Plan {
 	unsigned passes = 3;           // 3 = 3xTF32, 1 = single-pass TF32 (diagnostic)
 	unsigned flushStages = 8;      // reduction stages accumulated inside the tensor core before the fp32 flush
 	Product wtv, vht;
+	unsigned long long* trace = nullptr;   // device buffer of the optional kernel timeline (environment NMFGPU_TC_TRACE=<file>)
 	~Plan();
 };
 
