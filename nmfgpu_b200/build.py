@@ -19,7 +19,9 @@ LIBRARY = os.path.join(LIBDIR, "libnmfgpu64.so")
 SOURCES = ["api.cpp", "host.cpp", "dist.cpp", "engine.cu", "kernels.cu", "tc_gemm.cu", "kmeans.cu", "sparse.cu",
            "init_kernels.cu", "session.cu"]
 
-NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+# NMFGPU_TC_TRACE_BUILD=1 compiles the timeline / ablation hooks of tc_gemm.cu in (diagnostic builds only)
+EXTRA = ["-DNMFGPU_TC_TRACE_BUILD"] if os.environ.get("NMFGPU_TC_TRACE_BUILD") else []
+NVCC_FLAGS = EXTRA + ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unknown-pragmas", "-DNMFGPU_EXPORTING",
               "-I", os.path.join(os.path.dirname(HERE), "include")]
 

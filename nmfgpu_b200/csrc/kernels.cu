@@ -156,8 +156,9 @@ __global__ void __launch_bounds__(256) update_h_generic(unsigned k, unsigned n, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// H update, rank <= KP (fp32): 128 columns per block staged through shared memory, one column per
-// thread in registers, Gram matrix in shared memory read as broadcast float4.
+// H update, rank <= KP (fp32): 32 columns per block staged through shared memory; four threads share a
+// column (each holds the whole old column in registers and produces a quarter of the new one), the Gram
+// matrix sits in shared memory and is read as broadcast float4.  313 blocks at n = 10 000 fill the GPU.
 // ---------------------------------------------------------------------------------------------------
 template <int KP>
 __global__ void __launch_bounds__(128) update_h_reg(unsigned k, unsigned n, const float* __restrict__ G, const float* __restrict__ Hin,
@@ -165,35 +166,52 @@ __global__ void __launch_bounds__(128) update_h_reg(unsigned k, unsigned n, cons
                                                    unsigned splits, size_t splitStride, float eps, float* __restrict__ tracePartials,
                                                    float* __restrict__ HtHi, float* __restrict__ HtLo, size_t ldht,
                                                    const unsigned char* __restrict__ tileSlots) {
-	constexpr int COLS = 128, LD = KP + 1;
-	if (tileSlots != nullptr) splits = tileSlots[blockIdx.x];
+	constexpr int COLS = 32, LD = KP + 1, RPT = KP / 4;   // rows of the new column per thread
+	const unsigned j0 = blockIdx.x * COLS;
+	if (tileSlots != nullptr) splits = tileSlots[j0 >> 7];
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	float* Gs = reinterpret_cast<float*>(smem_raw);  // [KP][KP]: Gs[r*KP + t] = G[r + t*k]
 	float* Ht = Gs + KP * KP;                         // [COLS][LD] old H
 	float* Nt = Ht + COLS * LD;                       // [COLS][LD] numerator, then new H
 	const unsigned tid = threadIdx.x;
-	const unsigned j0 = blockIdx.x * COLS;
 	for (unsigned idx = tid; idx < KP * KP; idx += 128) {
 		const unsigned t = idx % KP, r = idx / KP;
 		Gs[idx] = (r < k && t < k) ? G[(size_t)t * k + r] : 0.f;
 	}
-	for (unsigned idx = tid; idx < COLS * KP; idx += 128) {
-		const unsigned t = idx % KP, col = idx / KP;
-		const unsigned j = j0 + col;
-		float h = 0.f, num = 0.f;
-		if (j < n && t < k) {
-			h = Hin[(size_t)j * ldh + t];
-			for (unsigned s = 0; s < splits; ++s) num += Npart[s * splitStride + (size_t)j * ldn + t];
+	constexpr int PER = COLS * KP / 128;
+	float hv[PER], nv[PER];
+#pragma unroll
+	for (int e = 0; e < PER; ++e) {   // all loads of this thread in flight before the first use
+		const unsigned idx = tid + e * 128;
+		const unsigned t = idx % KP, j = j0 + idx / KP;
+		const bool ok = j < n && t < k;
+		hv[e] = ok ? Hin[(size_t)j * ldh + t] : 0.f;
+		nv[e] = ok ? Npart[(size_t)j * ldn + t] : 0.f;
+	}
+	for (unsigned sl = 1; sl < splits; ++sl) {
+#pragma unroll
+		for (int e = 0; e < PER; ++e) {
+			const unsigned idx = tid + e * 128;
+			const unsigned t = idx % KP, j = j0 + idx / KP;
+			if (j < n && t < k) nv[e] += Npart[sl * splitStride + (size_t)j * ldn + t];
 		}
-		Ht[col * LD + t] = h;
-		Nt[col * LD + t] = num;
+	}
+#pragma unroll
+	for (int e = 0; e < PER; ++e) {
+		const unsigned idx = tid + e * 128;
+		Ht[(idx / KP) * LD + idx % KP] = hv[e];
+		Nt[(idx / KP) * LD + idx % KP] = nv[e];
 	}
 	__syncthreads();
+	const unsigned col = tid / 4, part = tid % 4;
 	float h[KP];
 #pragma unroll
-	for (int t = 0; t < KP; ++t) h[t] = Ht[tid * LD + t];
+	for (int t = 0; t < KP; ++t) h[t] = Ht[col * LD + t];
 	float tr = 0.f;
-	for (unsigned r = 0; r < k; ++r) {
+	float out[RPT];
+#pragma unroll
+	for (int rr = 0; rr < RPT; ++rr) {
+		const unsigned r = part * RPT + rr;
 		const float4* g4 = reinterpret_cast<const float4*>(Gs + r * KP);
 		float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
@@ -205,24 +223,29 @@ __global__ void __launch_bounds__(128) update_h_reg(unsigned k, unsigned n, cons
 			d3 = fmaf(g.w, h[4 * q + 3], d3);
 		}
 		const float d = (d0 + d1) + (d2 + d3);
-		const float num = Nt[tid * LD + r];
-		const float hn = Ht[tid * LD + r] * num / (d + eps);
+		const float num = Nt[col * LD + r];
+		const float hn = Ht[col * LD + r] * num / (d + eps);
 		tr = fmaf(hn, num, tr);
-		Nt[tid * LD + r] = hn;
+		out[rr] = hn;
 	}
-	if (tracePartials != nullptr && j0 + tid < n) tracePartials[j0 + tid] = tr;
+	tr += __shfl_xor_sync(0xffffffffu, tr, 1);
+	tr += __shfl_xor_sync(0xffffffffu, tr, 2);
+	if (tracePartials != nullptr && part == 0 && j0 + col < n) tracePartials[j0 + col] = tr;
+	__syncthreads();   // every thread has read its numerators: Nt now receives the new column
+#pragma unroll
+	for (int rr = 0; rr < RPT; ++rr) Nt[col * LD + part * RPT + rr] = out[rr];
 	__syncthreads();
 	for (unsigned idx = tid; idx < COLS * KP; idx += 128) {
-		const unsigned t = idx % KP, col = idx / KP;
-		const unsigned j = j0 + col;
-		if (j < n && t < k) Hout[(size_t)j * ldh + t] = Nt[col * LD + t];
+		const unsigned t = idx % KP, c = idx / KP;
+		const unsigned j = j0 + c;
+		if (j < n && t < k) Hout[(size_t)j * ldh + t] = Nt[c * LD + t];
 	}
 	if (HtHi != nullptr) {
 		for (unsigned idx = tid; idx < COLS * KP; idx += 128) {
-			const unsigned col = idx % COLS, t = idx / COLS;
-			const unsigned j = j0 + col;
+			const unsigned c = idx % COLS, t = idx / COLS;
+			const unsigned j = j0 + c;
 			if (j < n && t < k) {
-				const float v = Nt[col * LD + t];
+				const float v = Nt[c * LD + t];
 				const float hi = tf32_hi(v);
 				HtHi[(size_t)t * ldht + j] = hi;
 				HtLo[(size_t)t * ldht + j] = v - hi;
@@ -284,7 +307,8 @@ __global__ void __launch_bounds__(128) update_w_generic(unsigned m, unsigned k, 
 	}
 }
 
-// W update, rank <= KP (fp32): one row per thread in registers, H H^T in shared memory.
+// W update, rank <= KP (fp32): one row per thread in registers, H H^T in shared memory.  All global loads
+// of a thread (its row of W and of the partial products) are issued before the first use.
 template <int KP>
 __global__ void __launch_bounds__(128) update_w_reg(unsigned m, unsigned k, const float* __restrict__ B, const float* __restrict__ Win,
                                                    float* __restrict__ Wout, size_t ldw, const float* __restrict__ Ppart, size_t ldp,
@@ -295,39 +319,49 @@ __global__ void __launch_bounds__(128) update_w_reg(unsigned m, unsigned k, cons
 	float* Bs = reinterpret_cast<float*>(smem_raw);  // [KP][KP]: Bs[c*KP + t] = B[t + c*k]
 	float* sq = Bs + KP * KP;                         // [4][KP]
 	const unsigned tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+	const unsigned i = blockIdx.x * 128 + tid;
+	const bool valid = i < m;
+	float w[KP], pv[KP];
+#pragma unroll
+	for (int t = 0; t < KP; ++t) {
+		const bool ok = valid && t < (int)k;
+		w[t] = ok ? Win[(size_t)t * ldw + i] : 0.f;
+		pv[t] = ok ? Ppart[(size_t)t * ldp + i] : 0.f;
+	}
 	for (unsigned idx = tid; idx < KP * KP; idx += 128) {
 		const unsigned t = idx % KP, c = idx / KP;
 		Bs[idx] = (c < k && t < k) ? B[(size_t)c * k + t] : 0.f;
 	}
+	for (unsigned sl = 1; sl < splits; ++sl) {
+#pragma unroll
+		for (int t = 0; t < KP; ++t)
+			if (valid && t < (int)k) pv[t] += Ppart[sl * splitStride + (size_t)t * ldp + i];
+	}
 	__syncthreads();
-	const unsigned i = blockIdx.x * 128 + tid;
-	const bool valid = i < m;
-	float w[KP];
 #pragma unroll
-	for (int t = 0; t < KP; ++t) w[t] = (valid && t < (int)k) ? Win[(size_t)t * ldw + i] : 0.f;
-	for (unsigned c = 0; c < k; ++c) {
-		const float4* b4 = reinterpret_cast<const float4*>(Bs + c * KP);
-		float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+	for (int c = 0; c < KP; ++c) {
+		if (c < (int)k) {   // block-uniform
+			const float4* b4 = reinterpret_cast<const float4*>(Bs + c * KP);
+			float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
-		for (int q = 0; q < KP / 4; ++q) {
-			const float4 b = b4[q];
-			d0 = fmaf(w[4 * q + 0], b.x, d0);
-			d1 = fmaf(w[4 * q + 1], b.y, d1);
-			d2 = fmaf(w[4 * q + 2], b.z, d2);
-			d3 = fmaf(w[4 * q + 3], b.w, d3);
+			for (int q = 0; q < KP / 4; ++q) {
+				const float4 b = b4[q];
+				d0 = fmaf(w[4 * q + 0], b.x, d0);
+				d1 = fmaf(w[4 * q + 1], b.y, d1);
+				d2 = fmaf(w[4 * q + 2], b.z, d2);
+				d3 = fmaf(w[4 * q + 3], b.w, d3);
+			}
+			const float d = (d0 + d1) + (d2 + d3);
+			float wn = 0.f;
+			if (valid) {
+				wn = w[c] * pv[c] / (d + eps);
+				Wout[(size_t)c * ldw + i] = wn;
+			}
+			float s2 = wn * wn;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+			if (lane == 0) sq[warp * KP + c] = s2;
 		}
-		const float d = (d0 + d1) + (d2 + d3);
-		float wn = 0.f;
-		if (valid) {
-			float p = 0.f;
-			for (unsigned s = 0; s < splits; ++s) p += Ppart[s * splitStride + (size_t)c * ldp + i];
-			wn = Win[(size_t)c * ldw + i] * p / (d + eps);
-			Wout[(size_t)c * ldw + i] = wn;
-		}
-		float s2 = wn * wn;
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-		if (lane == 0) sq[warp * KP + c] = s2;
 	}
 	__syncthreads();
 	for (unsigned c = tid; c < k; c += 128)
@@ -652,9 +686,9 @@ template <int KP>
 static void updateHReg(unsigned k, unsigned n, const float* G, const float* Hin, float* Hout, size_t ldh, const float* Npart, size_t ldn,
                        unsigned splits, size_t splitStride, float eps, float* tracePartials, float* HtHi, float* HtLo, size_t ldht,
                        cudaStream_t stream, const unsigned char* tileSlots) {
-	const size_t smem = sizeof(float) * ((size_t)KP * KP + 2 * 128 * (KP + 1));
+	const size_t smem = sizeof(float) * ((size_t)KP * KP + 2 * 32 * (KP + 1));
 	allowSmem(update_h_reg<KP>, smem);
-	update_h_reg<KP><<<ceilDiv(n, 128), 128, smem, stream>>>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials,
+	update_h_reg<KP><<<ceilDiv(n, 32), 128, smem, stream>>>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials,
 	                                                          HtHi, HtLo, ldht, tileSlots);
 	launchCheck();
 }
