@@ -200,6 +200,7 @@ def sparse_description(fmt, rows, cols, values, ptr_a, ptr_b, base=IndexBase.Zer
     d.csr.ptrB = ptr_b.ctypes.data
     d.csr.nnz = len(values)
     d.csr.base = base
+    d._keep = (values, ptr_a, ptr_b)   # the description only holds raw pointers: keep the arrays alive with it
     return d
 
 

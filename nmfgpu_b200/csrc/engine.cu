@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -119,8 +120,13 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 		m_Wlo.zero(m_stream);
 		m_HtHi.zero(m_stream);
 		m_HtLo.zero(m_stream);
+		// centre of the products: the mean of V (any constant is exact algebra; the mean keeps the accumulators smallest)
+		float center = tc::meanOf(reinterpret_cast<const float*>(m_V.get()), m, n, m_ldV, m_stream);
+		if (const char* e = getenv("NMFGPU_TC_CENTER")) center = (float)atof(e) * center;   // study knob: 0 switches centring off
 		tc::makePlan(m_tc->plan, m, n, k, reinterpret_cast<const float*>(m_V.get()), m_ldV, m_Whi.get(), m_Wlo.get(), m_ldW, m_HtHi.get(),
-		             m_HtLo.get(), m_ldHt, m_cfg.precision == Precision::Tf32x1);
+		             m_HtLo.get(), m_ldHt, m_cfg.precision == Precision::Tf32x1, center);
+		m_corrN = reinterpret_cast<const T*>(m_tc->plan.corrN);
+		m_corrP = reinterpret_cast<const T*>(m_tc->plan.corrP);
 		m_splitsN = m_tc->plan.wtv.maxSlots;
 		m_splitsP = m_tc->plan.vht.maxSlots;
 		m_slotsN = m_tc->plan.wtv.slotCount;
@@ -184,7 +190,8 @@ void curandFill(float* p, size_t count, unsigned seed, cudaStream_t stream) {
 	if (curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS)
 		throw EngineError(ResultType::ErrorExternalLibrary, "curandCreateGenerator failed");
 	curandSetStream(gen, stream);
-	curandSetPseudoRandomGeneratorSeed(gen, seed);
+	// the reference passes the seed through an `int` parameter (RandomValueStrategy.cpp:29,41): sign-extended to 64 bits
+	curandSetPseudoRandomGeneratorSeed(gen, (unsigned long long)(long long)(int)seed);
 	const curandStatus_t st = curandGenerateUniform(gen, p, count);
 	curandDestroyGenerator(gen);
 	if (st != CURAND_STATUS_SUCCESS) throw EngineError(ResultType::ErrorExternalLibrary, "curandGenerateUniform failed");
@@ -194,7 +201,7 @@ void curandFill(double* p, size_t count, unsigned seed, cudaStream_t stream) {
 	if (curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS)
 		throw EngineError(ResultType::ErrorExternalLibrary, "curandCreateGenerator failed");
 	curandSetStream(gen, stream);
-	curandSetPseudoRandomGeneratorSeed(gen, seed);
+	curandSetPseudoRandomGeneratorSeed(gen, (unsigned long long)(long long)(int)seed);
 	const curandStatus_t st = curandGenerateUniformDouble(gen, p, count);
 	curandDestroyGenerator(gen);
 	if (st != CURAND_STATUS_SUCCESS) throw EngineError(ResultType::ErrorExternalLibrary, "curandGenerateUniformDouble failed");
@@ -260,6 +267,23 @@ void Engine<T>::finishInitialisation() {
 	float* H = reinterpret_cast<float*>(m_H[m_hCur].get());
 	kern::splitTf32(m_cfg.m, m_cfg.k, W, m_ldW, m_Whi.get(), m_Wlo.get(), m_ldW, m_stream);
 	tc::splitTransposeH(m_cfg.k, m_cfg.n, H, m_ldH, m_HtHi.get(), m_HtLo.get(), m_ldHt, m_stream);
+	operandChangedW(m_W[m_wCur].get());
+	operandChangedH(m_H[m_hCur].get());
+}
+
+// the tensor-core products read hi/lo copies of W resp. H; their rank-one centring terms follow the same values
+template <typename T>
+void Engine<T>::operandChangedW(const T* W) {
+	if (!m_useTC) return;
+	tc::refreshCorrectionW(m_tc->plan, reinterpret_cast<const float*>(W), m_ldW, m_stream);
+	m_launches += 2;
+}
+
+template <typename T>
+void Engine<T>::operandChangedH(const T* H) {
+	if (!m_useTC) return;
+	tc::refreshCorrectionH(m_tc->plan, reinterpret_cast<const float*>(H), m_ldH, m_stream);
+	m_launches += 2;
 }
 
 // ---- shared building blocks ---------------------------------------------------------------------------
@@ -307,6 +331,7 @@ void Engine<T>::normaliseW(unsigned blocks) {
 	kern::scaleColumns<T>(m_cfg.m, m_cfg.k, m_W[m_wCur].get(), m_ldW, m_colSq.get(), m_useTC ? m_Whi.get() : nullptr,
 	                      m_useTC ? m_Wlo.get() : nullptr, m_stream);
 	m_launches += 2;
+	operandChangedW(m_W[m_wCur].get());
 }
 
 // W <- W o P / (W B + eps) then unit columns; P is read as split partials, or -- with column shards --
@@ -316,17 +341,19 @@ void Engine<T>::multiplicativeW(const T* B) {
 	const T* P = m_Ppart.get();
 	unsigned splits = m_splitsP;
 	const unsigned char* slots = m_slotsP;
+	const T* corr = m_corrP;
 	if (m_cfg.comm && m_cfg.comm->worldSize() > 1) {
 		T* sum = m_Ppart.get() + m_strideP * m_splitsP;
-		kern::sumSplits<T>(m_cfg.m, m_cfg.k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, sum, m_ldW, m_stream, m_slotsP, true);
+		kern::sumSplits<T>(m_cfg.m, m_cfg.k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, sum, m_ldW, m_stream, m_slotsP, true, m_corrP);
 		m_cfg.comm->allReduceSum(sum, m_strideP, m_stream);
 		m_launches += 1;
 		P = sum;
 		splits = 1;
 		slots = nullptr;
+		corr = nullptr;
 	}
 	const unsigned blocks = kern::updateW<T>(m_cfg.m, m_cfg.k, B, m_W[m_wCur].get(), m_W[1 - m_wCur].get(), m_ldW, P, m_ldW, splits, m_strideP,
-	                                         m_eps, m_colSqPartials.get(), m_stream, slots);
+	                                         m_eps, m_colSqPartials.get(), m_stream, slots, corr);
 	m_launches += 1;
 	m_wCur = 1 - m_wCur;
 	normaliseW(blocks);
@@ -342,9 +369,10 @@ void Engine<T>::iterateMU(bool err) {
 	gramW(m_W[m_wCur].get(), m_G.get());                                                    // A = W^T W      MU.h:168/176
 	productWtV(m_W[m_wCur].get());                                                          // N = W^T V      MU.h:187
 	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_eps,
-	                 err ? m_partN.get() : nullptr, htHi, htLo, m_ldHt, m_stream, m_slotsN);   // H update  MU.h:181-197
+	                 err ? m_partN.get() : nullptr, htHi, htLo, m_ldHt, m_stream, m_slotsN, m_corrN);   // H update  MU.h:181-197
 	m_launches += 1;
 	m_hCur = 1 - m_hCur;
+	operandChangedH(m_H[m_hCur].get());
 
 	gramH(m_H[m_hCur].get(), m_ldH, m_B.get());                                             // B = H H^T      MU.h:208/231
 	if (err) {
@@ -371,12 +399,13 @@ void Engine<T>::iterateNsNMF(bool err) {
 	if (m_useTC) {  // the tensor-core product reads the hi/lo split of its left factor
 		kern::splitTf32(m, k, reinterpret_cast<float*>(m_smoothW.get()), m_ldW, m_Whi.get(), m_Wlo.get(), m_ldW, m_stream);
 		m_launches += 1;
+		operandChangedW(m_smoothW.get());
 	}
 	gramW(m_smoothW.get(), m_G.get());                                                      // W~^T W~
 	productWtV(m_smoothW.get());                                                            // W~^T V
 	// the H^T split written here is overwritten below by the split of S H (what V H~^T consumes)
 	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_eps,
-	                 err ? m_partN.get() : nullptr, nullptr, nullptr, m_ldHt, m_stream, m_slotsN);
+	                 err ? m_partN.get() : nullptr, nullptr, nullptr, m_ldHt, m_stream, m_slotsN, m_corrN);
 	m_launches += 1;
 	m_hCur = 1 - m_hCur;
 	if (!err && m_cfg.constantW) return;                                                     // nsNMF.h:193-195
@@ -393,6 +422,7 @@ void Engine<T>::iterateNsNMF(bool err) {
 		if (m_useTC) {
 			tc::splitTransposeH(k, n, reinterpret_cast<float*>(m_smoothH.get()), m_ldH, htHi, htLo, m_ldHt, m_stream);
 			m_launches += 1;
+			operandChangedH(m_smoothH.get());
 		}
 		productVHt(m_smoothH.get(), m_ldH);                                                 // V H~^T     nsNMF.h:211
 		multiplicativeW(m_B.get());                                                         // nsNMF.h:212-217
@@ -422,12 +452,13 @@ void Engine<T>::iterateLS(bool err) {
 	kern::qrFactor<T>(k, m_G.get(), m_qr.get(), m_stream);
 	productWtV(m_W[m_wCur].get());
 	T* H = m_H[m_hCur].get();
-	kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, H, m_ldH, m_stream, m_slotsN, false);
+	kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, H, m_ldH, m_stream, m_slotsN, false, m_corrN);
 	kern::qrSolveClamp<T>(k, m_qr.get(), H, m_ldH, n, false, m_stream);
 	m_launches += 4;
 	if (m_useTC) {
 		tc::splitTransposeH(k, n, reinterpret_cast<float*>(H), m_ldH, m_HtHi.get(), m_HtLo.get(), m_ldHt, m_stream);
 		m_launches += 1;
+		operandChangedH(H);
 	}
 
 	gramH(H, m_ldH, m_B.get());
@@ -442,7 +473,7 @@ void Engine<T>::iterateLS(bool err) {
 		if (!m_cfg.constantW) {
 			productVHt(H, m_ldH);
 			if (err && !multi) {  // multiplicativeW consumes the partials; keep a summed copy for the trace
-				kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, Psum, m_ldW, m_stream, m_slotsP, true);
+				kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, Psum, m_ldW, m_stream, m_slotsP, true, m_corrP);
 				m_launches += 1;
 			}
 			multiplicativeW(m_B.get());
@@ -459,7 +490,7 @@ void Engine<T>::iterateLS(bool err) {
 			kern::qrFactor<T>(k, m_B.get(), m_qr.get(), m_stream);
 			productVHt(H, m_ldH);
 			T* Wnext = m_W[1 - m_wCur].get();
-			kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, Wnext, m_ldW, m_stream, m_slotsP, true);
+			kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, Wnext, m_ldW, m_stream, m_slotsP, true, m_corrP);
 			m_launches += 2;
 			if (multi) m_cfg.comm->allReduceSum(Wnext, m_strideP, m_stream);
 			if (err) {
@@ -569,7 +600,7 @@ void Engine<T>::debugProducts(T* wtv, T* vht, float* msWtV, float* msVHt, cudaEv
 		if (msWtV) CUDA_CHECK(cudaEventElapsedTime(msWtV, e0, e1));
 		if (wtv) {
 			T* sum = m_H[1 - m_hCur].get();  // spare H buffer as the landing zone
-			kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, sum, m_ldH, m_stream, m_slotsN, false);
+			kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, sum, m_ldH, m_stream, m_slotsN, false, m_corrN);
 			CUDA_CHECK(cudaMemcpy2DAsync(wtv, (size_t)k * sizeof(T), sum, m_ldH * sizeof(T), (size_t)k * sizeof(T), n, cudaMemcpyDeviceToHost, m_stream));
 			synchronize();
 		}
@@ -582,7 +613,7 @@ void Engine<T>::debugProducts(T* wtv, T* vht, float* msWtV, float* msVHt, cudaEv
 		if (msVHt) CUDA_CHECK(cudaEventElapsedTime(msVHt, e0, e1));
 		if (vht) {
 			T* sum = m_Ppart.get() + m_strideP * m_splitsP;
-			kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, sum, m_ldW, m_stream, m_slotsP, true);
+			kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, sum, m_ldW, m_stream, m_slotsP, true, m_corrP);
 			CUDA_CHECK(cudaMemcpy2DAsync(vht, (size_t)m * sizeof(T), sum, m_ldW * sizeof(T), (size_t)m * sizeof(T), k, cudaMemcpyDeviceToHost, m_stream));
 			synchronize();
 		}

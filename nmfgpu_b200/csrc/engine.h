@@ -101,6 +101,8 @@ private:
 	void productWtV(const T* W);                               // m_Npart / m_splitsN <- W^T V
 	void productVHt(const T* H, size_t ldh);                   // m_Ppart / m_splitsP <- V H^T (all-reduced)
 	void normaliseW(unsigned blocks);
+	void operandChangedW(const T* W);                          // refresh what the tensor-core products derive from W resp. H
+	void operandChangedH(const T* H);
 	void multiplicativeW(const T* B);                          // W <- W o P / (W B + eps), normalise
 
 	EngineConfig m_cfg;
@@ -118,6 +120,8 @@ private:
 	size_t m_strideN = 0, m_strideP = 0;
 	const unsigned char* m_slotsN = nullptr;   // per-tile partial counts of the stream-K tensor-core products (tc_gemm.h)
 	const unsigned char* m_slotsP = nullptr;
+	const T* m_corrN = nullptr;   // rank-one terms of the mean-centred tensor-core products (tc_gemm.h), device, [k]
+	const T* m_corrP = nullptr;
 	DeviceBuffer<T> m_colSqPartials, m_colSq;
 	DeviceBuffer<T> m_partN, m_partK;
 	PinnedBuffer<T> m_hostSecond, m_hostThird;

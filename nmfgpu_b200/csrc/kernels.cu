@@ -96,12 +96,13 @@ __global__ void __launch_bounds__(256) gemm_simt(unsigned M, unsigned N, unsigne
 template <typename T>
 __global__ void sum_splits_kernel(unsigned rows, unsigned cols, const T* __restrict__ src, size_t ldsrc, unsigned splits,
                                   size_t splitStride, T* __restrict__ dst, size_t lddst, const unsigned char* __restrict__ tileSlots,
-                                  bool tilesAlongRows) {
+                                  bool tilesAlongRows, const T* __restrict__ corr) {
 	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned c = blockIdx.y;
 	if (r >= rows || c >= cols) return;
 	if (tileSlots != nullptr) splits = tileSlots[(tilesAlongRows ? r : c) >> 7];
-	T s = T(0);
+	// corr: rank-one term of a mean-centred tensor-core product (tc_gemm.h), indexed along the short (rank) dimension
+	T s = corr != nullptr ? corr[tilesAlongRows ? c : r] : T(0);
 	for (unsigned sp = 0; sp < splits; ++sp) s += src[sp * splitStride + (size_t)c * ldsrc + r];
 	dst[(size_t)c * lddst + r] = s;
 }
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(256) update_h_generic(unsigned k, unsigned n, 
                                                        T* __restrict__ Hout, size_t ldh, const T* __restrict__ Npart, size_t ldn,
                                                        unsigned splits, size_t splitStride, T eps, T* __restrict__ tracePartials,
                                                        float* __restrict__ HtHi, float* __restrict__ HtLo, size_t ldht,
-                                                       const unsigned char* __restrict__ tileSlots) {
+                                                       const unsigned char* __restrict__ tileSlots, const T* __restrict__ corr) {
 	extern __shared__ unsigned char smem_raw[];
 	T* hcol = reinterpret_cast<T*>(smem_raw);  // [8 warps][k]
 	const unsigned lane = threadIdx.x % 32, warp = threadIdx.x / 32;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(256) update_h_generic(unsigned k, unsigned n, 
 		for (unsigned r = lane; r < k; r += 32) {
 			T d = T(0);
 			for (unsigned t = 0; t < k; ++t) d = fma(G[(size_t)t * k + r], mine[t], d);
-			T num = T(0);
+			T num = corr != nullptr ? corr[r] : T(0);
 			for (unsigned s = 0; s < splits; ++s) num += Npart[s * splitStride + (size_t)j * ldn + r];
 			const T hn = mine[r] * num / (d + eps);
 			Hout[(size_t)j * ldh + r] = hn;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(128) update_h_reg(unsigned k, unsigned n, cons
                                                    float* __restrict__ Hout, size_t ldh, const float* __restrict__ Npart, size_t ldn,
                                                    unsigned splits, size_t splitStride, float eps, float* __restrict__ tracePartials,
                                                    float* __restrict__ HtHi, float* __restrict__ HtLo, size_t ldht,
-                                                   const unsigned char* __restrict__ tileSlots) {
+                                                   const unsigned char* __restrict__ tileSlots, const float* __restrict__ corr) {
 	constexpr int COLS = 32, LD = KP + 1, RPT = KP / 4;   // rows of the new column per thread
 	const unsigned j0 = blockIdx.x * COLS;
 	if (tileSlots != nullptr) splits = tileSlots[j0 >> 7];
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(128) update_h_reg(unsigned k, unsigned n, cons
 		const unsigned t = idx % KP, j = j0 + idx / KP;
 		const bool ok = j < n && t < k;
 		hv[e] = ok ? Hin[(size_t)j * ldh + t] : 0.f;
-		nv[e] = ok ? Npart[(size_t)j * ldn + t] : 0.f;
+		nv[e] = ok ? Npart[(size_t)j * ldn + t] + (corr != nullptr ? corr[t] : 0.f) : 0.f;
 	}
 	for (unsigned sl = 1; sl < splits; ++sl) {
 #pragma unroll
@@ -281,7 +282,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) update_w_generic(unsigned m, unsigned k, const T* __restrict__ B, const T* __restrict__ Win,
                                                        T* __restrict__ Wout, size_t ldw, const T* __restrict__ Ppart, size_t ldp,
                                                        unsigned splits, size_t splitStride, T eps, T* __restrict__ colSqPartials,
-                                                       const unsigned char* __restrict__ tileSlots) {
+                                                       const unsigned char* __restrict__ tileSlots, const T* __restrict__ corr) {
 	__shared__ T warpSq[4];
 	if (tileSlots != nullptr) splits = tileSlots[blockIdx.x];
 	const unsigned i = blockIdx.x * 128 + threadIdx.x;
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(128) update_w_generic(unsigned m, unsigned k, 
 		if (valid) {
 			T d = T(0);
 			for (unsigned t = 0; t < k; ++t) d = fma(Win[(size_t)t * ldw + i], B[(size_t)c * k + t], d);
-			T p = T(0);
+			T p = corr != nullptr ? corr[c] : T(0);
 			for (unsigned s = 0; s < splits; ++s) p += Ppart[s * splitStride + (size_t)c * ldp + i];
 			wn = Win[(size_t)c * ldw + i] * p / (d + eps);
 			Wout[(size_t)c * ldw + i] = wn;
@@ -313,7 +314,7 @@ template <int KP>
 __global__ void __launch_bounds__(128) update_w_reg(unsigned m, unsigned k, const float* __restrict__ B, const float* __restrict__ Win,
                                                    float* __restrict__ Wout, size_t ldw, const float* __restrict__ Ppart, size_t ldp,
                                                    unsigned splits, size_t splitStride, float eps, float* __restrict__ colSqPartials,
-                                                   const unsigned char* __restrict__ tileSlots) {
+                                                   const unsigned char* __restrict__ tileSlots, const float* __restrict__ corr) {
 	if (tileSlots != nullptr) splits = tileSlots[blockIdx.x];
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	float* Bs = reinterpret_cast<float*>(smem_raw);  // [KP][KP]: Bs[c*KP + t] = B[t + c*k]
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(128) update_w_reg(unsigned m, unsigned k, cons
 	for (int t = 0; t < KP; ++t) {
 		const bool ok = valid && t < (int)k;
 		w[t] = ok ? Win[(size_t)t * ldw + i] : 0.f;
-		pv[t] = ok ? Ppart[(size_t)t * ldp + i] : 0.f;
+		pv[t] = ok ? Ppart[(size_t)t * ldp + i] + (corr != nullptr ? corr[t] : 0.f) : 0.f;
 	}
 	for (unsigned idx = tid; idx < KP * KP; idx += 128) {
 		const unsigned t = idx % KP, c = idx / KP;
@@ -665,39 +666,39 @@ unsigned effectiveSplits(unsigned reduceLen, unsigned splits) {
 
 template <typename T>
 void sumSplits(unsigned rows, unsigned cols, const T* src, size_t ldsrc, unsigned splits, size_t splitStride, T* dst, size_t lddst,
-               cudaStream_t stream, const unsigned char* tileSlots, bool tilesAlongRows) {
+               cudaStream_t stream, const unsigned char* tileSlots, bool tilesAlongRows, const T* corr) {
 	dim3 grid(ceilDiv(rows, 128), cols);
-	sum_splits_kernel<T><<<grid, 128, 0, stream>>>(rows, cols, src, ldsrc, splits, splitStride, dst, lddst, tileSlots, tilesAlongRows);
+	sum_splits_kernel<T><<<grid, 128, 0, stream>>>(rows, cols, src, ldsrc, splits, splitStride, dst, lddst, tileSlots, tilesAlongRows, corr);
 	launchCheck();
 }
 
 template <typename T>
 static void updateHGeneric(unsigned k, unsigned n, const T* G, const T* Hin, T* Hout, size_t ldh, const T* Npart, size_t ldn,
                            unsigned splits, size_t splitStride, T eps, T* tracePartials, float* HtHi, float* HtLo, size_t ldht,
-                           cudaStream_t stream, const unsigned char* tileSlots) {
+                           cudaStream_t stream, const unsigned char* tileSlots, const T* corr) {
 	const size_t smem = (size_t)8 * k * sizeof(T);
 	allowSmem(update_h_generic<T>, smem);
 	update_h_generic<T><<<ceilDiv(n, 32), 256, smem, stream>>>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps,
-	                                                            tracePartials, HtHi, HtLo, ldht, tileSlots);
+	                                                            tracePartials, HtHi, HtLo, ldht, tileSlots, corr);
 	launchCheck();
 }
 
 template <int KP>
 static void updateHReg(unsigned k, unsigned n, const float* G, const float* Hin, float* Hout, size_t ldh, const float* Npart, size_t ldn,
                        unsigned splits, size_t splitStride, float eps, float* tracePartials, float* HtHi, float* HtLo, size_t ldht,
-                       cudaStream_t stream, const unsigned char* tileSlots) {
+                       cudaStream_t stream, const unsigned char* tileSlots, const float* corr) {
 	const size_t smem = sizeof(float) * ((size_t)KP * KP + 2 * 32 * (KP + 1));
 	allowSmem(update_h_reg<KP>, smem);
 	update_h_reg<KP><<<ceilDiv(n, 32), 128, smem, stream>>>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials,
-	                                                          HtHi, HtLo, ldht, tileSlots);
+	                                                          HtHi, HtLo, ldht, tileSlots, corr);
 	launchCheck();
 }
 
 template <>
 void updateH<float>(unsigned k, unsigned n, const float* G, const float* Hin, float* Hout, size_t ldh, const float* Npart, size_t ldn,
                     unsigned splits, size_t splitStride, float eps, float* tracePartials, float* HtHi, float* HtLo, size_t ldht,
-                    cudaStream_t stream, const unsigned char* tileSlots) {
-#define NMF_ARGS k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials, HtHi, HtLo, ldht, stream, tileSlots
+                    cudaStream_t stream, const unsigned char* tileSlots, const float* corr) {
+#define NMF_ARGS k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials, HtHi, HtLo, ldht, stream, tileSlots, corr
 	if (k <= 16) updateHReg<16>(NMF_ARGS);
 	else if (k <= 32) updateHReg<32>(NMF_ARGS);
 	else if (k <= 64) updateHReg<64>(NMF_ARGS);
@@ -709,8 +710,8 @@ void updateH<float>(unsigned k, unsigned n, const float* G, const float* Hin, fl
 template <>
 void updateH<double>(unsigned k, unsigned n, const double* G, const double* Hin, double* Hout, size_t ldh, const double* Npart,
                      size_t ldn, unsigned splits, size_t splitStride, double eps, double* tracePartials, float* HtHi, float* HtLo,
-                     size_t ldht, cudaStream_t stream, const unsigned char* tileSlots) {
-	updateHGeneric<double>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials, HtHi, HtLo, ldht, stream, tileSlots);
+                     size_t ldht, cudaStream_t stream, const unsigned char* tileSlots, const double* corr) {
+	updateHGeneric<double>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials, HtHi, HtLo, ldht, stream, tileSlots, corr);
 }
 
 template <typename T>
@@ -730,26 +731,26 @@ void absInPlace(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream_t str
 template <int KP>
 static unsigned updateWReg(unsigned m, unsigned k, const float* B, const float* Win, float* Wout, size_t ldw, const float* Ppart,
                            size_t ldp, unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream,
-                           const unsigned char* tileSlots) {
+                           const unsigned char* tileSlots, const float* corr) {
 	const size_t smem = sizeof(float) * ((size_t)KP * KP + 4 * KP);
 	allowSmem(update_w_reg<KP>, smem);
 	const unsigned blocks = ceilDiv(m, 128);
-	update_w_reg<KP><<<blocks, 128, smem, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots);
+	update_w_reg<KP><<<blocks, 128, smem, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots, corr);
 	launchCheck();
 	return blocks;
 }
 
 template <>
 unsigned updateW<float>(unsigned m, unsigned k, const float* B, const float* Win, float* Wout, size_t ldw, const float* Ppart, size_t ldp,
-                        unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream, const unsigned char* tileSlots) {
-#define NMF_ARGS m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, stream, tileSlots
+                        unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream, const unsigned char* tileSlots, const float* corr) {
+#define NMF_ARGS m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, stream, tileSlots, corr
 	if (k <= 16) return updateWReg<16>(NMF_ARGS);
 	if (k <= 32) return updateWReg<32>(NMF_ARGS);
 	if (k <= 64) return updateWReg<64>(NMF_ARGS);
 	if (k <= 128) return updateWReg<128>(NMF_ARGS);
 #undef NMF_ARGS
 	const unsigned blocks = ceilDiv(m, 128);
-	update_w_generic<float><<<blocks, 128, 0, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots);
+	update_w_generic<float><<<blocks, 128, 0, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots, corr);
 	launchCheck();
 	return blocks;
 }
@@ -757,9 +758,9 @@ unsigned updateW<float>(unsigned m, unsigned k, const float* B, const float* Win
 template <>
 unsigned updateW<double>(unsigned m, unsigned k, const double* B, const double* Win, double* Wout, size_t ldw, const double* Ppart,
                          size_t ldp, unsigned splits, size_t splitStride, double eps, double* colSqPartials, cudaStream_t stream,
-                         const unsigned char* tileSlots) {
+                         const unsigned char* tileSlots, const double* corr) {
 	const unsigned blocks = ceilDiv(m, 128);
-	update_w_generic<double><<<blocks, 128, 0, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots);
+	update_w_generic<double><<<blocks, 128, 0, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots, corr);
 	launchCheck();
 	return blocks;
 }
@@ -841,7 +842,7 @@ void splitTf32(unsigned rows, unsigned cols, const float* X, size_t ldx, float* 
 #define NMF_INSTANTIATE(T)                                                                                                             \
 	template void gemmTN<T>(unsigned, unsigned, unsigned, const T*, size_t, const T*, size_t, T*, size_t, unsigned, size_t, cudaStream_t); \
 	template void gemmNT<T>(unsigned, unsigned, unsigned, const T*, size_t, const T*, size_t, T*, size_t, unsigned, size_t, cudaStream_t); \
-	template void sumSplits<T>(unsigned, unsigned, const T*, size_t, unsigned, size_t, T*, size_t, cudaStream_t, const unsigned char*, bool); \
+	template void sumSplits<T>(unsigned, unsigned, const T*, size_t, unsigned, size_t, T*, size_t, cudaStream_t, const unsigned char*, bool, const T*); \
 	template void clampNonNegative<T>(unsigned, unsigned, T*, size_t, cudaStream_t);                                                      \
 	template void absInPlace<T>(unsigned, unsigned, T*, size_t, cudaStream_t);                                                            \
 	template void finishColumnNorms<T>(unsigned, unsigned, const T*, T*, cudaStream_t);                                                   \

@@ -34,10 +34,11 @@ unsigned effectiveSplits(unsigned reduceLen, unsigned splits);
 // Partial products written by the stream-K tensor-core kernels (tc_gemm.h) have a per-tile slot count:
 // when tileSlots != nullptr the number of partials of an element is tileSlots[t], t = its 128-wide tile
 // along the rows (tilesAlongRows) or the columns; the same convention holds for updateH (column tiles)
-// and updateW (row tiles).
+// and updateW (row tiles).  `corr` (rank entries) is the rank-one term the mean-centred tensor-core products
+// leave out (tc_gemm.h): it is added once to every element, indexed along the short dimension.
 template <typename T>
 void sumSplits(unsigned rows, unsigned cols, const T* src, size_t ldsrc, unsigned splits, size_t splitStride, T* dst, size_t lddst,
-               cudaStream_t stream, const unsigned char* tileSlots = nullptr, bool tilesAlongRows = false);
+               cudaStream_t stream, const unsigned char* tileSlots = nullptr, bool tilesAlongRows = false, const T* corr = nullptr);
 
 // ---- H side ---------------------------------------------------------------------------------------
 // Hout = Hin o N / (G Hin + eps), N = sum of `splits` partials  (MU.h:181-191, KernelMultiplyDivide.cu:42).
@@ -46,7 +47,7 @@ void sumSplits(unsigned rows, unsigned cols, const T* src, size_t ldsrc, unsigne
 template <typename T>
 void updateH(unsigned k, unsigned n, const T* G, const T* Hin, T* Hout, size_t ldh, const T* Npart, size_t ldn, unsigned splits,
              size_t splitStride, T eps, T* tracePartials, float* HtHi, float* HtLo, size_t ldht, cudaStream_t stream,
-             const unsigned char* tileSlots = nullptr);
+             const unsigned char* tileSlots = nullptr, const T* corr = nullptr);
 
 // Hout = max(0, N) after N was overwritten by the least-squares solve (GDCLS.h:206-209)
 template <typename T>
@@ -58,7 +59,8 @@ void clampNonNegative(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream
 // Returns the number of row blocks written.
 template <typename T>
 unsigned updateW(unsigned m, unsigned k, const T* B, const T* Win, T* Wout, size_t ldw, const T* Ppart, size_t ldp, unsigned splits,
-                 size_t splitStride, T eps, T* colSqPartials, cudaStream_t stream, const unsigned char* tileSlots = nullptr);
+                 size_t splitStride, T eps, T* colSqPartials, cudaStream_t stream, const unsigned char* tileSlots = nullptr,
+                 const T* corr = nullptr);
 
 // colSq[c] = sum_b colSqPartials[b][c] (fixed order) ; used by scaleColumns
 template <typename T>

@@ -39,7 +39,17 @@ struct Plan {
 	unsigned m = 0, n = 0, k = 0;
 	unsigned kp = 0;               // rank padded to the UMMA N granularity (multiple of 16, <= 128)
 	unsigned passes = 3;           // 3 = 3xTF32, 1 = single-pass TF32 (diagnostic)
-	unsigned flushStages = 8;      // reduction stages accumulated inside the tensor core before the fp32 flush
+	unsigned flushStages = 16;     // reduction stages accumulated inside the tensor core before the fp32 flush
+	// Mean centring: the kernels multiply (V - center) instead of V, so the tensor-core accumulators hover around
+	// zero instead of growing monotonically.  The tensor core truncates its fp32 accumulator after every MMA; on
+	// the all-positive data of an NMF that is a systematic -2.4e-7 per accumulated stage, on centred data it is an
+	// unbiased error of a much smaller accumulator.  The omitted rank-one terms
+	//     W^T V = W^T (V - c 1 1^T) + c (W^T 1) 1^T ,     V H^T = (V - c 1 1^T) H^T + c 1 (H 1)^T
+	// are k numbers each (corrN, corrP), recomputed in fp64 whenever W resp. H changes and added by the consumers.
+	float center = 0.f;
+	float* corrN = nullptr;        // device, [k]: center * column sums of W
+	float* corrP = nullptr;        // device, [k]: center * row sums of H
+	double* sumScratch = nullptr;
 	Product wtv, vht;
 	unsigned long long* trace = nullptr;   // device buffer of the optional kernel timeline (environment NMFGPU_TC_TRACE=<file>)
 	~Plan();
@@ -49,7 +59,15 @@ struct Plan {
 bool shapeSupported(unsigned m, unsigned n, unsigned k, size_t ldV, size_t ldW);
 
 void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, size_t ldV, const float* Whi, const float* Wlo, size_t ldW,
-              const float* HtHi, const float* HtLo, size_t ldHt, bool singlePass);
+              const float* HtHi, const float* HtLo, size_t ldHt, bool singlePass, float center);
+
+// mean of all elements of V (fp64 accumulation; synchronises the stream)
+float meanOf(const float* V, unsigned m, unsigned n, size_t ldV, cudaStream_t stream);
+
+// corrN <- center * column sums of W (m x k) ; corrP <- center * row sums of H (k x n).  Call after every change of the
+// operand the products will read (the hi/lo copies must stem from the same values).
+void refreshCorrectionW(Plan& plan, const float* W, size_t ldW, cudaStream_t stream);
+void refreshCorrectionH(Plan& plan, const float* H, size_t ldH, cudaStream_t stream);
 
 // Npart + slot*slotStride (k x n, leading dimension ldn) receives the partial products of W^T V
 void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream);
