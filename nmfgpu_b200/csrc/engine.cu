@@ -33,7 +33,7 @@ namespace b200 {
 namespace {
 unsigned pickSplits(unsigned tiles, unsigned reduceLen) {
 	// enough CTAs for two waves on 148 SMs, but never slices shorter than 64 reduction steps
-	unsigned s = ceilDiv(2 * 148, std::max(1u, tiles));
+	unsigned s = ceilDiv(148, std::max(1u, tiles));
 	s = std::min(s, std::max(1u, reduceLen / 256));
 	return std::max(1u, s);
 }

@@ -107,6 +107,24 @@ __global__ void sum_splits_kernel(unsigned rows, unsigned cols, const T* __restr
 	dst[(size_t)c * lddst + r] = s;
 }
 
+// many partials of a small matrix (the split-K Gram products): 32 elements x 8 partial groups per block
+template <typename T>
+__global__ void __launch_bounds__(256) sum_splits_small_kernel(unsigned rows, unsigned cols, const T* __restrict__ src, size_t ldsrc, unsigned splits,
+                                                              size_t splitStride, T* __restrict__ dst, size_t lddst) {
+	__shared__ T red[8][33];
+	const unsigned e = blockIdx.x * 32 + threadIdx.x % 32, g = threadIdx.x / 32;
+	const unsigned r = e % rows, c = e / rows;
+	T acc = T(0);
+	if (c < cols)
+		for (unsigned sp = g; sp < splits; sp += 8) acc += src[sp * splitStride + (size_t)c * ldsrc + r];
+	red[g][threadIdx.x % 32] = acc;
+	__syncthreads();
+	if (g == 0 && c < cols) {
+		const unsigned x = threadIdx.x;
+		dst[(size_t)c * lddst + r] = ((red[0][x] + red[1][x]) + (red[2][x] + red[3][x])) + ((red[4][x] + red[5][x]) + (red[6][x] + red[7][x]));
+	}
+}
+
 __device__ __forceinline__ float tf32_hi(float x) {
 	uint32_t u;
 	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -157,99 +175,90 @@ __global__ void __launch_bounds__(256) update_h_generic(unsigned k, unsigned n, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// H update, rank <= KP (fp32): 32 columns per block staged through shared memory; four threads share a
-// column (each holds the whole old column in registers and produces a quarter of the new one), the Gram
-// matrix sits in shared memory and is read as broadcast float4.  313 blocks at n = 10 000 fill the GPU.
+// H update, rank <= KP (fp32): a 64-column panel per block.  D = G H is a register-tiled product out of
+// shared memory (thread = KP/16 rows x 4 columns), the multiplicative update, the residual trace term and
+// the TF32 hi/lo copy of the new H^T are its epilogue.
 // ---------------------------------------------------------------------------------------------------
 template <int KP>
-__global__ void __launch_bounds__(128) update_h_reg(unsigned k, unsigned n, const float* __restrict__ G, const float* __restrict__ Hin,
+__global__ void __launch_bounds__(256) update_h_reg(unsigned k, unsigned n, const float* __restrict__ G, const float* __restrict__ Hin,
                                                    float* __restrict__ Hout, size_t ldh, const float* __restrict__ Npart, size_t ldn,
                                                    unsigned splits, size_t splitStride, float eps, float* __restrict__ tracePartials,
                                                    float* __restrict__ HtHi, float* __restrict__ HtLo, size_t ldht,
                                                    const unsigned char* __restrict__ tileSlots, const float* __restrict__ corr) {
-	constexpr int COLS = 32, LD = KP + 1, RPT = KP / 4;   // rows of the new column per thread
+	constexpr int COLS = 64, RPT = KP / 16, LDJ = COLS + 4;
 	const unsigned j0 = blockIdx.x * COLS;
 	if (tileSlots != nullptr) splits = tileSlots[j0 >> 7];
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	float* Gs = reinterpret_cast<float*>(smem_raw);  // [KP][KP]: Gs[r*KP + t] = G[r + t*k]
-	float* Ht = Gs + KP * KP;                         // [COLS][LD] old H
-	float* Nt = Ht + COLS * LD;                       // [COLS][LD] numerator, then new H
+	float* Gs = reinterpret_cast<float*>(smem_raw);  // [KP t][KP r]: Gs[t*KP + r] = G[r + t*k]
+	float* Hs = Gs + KP * KP;                         // [KP t][LDJ]:  Hs[t*LDJ + j] = H[t, j0 + j]
 	const unsigned tid = threadIdx.x;
-	for (unsigned idx = tid; idx < KP * KP; idx += 128) {
-		const unsigned t = idx % KP, r = idx / KP;
+	for (unsigned idx = tid; idx < KP * KP; idx += 256) {
+		const unsigned r = idx % KP, t = idx / KP;
 		Gs[idx] = (r < k && t < k) ? G[(size_t)t * k + r] : 0.f;
 	}
-	constexpr int PER = COLS * KP / 128;
-	float hv[PER], nv[PER];
-#pragma unroll
-	for (int e = 0; e < PER; ++e) {   // all loads of this thread in flight before the first use
-		const unsigned idx = tid + e * 128;
-		const unsigned t = idx % KP, j = j0 + idx / KP;
-		const bool ok = j < n && t < k;
-		hv[e] = ok ? Hin[(size_t)j * ldh + t] : 0.f;
-		nv[e] = ok ? Npart[(size_t)j * ldn + t] + (corr != nullptr ? corr[t] : 0.f) : 0.f;
-	}
-	for (unsigned sl = 1; sl < splits; ++sl) {
-#pragma unroll
-		for (int e = 0; e < PER; ++e) {
-			const unsigned idx = tid + e * 128;
-			const unsigned t = idx % KP, j = j0 + idx / KP;
-			if (j < n && t < k) nv[e] += Npart[sl * splitStride + (size_t)j * ldn + t];
-		}
-	}
-#pragma unroll
-	for (int e = 0; e < PER; ++e) {
-		const unsigned idx = tid + e * 128;
-		Ht[(idx / KP) * LD + idx % KP] = hv[e];
-		Nt[(idx / KP) * LD + idx % KP] = nv[e];
+	for (unsigned idx = tid; idx < COLS * KP; idx += 256) {
+		const unsigned t = idx % KP, j = idx / KP;
+		Hs[t * LDJ + j] = (j0 + j < n && t < k) ? Hin[(size_t)(j0 + j) * ldh + t] : 0.f;
 	}
 	__syncthreads();
-	const unsigned col = tid / 4, part = tid % 4;
-	float h[KP];
+	const unsigned rx = tid % 16, jx = tid / 16;      // rows rx*RPT.., columns jx*4..
+	float acc[RPT][4];
 #pragma unroll
-	for (int t = 0; t < KP; ++t) h[t] = Ht[col * LD + t];
-	float tr = 0.f;
-	float out[RPT];
+	for (int i = 0; i < RPT; ++i)
 #pragma unroll
-	for (int rr = 0; rr < RPT; ++rr) {
-		const unsigned r = part * RPT + rr;
-		const float4* g4 = reinterpret_cast<const float4*>(Gs + r * KP);
-		float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+		for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+#pragma unroll 8
+	for (int t = 0; t < KP; ++t) {
+		float a[RPT];
 #pragma unroll
-		for (int q = 0; q < KP / 4; ++q) {
-			const float4 g = g4[q];
-			d0 = fmaf(g.x, h[4 * q + 0], d0);
-			d1 = fmaf(g.y, h[4 * q + 1], d1);
-			d2 = fmaf(g.z, h[4 * q + 2], d2);
-			d3 = fmaf(g.w, h[4 * q + 3], d3);
+		for (int i = 0; i < RPT; ++i) a[i] = Gs[t * KP + rx * RPT + i];
+		const float4 b = *reinterpret_cast<const float4*>(Hs + t * LDJ + jx * 4);
+#pragma unroll
+		for (int i = 0; i < RPT; ++i) {
+			acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+			acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+			acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+			acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
 		}
-		const float d = (d0 + d1) + (d2 + d3);
-		const float num = Nt[col * LD + r];
-		const float hn = Ht[col * LD + r] * num / (d + eps);
-		tr = fmaf(hn, num, tr);
-		out[rr] = hn;
 	}
-	tr += __shfl_xor_sync(0xffffffffu, tr, 1);
-	tr += __shfl_xor_sync(0xffffffffu, tr, 2);
-	if (tracePartials != nullptr && part == 0 && j0 + col < n) tracePartials[j0 + col] = tr;
-	__syncthreads();   // every thread has read its numerators: Nt now receives the new column
+	float hn[RPT][4];
 #pragma unroll
-	for (int rr = 0; rr < RPT; ++rr) Nt[col * LD + part * RPT + rr] = out[rr];
-	__syncthreads();
-	for (unsigned idx = tid; idx < COLS * KP; idx += 128) {
-		const unsigned t = idx % KP, c = idx / KP;
-		const unsigned j = j0 + c;
-		if (j < n && t < k) Hout[(size_t)j * ldh + t] = Nt[c * LD + t];
+	for (int q = 0; q < 4; ++q) {
+		const unsigned j = j0 + jx * 4 + q;
+		float tr = 0.f;
+#pragma unroll
+		for (int i = 0; i < RPT; ++i) {
+			const unsigned r = rx * RPT + i;
+			float num = 0.f, h = 0.f;
+			if (j < n && r < k) {
+				num = corr != nullptr ? corr[r] : 0.f;
+				for (unsigned sl = 0; sl < splits; ++sl) num += Npart[sl * splitStride + (size_t)j * ldn + r];
+				h = Hs[r * LDJ + jx * 4 + q];
+			}
+			const float v = h * num / (acc[i][q] + eps);
+			hn[i][q] = v;
+			tr = fmaf(v, num, tr);
+			if (j < n && r < k) Hout[(size_t)j * ldh + r] = v;
+		}
+		tr += __shfl_xor_sync(0xffffffffu, tr, 1);
+		tr += __shfl_xor_sync(0xffffffffu, tr, 2);
+		tr += __shfl_xor_sync(0xffffffffu, tr, 4);
+		tr += __shfl_xor_sync(0xffffffffu, tr, 8);
+		if (tracePartials != nullptr && rx == 0 && j < n) tracePartials[j] = tr;
 	}
 	if (HtHi != nullptr) {
-		for (unsigned idx = tid; idx < COLS * KP; idx += 128) {
-			const unsigned c = idx % COLS, t = idx / COLS;
-			const unsigned j = j0 + c;
-			if (j < n && t < k) {
-				const float v = Nt[c * LD + t];
-				const float hi = tf32_hi(v);
-				HtHi[(size_t)t * ldht + j] = hi;
-				HtLo[(size_t)t * ldht + j] = v - hi;
+#pragma unroll
+		for (int i = 0; i < RPT; ++i) {
+			const unsigned r = rx * RPT + i;
+			if (r >= k) continue;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const unsigned j = j0 + jx * 4 + q;
+				if (j < n) {
+					const float hi = tf32_hi(hn[i][q]);
+					HtHi[(size_t)r * ldht + j] = hi;
+					HtLo[(size_t)r * ldht + j] = hn[i][q] - hi;
+				}
 			}
 		}
 	}
@@ -308,65 +317,88 @@ __global__ void __launch_bounds__(128) update_w_generic(unsigned m, unsigned k, 
 	}
 }
 
-// W update, rank <= KP (fp32): one row per thread in registers, H H^T in shared memory.  All global loads
-// of a thread (its row of W and of the partial products) are issued before the first use.
+// W update, rank <= KP (fp32): a 128-row panel per block.  D = W (H H^T) is a register-tiled product out of
+// shared memory (thread = 4 rows x KP/8 columns); the multiplicative update and the per-block column sums of
+// squares (first half of the normalisation, MU.h:247) are its epilogue.
 template <int KP>
-__global__ void __launch_bounds__(128) update_w_reg(unsigned m, unsigned k, const float* __restrict__ B, const float* __restrict__ Win,
+__global__ void __launch_bounds__(256) update_w_reg(unsigned m, unsigned k, const float* __restrict__ B, const float* __restrict__ Win,
                                                    float* __restrict__ Wout, size_t ldw, const float* __restrict__ Ppart, size_t ldp,
                                                    unsigned splits, size_t splitStride, float eps, float* __restrict__ colSqPartials,
                                                    const unsigned char* __restrict__ tileSlots, const float* __restrict__ corr) {
+	constexpr int ROWS = 128, CPT = KP / 8;
 	if (tileSlots != nullptr) splits = tileSlots[blockIdx.x];
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	float* Bs = reinterpret_cast<float*>(smem_raw);  // [KP][KP]: Bs[c*KP + t] = B[t + c*k]
-	float* sq = Bs + KP * KP;                         // [4][KP]
-	const unsigned tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
-	const unsigned i = blockIdx.x * 128 + tid;
-	const bool valid = i < m;
-	float w[KP], pv[KP];
-#pragma unroll
-	for (int t = 0; t < KP; ++t) {
-		const bool ok = valid && t < (int)k;
-		w[t] = ok ? Win[(size_t)t * ldw + i] : 0.f;
-		pv[t] = ok ? Ppart[(size_t)t * ldp + i] + (corr != nullptr ? corr[t] : 0.f) : 0.f;
+	float* Ws = reinterpret_cast<float*>(smem_raw);  // [KP t][ROWS]: Ws[t*ROWS + r] = W[i0 + r, t]
+	float* Bs = Ws + KP * ROWS;                       // [KP t][KP c]: Bs[t*KP + c] = B[t + c*k]
+	const unsigned tid = threadIdx.x;
+	const unsigned i0 = blockIdx.x * ROWS;
+	for (unsigned idx = tid; idx < KP * ROWS; idx += 256) {
+		const unsigned r = idx % ROWS, t = idx / ROWS;
+		Ws[idx] = (i0 + r < m && t < k) ? Win[(size_t)t * ldw + i0 + r] : 0.f;
 	}
-	for (unsigned idx = tid; idx < KP * KP; idx += 128) {
-		const unsigned t = idx % KP, c = idx / KP;
+	for (unsigned idx = tid; idx < KP * KP; idx += 256) {
+		const unsigned c = idx % KP, t = idx / KP;
 		Bs[idx] = (c < k && t < k) ? B[(size_t)c * k + t] : 0.f;
 	}
-	for (unsigned sl = 1; sl < splits; ++sl) {
-#pragma unroll
-		for (int t = 0; t < KP; ++t)
-			if (valid && t < (int)k) pv[t] += Ppart[sl * splitStride + (size_t)t * ldp + i];
-	}
 	__syncthreads();
+	const unsigned tx = tid % 32, ty = tid / 32;      // rows tx*4.., columns ty*CPT..
+	float acc[4][CPT];
 #pragma unroll
-	for (int c = 0; c < KP; ++c) {
-		if (c < (int)k) {   // block-uniform
-			const float4* b4 = reinterpret_cast<const float4*>(Bs + c * KP);
-			float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+	for (int i = 0; i < 4; ++i)
 #pragma unroll
-			for (int q = 0; q < KP / 4; ++q) {
-				const float4 b = b4[q];
-				d0 = fmaf(w[4 * q + 0], b.x, d0);
-				d1 = fmaf(w[4 * q + 1], b.y, d1);
-				d2 = fmaf(w[4 * q + 2], b.z, d2);
-				d3 = fmaf(w[4 * q + 3], b.w, d3);
-			}
-			const float d = (d0 + d1) + (d2 + d3);
-			float wn = 0.f;
-			if (valid) {
-				wn = w[c] * pv[c] / (d + eps);
-				Wout[(size_t)c * ldw + i] = wn;
-			}
-			float s2 = wn * wn;
+		for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+	for (int t = 0; t < KP; ++t) {
+		const float4 a = *reinterpret_cast<const float4*>(Ws + t * ROWS + tx * 4);
+		float b[CPT];
 #pragma unroll
-			for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-			if (lane == 0) sq[warp * KP + c] = s2;
+		for (int j = 0; j < CPT; ++j) b[j] = Bs[t * KP + ty * CPT + j];
+#pragma unroll
+		for (int j = 0; j < CPT; ++j) {
+			acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
+			acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
+			acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
+			acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
 		}
 	}
-	__syncthreads();
-	for (unsigned c = tid; c < k; c += 128)
-		colSqPartials[(size_t)blockIdx.x * k + c] = (sq[c] + sq[KP + c]) + (sq[2 * KP + c] + sq[3 * KP + c]);
+	const unsigned r0 = i0 + tx * 4;
+#pragma unroll
+	for (int j = 0; j < CPT; ++j) {
+		const unsigned c = ty * CPT + j;
+		float s2 = 0.f;
+		if (c < k) {   // warp-uniform
+			const float base = corr != nullptr ? corr[c] : 0.f;
+			float p[4] = {base, base, base, base};
+			if (r0 + 3 < m) {
+				for (unsigned sl = 0; sl < splits; ++sl) {
+					const float4 x = *reinterpret_cast<const float4*>(Ppart + sl * splitStride + (size_t)c * ldp + r0);
+					p[0] += x.x; p[1] += x.y; p[2] += x.z; p[3] += x.w;
+				}
+			} else {
+				for (unsigned sl = 0; sl < splits; ++sl)
+					for (int i = 0; i < 4; ++i)
+						if (r0 + i < m) p[i] += Ppart[sl * splitStride + (size_t)c * ldp + r0 + i];
+			}
+			const float4 w = *reinterpret_cast<const float4*>(Ws + c * ROWS + tx * 4);
+			float wn[4];
+			wn[0] = w.x * p[0] / (acc[0][j] + eps);
+			wn[1] = w.y * p[1] / (acc[1][j] + eps);
+			wn[2] = w.z * p[2] / (acc[2][j] + eps);
+			wn[3] = w.w * p[3] / (acc[3][j] + eps);
+			if (r0 + 3 < m) {
+				*reinterpret_cast<float4*>(Wout + (size_t)c * ldw + r0) = make_float4(wn[0], wn[1], wn[2], wn[3]);
+			} else {
+				for (int i = 0; i < 4; ++i) {
+					if (r0 + i < m) Wout[(size_t)c * ldw + r0 + i] = wn[i];
+					else wn[i] = 0.f;
+				}
+			}
+			s2 = (wn[0] * wn[0] + wn[1] * wn[1]) + (wn[2] * wn[2] + wn[3] * wn[3]);
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+		if (tx == 0 && c < k) colSqPartials[(size_t)blockIdx.x * k + c] = s2;
+	}
 }
 
 template <typename T>
@@ -667,6 +699,11 @@ unsigned effectiveSplits(unsigned reduceLen, unsigned splits) {
 template <typename T>
 void sumSplits(unsigned rows, unsigned cols, const T* src, size_t ldsrc, unsigned splits, size_t splitStride, T* dst, size_t lddst,
                cudaStream_t stream, const unsigned char* tileSlots, bool tilesAlongRows, const T* corr) {
+	if (tileSlots == nullptr && corr == nullptr && splits > 8 && (size_t)rows * cols <= 65536) {
+		sum_splits_small_kernel<T><<<ceilDiv(rows * cols, 32), 256, 0, stream>>>(rows, cols, src, ldsrc, splits, splitStride, dst, lddst);
+		launchCheck();
+		return;
+	}
 	dim3 grid(ceilDiv(rows, 128), cols);
 	sum_splits_kernel<T><<<grid, 128, 0, stream>>>(rows, cols, src, ldsrc, splits, splitStride, dst, lddst, tileSlots, tilesAlongRows, corr);
 	launchCheck();
@@ -687,9 +724,9 @@ template <int KP>
 static void updateHReg(unsigned k, unsigned n, const float* G, const float* Hin, float* Hout, size_t ldh, const float* Npart, size_t ldn,
                        unsigned splits, size_t splitStride, float eps, float* tracePartials, float* HtHi, float* HtLo, size_t ldht,
                        cudaStream_t stream, const unsigned char* tileSlots, const float* corr) {
-	const size_t smem = sizeof(float) * ((size_t)KP * KP + 2 * 32 * (KP + 1));
+	const size_t smem = sizeof(float) * ((size_t)KP * KP + (size_t)KP * (64 + 4));
 	allowSmem(update_h_reg<KP>, smem);
-	update_h_reg<KP><<<ceilDiv(n, 32), 128, smem, stream>>>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials,
+	update_h_reg<KP><<<ceilDiv(n, 64), 256, smem, stream>>>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials,
 	                                                          HtHi, HtLo, ldht, tileSlots, corr);
 	launchCheck();
 }
@@ -732,10 +769,10 @@ template <int KP>
 static unsigned updateWReg(unsigned m, unsigned k, const float* B, const float* Win, float* Wout, size_t ldw, const float* Ppart,
                            size_t ldp, unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream,
                            const unsigned char* tileSlots, const float* corr) {
-	const size_t smem = sizeof(float) * ((size_t)KP * KP + 4 * KP);
+	const size_t smem = sizeof(float) * ((size_t)KP * KP + (size_t)KP * 128);
 	allowSmem(update_w_reg<KP>, smem);
 	const unsigned blocks = ceilDiv(m, 128);
-	update_w_reg<KP><<<blocks, 128, smem, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots, corr);
+	update_w_reg<KP><<<blocks, 256, smem, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots, corr);
 	launchCheck();
 	return blocks;
 }

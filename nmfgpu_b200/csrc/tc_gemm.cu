@@ -605,8 +605,16 @@ __global__ void __launch_bounds__(256) column_sums_stage1(unsigned rows, unsigne
 	const unsigned c = blockIdx.x, s = blockIdx.y;
 	const unsigned begin = s * chunk, end = min(rows, begin + chunk);
 	const float* a = A + (size_t)c * lda;
-	double acc = 0.0;
-	for (unsigned i = begin + threadIdx.x; i < end; i += 256) acc += (double)a[i];
+	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+	unsigned i = begin + threadIdx.x;
+	for (; i + 768 < end; i += 1024) {
+		a0 += (double)a[i];
+		a1 += (double)a[i + 256];
+		a2 += (double)a[i + 512];
+		a3 += (double)a[i + 768];
+	}
+	for (; i < end; i += 256) a0 += (double)a[i];
+	double acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
 	if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
@@ -620,8 +628,18 @@ __global__ void __launch_bounds__(256) row_sums_stage1(unsigned rows, unsigned c
 	const unsigned r = threadIdx.x % rp, part = threadIdx.x / rp, parts = 256 / rp;
 	const unsigned begin = blockIdx.x * chunk, end = min(cols, begin + chunk);
 	double acc = 0.0;
-	if (r < rows)
-		for (unsigned j = begin + part; j < end; j += parts) acc += (double)H[(size_t)j * ldh + r];
+	if (r < rows) {
+		double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // independent chains: the loads of a thread overlap
+		unsigned j = begin + part;
+		for (; j + 3 * parts < end; j += 4 * parts) {
+			a0 += (double)H[(size_t)j * ldh + r];
+			a1 += (double)H[(size_t)(j + parts) * ldh + r];
+			a2 += (double)H[(size_t)(j + 2 * parts) * ldh + r];
+			a3 += (double)H[(size_t)(j + 3 * parts) * ldh + r];
+		}
+		for (; j < end; j += parts) a0 += (double)H[(size_t)j * ldh + r];
+		acc = (a0 + a1) + (a2 + a3);
+	}
 	red[threadIdx.x] = acc;
 	__syncthreads();
 	if (part == 0 && r < rows) {
@@ -636,7 +654,7 @@ __global__ void sums_stage2(unsigned count, unsigned slices, const double* __res
 	for (unsigned s = 0; s < slices; ++s) acc += partial[(size_t)s * count + x];
 	out[x] = (float)((double)scale * acc);
 }
-constexpr unsigned SUM_SLICES = 32;
+constexpr unsigned SUM_SLICES = 32, ROW_SUM_SLICES = 128;
 
 // ---- host side -----------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -757,9 +775,9 @@ void refreshCorrectionW(Plan& plan, const float* W, size_t ldW, cudaStream_t str
 }
 
 void refreshCorrectionH(Plan& plan, const float* H, size_t ldH, cudaStream_t stream) {
-	const unsigned chunk = ceilDiv(plan.n, SUM_SLICES);
-	row_sums_stage1<<<SUM_SLICES, 256, 0, stream>>>(plan.k, plan.n, H, ldH, chunk, plan.sumScratch);
-	sums_stage2<<<1, 128, 0, stream>>>(plan.k, SUM_SLICES, plan.sumScratch, plan.center, plan.corrP);
+	const unsigned chunk = ceilDiv(plan.n, ROW_SUM_SLICES);
+	row_sums_stage1<<<ROW_SUM_SLICES, 256, 0, stream>>>(plan.k, plan.n, H, ldH, chunk, plan.sumScratch);
+	sums_stage2<<<1, 128, 0, stream>>>(plan.k, ROW_SUM_SLICES, plan.sumScratch, plan.center, plan.corrP);
 	CUDA_CHECK(cudaGetLastError());
 }
 
@@ -814,7 +832,7 @@ void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, si
 	if (plan.corrN == nullptr) {
 		CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&plan.corrN), 128 * sizeof(float)));
 		CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&plan.corrP), 128 * sizeof(float)));
-		CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&plan.sumScratch), (size_t)SUM_SLICES * 128 * sizeof(double)));
+		CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&plan.sumScratch), (size_t)ROW_SUM_SLICES * 128 * sizeof(double)));
 		CUDA_CHECK(cudaMemset(plan.corrN, 0, 128 * sizeof(float)));
 		CUDA_CHECK(cudaMemset(plan.corrP, 0, 128 * sizeof(float)));
 	}
