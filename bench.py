@@ -52,7 +52,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + NVSMI_QUERY, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
 
@@ -200,11 +200,11 @@ def run_ours(args, rank, world, local):
     H0 = uniform_block(SEED_H, K, nloc, total_rows=K, col0=c0)
     s = api.Session(L, "mu", M, nloc, K, device_ptr=dev, ld_v=ld)
     s.set_factors(W0, H0)
+    sampler = ClockSampler(local) if rank == 0 else None      # started before the warm-up: nvidia-smi needs ~0.1 s to produce its first line
     s.iterate(args.warmup)
     s.synchronize()
     info0 = s.info()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     ms = s.time_iterations(args.steps)          # CUDA events on the engine's stream around exactly K iterations
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -234,7 +234,7 @@ def run_ours(args, rank, world, local):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(name.split()[0])
+            traffic = json.load(open(tpath)).get(name.split()[0]) if world == 1 else None   # the capture is of the full 100k x 10k launch
         achieved = by / (tms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "peak_source": how, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "bytes_per_launch": by, "ms_per_launch": tms,
@@ -299,8 +299,8 @@ def run_ours(args, rank, world, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
