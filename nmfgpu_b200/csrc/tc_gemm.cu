@@ -41,13 +41,12 @@ namespace tc {
 namespace {
 
 constexpr int TILE_ROWS = 128;        // A rows per tile (= TMEM lanes)
-constexpr int STAGE_K = 32;           // reduction elements per stage (128 bytes of fp32: one swizzle row)
+constexpr int HALF_K = 32;            // reduction elements per TMA box / swizzle row (128 bytes of fp32)
+constexpr int STAGE_K = 64;           // reduction elements per stage: two halves, so every barrier hop covers 2 x 12 MMAs
+constexpr int V_HALF_BYTES = TILE_ROWS * HALF_K * 4;
 constexpr int V_STAGE_BYTES = TILE_ROWS * STAGE_K * 4;
 constexpr int PAIR_ROWS = 2 * TILE_ROWS;   // A rows per stream-K tile: two UMMA tiles that share their B tiles
-constexpr int SLOTS = 4;              // TMEM A operand ring, in tiles (64 columns each: 32 hi + 32 lo)
-constexpr int SLOTS_SHIFT = 2;
-constexpr int SV = 8;                 // shared-memory ring of V tiles (16 KB each): 4 stages of 2 tiles
-constexpr int SV_SHIFT = 3;
+constexpr int SLOTS = 2;              // TMEM A operand slots: one per A tile / worker warpgroup (128 columns: 64 hi + 64 lo)
 constexpr int A_BASE_COL = 256;       // TMEM columns [0, 256): accumulators, [256, 512): A slots
 constexpr int NUM_THREADS = 384;
 constexpr int HELPER_REGS = 72, WORKER_REGS = 216;   // 128 * 72 + 256 * 216 = 64512 <= 384 * 168
@@ -57,9 +56,10 @@ constexpr uint64_t POLICY_EVICT_LAST = 0x14F0000000000000ull;
 template <int KPM> struct Rings;
 // shared-memory rings: SV tiles of V (16 KB each) and SB tile pairs of B (hi + lo, KPM x 32 fp32 each).  Both
 // must cover the loaded TMA latency (~2700 cycles measured under full HBM traffic) at one stage per 400-650 cycles.
-// SB: shared-memory ring of B tile pairs (hi + lo, KPM x 32 fp32 each); ACC_BUFS: accumulator buffers per A tile
-template <> struct Rings<64> { static constexpr int SB = 4, ACC_BUFS = 2; };
-template <> struct Rings<128> { static constexpr int SB = 2, ACC_BUFS = 1; };
+// SV: shared-memory ring of V tiles (32 KB each, two per stage); SB: ring of B stages (hi and lo, two K halves:
+// 4 x KPM x 32 fp32); ACC_BUFS: accumulator buffers per A tile
+template <> struct Rings<64> { static constexpr int SV = 4, SV_SHIFT = 2, SB = 2, ACC_BUFS = 2; };
+template <> struct Rings<128> { static constexpr int SV = 2, SV_SHIFT = 1, SB = 2, ACC_BUFS = 1; };
 
 // position in a ring of arbitrary depth: slot index plus the parity of the number of completed laps
 struct RingPos {
@@ -81,6 +81,7 @@ struct KParams {
 	unsigned long long ldOut, slotStride, units;
 	unsigned rowsA, k, kp, tiles, stagesPerTile, flushStages, passes, grid;
 	float center;   // subtracted from every element of V before the split (see tc_gemm.h)
+	unsigned prefetchStages;   // how many stages ahead of the TMA loads the V tiles are prefetched into L2
 };
 
 // ---- stream-K bookkeeping shared by host and device ---------------------------------------------------
@@ -152,6 +153,9 @@ __device__ __forceinline__ void tmaLoad2D(uint32_t dst, const CUtensorMap* map, 
 	    "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
 	    : "memory");
 }
+__device__ __forceinline__ void tmaPrefetchL2(const CUtensorMap* map, int c0, int c1) {
+	asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ bool electOne() {
 	uint32_t pred;
 	asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -219,27 +223,28 @@ __device__ __forceinline__ void traceEvent(unsigned long long* trace, unsigned g
 }
 
 struct __align__(8) Barriers {
-	uint64_t vFull[SV], vEmpty[SV];        // V tile ring: TMA -> workers
-	uint64_t bFull[4], bEmpty[4];          // B tile ring: TMA -> MMA
+	uint64_t vFull[4], vEmpty[4];          // V tile ring: TMA -> workers
+	uint64_t bFull[4], bEmpty[4];          // B stage ring: TMA -> MMA
 	uint64_t full[SLOTS], empty[SLOTS];    // A operand slots in tensor memory: workers -> MMA
 	uint64_t accFull[2], accEmpty[2];      // accumulator buffers: MMA -> workers
 	uint32_t tmemBase;
 };
 
 // ---- the kernel ----------------------------------------------------------------------------------------
-// V_COLS_ARE_ROWS = true : W^T V (A rows are columns of V; V tile in smem is [128 cols][32 rows], 128B swizzle)
-//                 = false: V H^T (A rows are rows of V;    V tile in smem is [32 cols][128 rows], linear)
-// Counters: g = stage of this CTA (a stage = 32 reduction elements of one 256-row pair tile), tile step
-// t = 2 g + w for the A tile w of that stage; V ring slot = t mod 8, A slot = t mod 4, B slot = g mod SB.
+// V_COLS_ARE_ROWS = true : W^T V (A rows are columns of V; a V tile in smem is two [128 cols][32 rows] halves, 128B swizzle)
+//                 = false: V H^T (A rows are rows of V;    a V tile in smem is [64 cols][128 rows], linear)
+// Counters: g = stage of this CTA (64 reduction elements of one 256-row pair tile), tile step t = 2 g + w for
+// A tile w; V ring slot = t mod SV, A slot = w, B slot = g mod SB.
 template <int KPM, bool V_COLS_ARE_ROWS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_constant__ KParams p) {
-	constexpr int SB = Rings<KPM>::SB, ACC_BUFS = Rings<KPM>::ACC_BUFS;
-	constexpr int B_HALF_BYTES = KPM * STAGE_K * 4;
+	constexpr int SV = Rings<KPM>::SV, SV_SHIFT = Rings<KPM>::SV_SHIFT, SB = Rings<KPM>::SB, ACC_BUFS = Rings<KPM>::ACC_BUFS;
+	constexpr int B_PART_BYTES = KPM * HALF_K * 4;            // one of {hi, lo} x {K half 0, 1}
+	constexpr int B_STAGE_BYTES = 4 * B_PART_BYTES;
 	extern __shared__ unsigned char smemRaw[];
 	unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~(uintptr_t)1023);
 	unsigned char* vRing = smem;
 	unsigned char* bRing = smem + SV * V_STAGE_BYTES;
-	Barriers* bars = reinterpret_cast<Barriers*>(bRing + SB * 2 * B_HALF_BYTES);
+	Barriers* bars = reinterpret_cast<Barriers*>(bRing + SB * B_STAGE_BYTES);
 
 	const unsigned warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 	const unsigned F = p.flushStages;
@@ -286,55 +291,72 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 			Segment s;
 			unsigned t = 0;
 			const uint32_t vBase = smemAddr(vRing);
+			// L2 prefetch cursor: runs `prefetchStages` stages ahead of the loads, so a TMA load finds its tile in L2 and
+			// the shared-memory ring only has to cover the L2 latency, not the loaded HBM latency (3-4 us measured)
+			SegmentWalker ahead(p, blockIdx.x);
+			Segment sa;
+			unsigned la = 0;
+			bool more = ahead.next(sa);
+			auto prefetchOne = [&]() {
+				if (!more) return;
+				const int rA = (int)(sa.tile * PAIR_ROWS), kA = (int)((sa.stage0 + la) * STAGE_K);
+				if (V_COLS_ARE_ROWS) {
+					tmaPrefetchL2(&p.mapV, kA, rA);
+					tmaPrefetchL2(&p.mapV, kA + HALF_K, rA);
+					tmaPrefetchL2(&p.mapV, kA, rA + TILE_ROWS);
+					tmaPrefetchL2(&p.mapV, kA + HALF_K, rA + TILE_ROWS);
+				} else {
+					tmaPrefetchL2(&p.mapV, rA, kA);
+					tmaPrefetchL2(&p.mapV, rA + TILE_ROWS, kA);
+				}
+				if (++la == sa.len) {
+					la = 0;
+					more = ahead.next(sa);
+				}
+			};
+			for (unsigned i = 0; i < p.prefetchStages; ++i) prefetchOne();
 			while (walk.next(s)) {
 				const int rIdx = (int)(s.tile * PAIR_ROWS);
 				int kIdx = (int)(s.stage0 * STAGE_K);
 				for (unsigned ls = 0; ls < s.len; ++ls, kIdx += STAGE_K) {
+					if (p.prefetchStages) prefetchOne();
 #pragma unroll
 					for (int w = 0; w < 2; ++w, ++t) {
 						const unsigned sv = t & (SV - 1);
 						mbarWait(vEmptyBar + sv * 8, ((t >> SV_SHIFT) & 1) ^ 1);
-						if (w == 0) traceEvent(p.trace, t >> 1, 8);
 						const uint32_t full = vFullBar + sv * 8;
-#ifdef NMFGPU_TC_TRACE_BUILD
-						if (p.passes & 0x2000) {
-							mbarArrive(full);
-							continue;
-						}
-#endif
 						mbarArriveExpectTx(full, V_STAGE_BYTES);
-						if (V_COLS_ARE_ROWS) tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, kIdx, rIdx + w * TILE_ROWS, POLICY_EVICT_FIRST);
-						else tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, rIdx + w * TILE_ROWS, kIdx, POLICY_EVICT_FIRST);
+						const uint32_t dst = vBase + sv * V_STAGE_BYTES;
+						if (V_COLS_ARE_ROWS) {
+							tmaLoad2D(dst, &p.mapV, full, kIdx, rIdx + w * TILE_ROWS, POLICY_EVICT_FIRST);
+							tmaLoad2D(dst + V_HALF_BYTES, &p.mapV, full, kIdx + HALF_K, rIdx + w * TILE_ROWS, POLICY_EVICT_FIRST);
+						} else {
+							tmaLoad2D(dst, &p.mapV, full, rIdx + w * TILE_ROWS, kIdx, POLICY_EVICT_FIRST);
+						}
 					}
 				}
 			}
 		}
 	} else if (warp == 2) {
-		// ===== B producer (hi and lo tiles of W resp. H^T) =====
+		// ===== B producer (hi and lo tiles of W resp. H^T, two K halves each) =====
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS));
 		if (lane == 0) {
 			SegmentWalker walk(p, blockIdx.x);
 			Segment s;
 			RingPos b;
-			unsigned g = 0;
-			const uint32_t bytes = 2u * p.kp * STAGE_K * 4u;
+			const uint32_t bytes = 4u * p.kp * HALF_K * 4u;
 			const uint32_t bBase = smemAddr(bRing);
 			while (walk.next(s)) {
 				int kIdx = (int)(s.stage0 * STAGE_K);
-				for (unsigned ls = 0; ls < s.len; ++ls, kIdx += STAGE_K, b.advance(SB), ++g) {
+				for (unsigned ls = 0; ls < s.len; ++ls, kIdx += STAGE_K, b.advance(SB)) {
 					mbarWait(bEmptyBar + b.idx * 8, b.lap ^ 1);
-					traceEvent(p.trace, g, 7);
 					const uint32_t full = bFullBar + b.idx * 8;
-#ifdef NMFGPU_TC_TRACE_BUILD
-					if (p.passes & 0x1000) {
-						mbarArrive(full);
-						continue;
-					}
-#endif
 					mbarArriveExpectTx(full, bytes);
-					const uint32_t dst = bBase + b.idx * 2 * B_HALF_BYTES;
+					const uint32_t dst = bBase + b.idx * B_STAGE_BYTES;
 					tmaLoad2D(dst, &p.mapBhi, full, kIdx, 0, POLICY_EVICT_LAST);
-					tmaLoad2D(dst + B_HALF_BYTES, &p.mapBlo, full, kIdx, 0, POLICY_EVICT_LAST);
+					tmaLoad2D(dst + B_PART_BYTES, &p.mapBhi, full, kIdx + HALF_K, 0, POLICY_EVICT_LAST);
+					tmaLoad2D(dst + 2 * B_PART_BYTES, &p.mapBlo, full, kIdx, 0, POLICY_EVICT_LAST);
+					tmaLoad2D(dst + 3 * B_PART_BYTES, &p.mapBlo, full, kIdx + HALF_K, 0, POLICY_EVICT_LAST);
 				}
 			}
 		}
@@ -342,9 +364,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 		// ===== MMA issuers: warp 1 feeds A tile 0 of every stage, warp 3 A tile 1 (separate accumulators) =====
 		// Each warp walks its loop convergently so that every address and descriptor lives in uniform registers
 		// (a divergent single-thread loop costs ~140 cycles per MMA in R2UR traffic); one elected lane issues the
-		// 12 MMAs of a tile back to back.  Issuing blocks for about as long as the MMAs execute and every barrier
-		// probe costs ~100 cycles, so one issuer leaves the tensor pipe idle during its waits (measured: 2000
-		// cycles per stage for 768 cycles of MMA); two issuers cover each other's waits.
+		// 24 MMAs of a tile back to back.  Issuing blocks for about as long as the MMAs execute and every barrier
+		// probe costs ~100 cycles, so one issuer leaves the tensor pipe idle during its waits; two issuers cover
+		// each other's waits.
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS));
 		const unsigned w = warp == 1 ? 0u : 1u;
 		const bool leader = electOne();
@@ -352,16 +374,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 		const uint32_t iDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((p.kp >> 3) << 17) | ((TILE_ROWS >> 4) << 24);
 		const uint64_t bDesc0 = smemDescSw128(smemAddr(bRing));
 		const bool threePass = (p.passes & 0xFF) == 3;
-#ifdef NMFGPU_TC_TRACE_BUILD
-		const bool skipMma = (p.passes & 0x100) != 0;
-#else
-		constexpr bool skipMma = false;
-#endif
-#ifdef NMFGPU_TC_TRACE_BUILD
-		const bool tracing = leader && w == 0;
-#else
-		constexpr bool tracing = false;
-#endif
+		const uint32_t aHi = tmem + A_BASE_COL + w * 128, aLo = aHi + 64;
 		SegmentWalker walk(p, blockIdx.x);
 		Segment s;
 		unsigned g = 0, gc = 0;
@@ -373,31 +386,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 					buf = gc % ACC_BUFS;
 					mbarWait(accEmptyBar + buf * 8, (((gc / ACC_BUFS) & 1) ^ 1));
 				}
-				const unsigned t = 2 * g + w, sl = t & (SLOTS - 1);
 				mbarWait(bFullBar + b.idx * 8, b.lap);
-				if (tracing) traceEvent(p.trace, g, 6);
-				mbarWait(fullBar + sl * 8, (t >> SLOTS_SHIFT) & 1);
+				mbarWait(fullBar + w * 8, g & 1);
 				tcFenceAfter();
 				if (leader) {
-					if (tracing) traceEvent(p.trace, g, 4);
-					const uint64_t dHi = bDesc0 + (uint64_t)((b.idx * 2 * B_HALF_BYTES) >> 4), dLo = dHi + (B_HALF_BYTES >> 4);
 					const uint32_t acc = tmem + (w * ACC_BUFS + buf) * KPM;
-					const uint32_t aHi = tmem + A_BASE_COL + sl * 64, aLo = aHi + 32;
-					if (skipMma) {
-					} else if (threePass) {
+					const uint64_t dB = bDesc0 + (uint64_t)((b.idx * B_STAGE_BYTES) >> 4);
 #pragma unroll
-						for (int q = 0; q < STAGE_K / 8; ++q) {
-							mmaTf32(acc, aHi + q * 8, dHi + q * 2, iDesc, q == 0 ? (uint32_t)(inChunk != 0) : 1u);
-							mmaTf32(acc, aLo + q * 8, dHi + q * 2, iDesc, 1);
-							mmaTf32(acc, aHi + q * 8, dLo + q * 2, iDesc, 1);
+					for (int q = 0; q < STAGE_K / 8; ++q) {
+						// k-step q: A columns q*8.. ; B part (q / 4) of {hi, lo}, 32 bytes per k-step inside the swizzled row
+						const uint64_t dHi = dB + (uint64_t)(((q / 4) * B_PART_BYTES + (q % 4) * 32) >> 4);
+						const uint64_t dLo = dHi + (uint64_t)((2 * B_PART_BYTES) >> 4);
+						mmaTf32(acc, aHi + q * 8, dHi, iDesc, q == 0 ? (uint32_t)(inChunk != 0) : 1u);
+						if (threePass) {
+							mmaTf32(acc, aLo + q * 8, dHi, iDesc, 1);
+							mmaTf32(acc, aHi + q * 8, dLo, iDesc, 1);
 						}
-					} else {
-#pragma unroll
-						for (int q = 0; q < STAGE_K / 8; ++q) mmaTf32(acc, aHi + q * 8, dHi + q * 2, iDesc, q == 0 ? (uint32_t)(inChunk != 0) : 1u);
 					}
-					tcCommit(emptyBar + sl * 8);
+					tcCommit(emptyBar + w * 8);
 					tcCommit(bEmptyBar + b.idx * 8);
-					if (tracing) traceEvent(p.trace, g, 5);
 				}
 				++inChunk;
 				if (inChunk == F || ls + 1 == s.len) {
@@ -416,78 +423,62 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 		const uint32_t laneBase = ((warp % 4) * 32) << 16;
 		const unsigned kp = p.kp;
 		const float center = p.center;
-#ifdef NMFGPU_TC_TRACE_BUILD
-		const bool skipStore = (p.passes & 0x200) != 0, skipRead = (p.passes & 0x400) != 0, skipFlush = (p.passes & 0x800) != 0;
-#else
-		constexpr bool skipStore = false, skipRead = false, skipFlush = false;
-#endif
-#ifdef NMFGPU_TC_TRACE_BUILD
-		const bool tracing = row == 1 && wg == 0;   // not lane 0: its mbarrier arrivals would wait for the trace stores
-#else
-		constexpr bool tracing = false;
-#endif
+		const uint32_t aSlot = tmem + laneBase + A_BASE_COL + wg * 128;
 		float sum[KPM];
 #pragma unroll
 		for (int c = 0; c < KPM; ++c) sum[c] = 0.f;
 
-		// The worker loop is software pipelined: while the tcgen05.st of tile t drain, the V tile of this
-		// warpgroup's next stage is already read from shared memory into v[], so neither the shared-memory
-		// latency nor the TMEM store latency sits on the per-tile critical path.
-		float v[STAGE_K];
-		auto loadTile = [&](unsigned g) {
-			const unsigned t = 2 * g + wg, sv = t & (SV - 1);
-			mbarWait(vFullBar + sv * 8, (t >> SV_SHIFT) & 1);
-			if (tracing) traceEvent(p.trace, g, 0);
+		// one K half (32 values of this thread's A row) of the tile in V ring slot sv
+		float v[HALF_K];
+		auto loadHalf = [&](unsigned sv, int h) {
 			const unsigned char* tile = vRing + sv * V_STAGE_BYTES;
-			if (skipRead) {
-#pragma unroll
-				for (int j = 0; j < STAGE_K; ++j) v[j] = 1.f;
-			} else if (V_COLS_ARE_ROWS) {
-				// row `row` of the [128][32] tile; 16-byte chunk c lives at chunk c ^ (row & 7)
-				const unsigned char* base = tile + row * 128;
+			if (V_COLS_ARE_ROWS) {
+				// row `row` of the [128][32] half tile; 16-byte chunk c lives at chunk c ^ (row & 7)
+				const unsigned char* base = tile + h * V_HALF_BYTES + row * 128;
 #pragma unroll
 				for (int c = 0; c < 8; ++c) {
 					const float4 x = *reinterpret_cast<const float4*>(base + ((c ^ (row & 7)) << 4));
 					v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
 				}
 			} else {
-				const float* base = reinterpret_cast<const float*>(tile) + row;
+				const float* base = reinterpret_cast<const float*>(tile) + h * HALF_K * TILE_ROWS + row;
 #pragma unroll
-				for (int j = 0; j < STAGE_K; ++j) v[j] = base[j * TILE_ROWS];
+				for (int j = 0; j < HALF_K; ++j) v[j] = base[j * TILE_ROWS];
 			}
-			// the tile is in registers: release the slot (one arrival per warp: 128 per-thread arrivals on one
-			// mbarrier serialise in the barrier unit and delay the TMA completions that share it)
-			if (tracing) traceEvent(p.trace, g, 12);
-			__syncwarp();
-			if (lane == 0) mbarArrive(vEmptyBar + sv * 8);
-			if (tracing) traceEvent(p.trace, g, 13);
 		};
-		// split v[] (tile of stage g), store it to its A slot, prefetch the tile of stage g + 1, publish the slot
-		auto splitAndStore = [&](unsigned g, bool prefetchNext) {
-			const unsigned t = 2 * g + wg, sl = t & (SLOTS - 1);
-			uint32_t hi[STAGE_K], lo[STAGE_K];
+		// TF32 split of v[] into the A slot columns of K half h (hi at 32 h, lo at 64 + 32 h)
+		auto storeHalf = [&](int h) {
+			uint32_t hi[HALF_K], lo[HALF_K];
 #pragma unroll
-			for (int e = 0; e < STAGE_K; ++e) splitValue(v[e] - center, hi[e], lo[e]);
-			if (tracing) traceEvent(p.trace, g, 1);
-			mbarWait(emptyBar + sl * 8, ((t >> SLOTS_SHIFT) & 1) ^ 1);
+			for (int e = 0; e < HALF_K; ++e) splitValue(v[e] - center, hi[e], lo[e]);
+			tmemStore16(aSlot + 32 * h, hi);
+			tmemStore16(aSlot + 32 * h + 16, hi + 16);
+			tmemStore16(aSlot + 64 + 32 * h, lo);
+			tmemStore16(aSlot + 64 + 32 * h + 16, lo + 16);
+		};
+		auto waitTile = [&](unsigned g) {
+			const unsigned t = 2 * g + wg;
+			mbarWait(vFullBar + (t & (SV - 1)) * 8, (t >> SV_SHIFT) & 1);
+		};
+		// The loop is software pipelined: half 0 of the next stage's tile is read from shared memory while the
+		// tcgen05.st of this stage drain, so neither latency sits on the per-stage critical path.
+		auto processStage = [&](unsigned g, bool prefetchNext) {
+			const unsigned t = 2 * g + wg, sv = t & (SV - 1);
+			mbarWait(emptyBar + wg * 8, (g & 1) ^ 1);         // the issuer has consumed the previous content of the A slot
 			tcFenceAfter();
-			if (tracing) traceEvent(p.trace, g, 2);
-			const uint32_t aSlot = tmem + laneBase + A_BASE_COL + sl * 64;
-			if (!skipStore) {
-				tmemStore16(aSlot, hi);
-				tmemStore16(aSlot + 16, hi + 16);
-				tmemStore16(aSlot + 32, lo);
-				tmemStore16(aSlot + 48, lo + 16);
+			storeHalf(0);                                      // v[] holds half 0 (loaded by the previous iteration)
+			loadHalf(sv, 1);
+			__syncwarp();
+			if (lane == 0) mbarArrive(vEmptyBar + sv * 8);     // the whole tile is in registers / TMEM: release the smem slot
+			storeHalf(1);
+			if (prefetchNext) {
+				waitTile(g + 1);
+				loadHalf((t + 2) & (SV - 1), 0);
 			}
-			if (tracing) traceEvent(p.trace, g, 9);
-			if (prefetchNext) loadTile(g + 1);
-			if (tracing) traceEvent(p.trace, g, 10);
-			if (!skipStore) tmemWaitStore();
-			if (tracing) traceEvent(p.trace, g, 11);
+			tmemWaitStore();
 			tcFenceBefore();
 			__syncwarp();
-			if (lane == 0) mbarArrive(fullBar + sl * 8);
-			if (tracing) traceEvent(p.trace, g, 3);
+			if (lane == 0) mbarArrive(fullBar + wg * 8);
 		};
 
 		auto flush = [&](unsigned gc) {
@@ -497,7 +488,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 			const uint32_t acc = tmem + laneBase + (wg * ACC_BUFS + buf) * KPM;
 #pragma unroll
 			for (int q = 0; q < KPM / 32; ++q) {
-				if (q * 32 < (int)kp && !skipFlush) {
+				if (q * 32 < (int)kp) {
 					uint32_t r[32];
 					tmemLoad16(acc + q * 32, r);
 					if (q * 32 + 16 < (int)kp) tmemLoad16(acc + q * 32 + 16, r + 16);
@@ -519,18 +510,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 		Segment s;
 		unsigned gBase = 0, gcBase = 0;
 		const unsigned totalStages = (unsigned)(walk.uEnd - walk.u);
-		if (totalStages > 0) loadTile(0);
+		if (totalStages > 0) {
+			waitTile(0);
+			loadHalf(wg & (SV - 1), 0);
+		}
 		while (walk.next(s)) {
 			// chunk c of this segment covers local stages [c F, (c+1) F); both warpgroups flush every chunk
-			// (each its own tile) once they have split LOOKAHEAD stages past the chunk's end
-			// The A ring holds two stages, so a worker can get at most two stages past a chunk end while the MMA
-			// warp waits for a single-buffered accumulator: the look-ahead must stay below that or both sides block.
-			constexpr unsigned LOOKAHEAD = ACC_BUFS == 2 ? 2 : 1;
+			// (each its own tile).  With one A slot per warpgroup a worker is at most one stage ahead of its issuer,
+			// and the issuer cannot pass a chunk end before the flush when the accumulator is single-buffered:
+			// flush right after the last stage of the chunk in that case, one stage later otherwise.
+			constexpr unsigned LOOKAHEAD = ACC_BUFS == 2 ? 1 : 0;
 			const unsigned nChunks = (s.len + F - 1) / F;
 			unsigned nextChunk = 0;
 			unsigned flushAt = F - 1 + LOOKAHEAD;
 			for (unsigned ls = 0; ls < s.len; ++ls) {
-				splitAndStore(gBase + ls, gBase + ls + 1 < totalStages);
+				processStage(gBase + ls, gBase + ls + 1 < totalStages);
 				if (ls >= flushAt && nextChunk + 1 < nChunks) {
 					flush(gcBase + nextChunk);
 					++nextChunk;
@@ -571,7 +565,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 
 template <int KPM>
 size_t smemBytes() {
-	return 1024 + (size_t)SV * V_STAGE_BYTES + (size_t)Rings<KPM>::SB * 2 * KPM * STAGE_K * 4 + sizeof(Barriers);
+	return 1024 + (size_t)Rings<KPM>::SV * V_STAGE_BYTES + (size_t)Rings<KPM>::SB * 4 * KPM * HALF_K * 4 + sizeof(Barriers);
 }
 
 // ---- H -> H^T hi/lo ----------------------------------------------------------------------------------
@@ -746,6 +740,7 @@ void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, s
 	p.passes = plan.passes;
 	p.grid = prod.grid;
 	p.center = plan.center;
+	p.prefetchStages = plan.prefetchStages;
 	tc_stream_gemm<KPM, VC><<<prod.grid, NUM_THREADS, smem, stream>>>(p);
 	CUDA_CHECK(cudaGetLastError());
 }
@@ -822,8 +817,10 @@ void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, si
 	plan.k = k;
 	plan.kp = (unsigned)roundUp(k, 16);
 	plan.passes = singlePass ? 1 : 3;
+	plan.prefetchStages = 4;
+	if (const char* e = getenv("NMFGPU_TC_PREFETCH")) plan.prefetchStages = (unsigned)strtol(e, nullptr, 10);   // tuning knob
 	if (const char* e = getenv("NMFGPU_TC_ABLATE")) plan.passes |= (unsigned)strtol(e, nullptr, 0) & 0xFF00;   // timing experiments only: results are garbage
-	plan.flushStages = 16;   // centred data: 5e-8 relative error for any value >= 4; all-positive worst case 2.4e-7 per stage
+	plan.flushStages = 8;    // 512 reduction elements per chunk. Centred data: 5e-8 relative error for any value >= 2; all-positive worst case 5e-7 per stage
 	if (const char* e = getenv("NMFGPU_TC_FLUSH_STAGES")) {   // tuning knob: 0 = accumulate whole segments inside the tensor core
 		const long v = strtol(e, nullptr, 10);
 		plan.flushStages = v <= 0 ? 0x40000000u : (unsigned)v;
@@ -842,14 +839,14 @@ void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, si
 	}
 	// W^T V: A rows = columns of V, reduction over m
 	planProduct(plan.wtv, n, m);
-	makeMap(plan.wtv.mapV, V, m, n, ldV, STAGE_K, TILE_ROWS, true);
-	makeMap(plan.wtv.mapBhi, Whi, m, k, ldW, STAGE_K, plan.kp, true);
-	makeMap(plan.wtv.mapBlo, Wlo, m, k, ldW, STAGE_K, plan.kp, true);
+	makeMap(plan.wtv.mapV, V, m, n, ldV, HALF_K, TILE_ROWS, true);
+	makeMap(plan.wtv.mapBhi, Whi, m, k, ldW, HALF_K, plan.kp, true);
+	makeMap(plan.wtv.mapBlo, Wlo, m, k, ldW, HALF_K, plan.kp, true);
 	// V H^T: A rows = rows of V, reduction over n
 	planProduct(plan.vht, m, n);
 	makeMap(plan.vht.mapV, V, m, n, ldV, TILE_ROWS, STAGE_K, false, false);   // 512-byte rows: promotion only costs bandwidth (tools/tma_stream_bench)
-	makeMap(plan.vht.mapBhi, HtHi, n, k, ldHt, STAGE_K, plan.kp, true);
-	makeMap(plan.vht.mapBlo, HtLo, n, k, ldHt, STAGE_K, plan.kp, true);
+	makeMap(plan.vht.mapBhi, HtHi, n, k, ldHt, HALF_K, plan.kp, true);
+	makeMap(plan.vht.mapBlo, HtLo, n, k, ldHt, HALF_K, plan.kp, true);
 }
 
 void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream) {

@@ -20,9 +20,10 @@ ap.add_argument("--k", type=int, default=64)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--iters", type=int, default=0)
 ap.add_argument("--mode", default="auto")
+ap.add_argument("--lib", default=None, help="alternative libnmfgpu64.so (A/B comparisons)")
 a = ap.parse_args()
 
-L = api.Library()
+L = api.Library(a.lib)
 L.set_verbosity(api.Verbosity.NoOutput)
 assert L.initialize() == 0
 L.set_precision(a.mode)
