@@ -41,25 +41,29 @@ namespace tc {
 namespace {
 
 constexpr int TILE_ROWS = 128;        // A rows per tile (= TMEM lanes)
-constexpr int HALF_K = 32;            // reduction elements per TMA box / swizzle row (128 bytes of fp32)
-constexpr int STAGE_K = 64;           // reduction elements per stage: two halves, so every barrier hop covers 2 x 12 MMAs
-constexpr int V_HALF_BYTES = TILE_ROWS * HALF_K * 4;
+constexpr int STAGE_K = 32;           // reduction elements per stage (128 bytes of fp32: one swizzle row)
 constexpr int V_STAGE_BYTES = TILE_ROWS * STAGE_K * 4;
 constexpr int PAIR_ROWS = 2 * TILE_ROWS;   // A rows per stream-K tile: two UMMA tiles that share their B tiles
-constexpr int SLOTS = 2;              // TMEM A operand slots: one per A tile / worker warpgroup (128 columns: 64 hi + 64 lo)
+constexpr int SLOTS = 4;              // TMEM A operand ring, in tiles (64 columns each: 32 hi + 32 lo)
+constexpr int SLOTS_SHIFT = 2;
+constexpr int SV = 8;                 // shared-memory ring of V tiles (16 KB each): 4 stages of 2 tiles
+constexpr int SV_SHIFT = 3;
 constexpr int A_BASE_COL = 256;       // TMEM columns [0, 256): accumulators, [256, 512): A slots
-constexpr int NUM_THREADS = 384;
-constexpr int HELPER_REGS = 72, WORKER_REGS = 216;   // 128 * 72 + 256 * 216 = 64512 <= 384 * 168
+constexpr int NUM_THREADS = 640;      // 4 helper warps + 16 warps of splitters and flushers
 constexpr uint64_t POLICY_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t POLICY_EVICT_LAST = 0x14F0000000000000ull;
 
 template <int KPM> struct Rings;
 // shared-memory rings: SV tiles of V (16 KB each) and SB tile pairs of B (hi + lo, KPM x 32 fp32 each).  Both
 // must cover the loaded TMA latency (~2700 cycles measured under full HBM traffic) at one stage per 400-650 cycles.
-// SV: shared-memory ring of V tiles (32 KB each, two per stage); SB: ring of B stages (hi and lo, two K halves:
-// 4 x KPM x 32 fp32); ACC_BUFS: accumulator buffers per A tile
-template <> struct Rings<64> { static constexpr int SV = 4, SV_SHIFT = 2, SB = 2, ACC_BUFS = 2; };
-template <> struct Rings<128> { static constexpr int SV = 2, SV_SHIFT = 1, SB = 2, ACC_BUFS = 1; };
+// SB: shared-memory ring of B tile pairs (hi + lo, KPM x 32 fp32 each); ACC_BUFS: accumulator buffers per A tile.
+// Warp roles beyond the four helpers: SPLIT_WGS warpgroups turn V tiles into TMEM A slots (round robin over the
+// tile steps), FLUSH_WGS warpgroups own the running sums.  Register budget: setmaxnreg only redistributes what the
+// CTA was launched with, 640 threads x 96 = 61440 (an .inc beyond that pool never returns):
+//   KPM  64: 128 x 48 + 2 x 128 x 80 + 2 x 128 x 136 = 61440      KPM 128: 128 x 40 + 2 x 128 x 72 + 2 x 128 x 144 = 60416
+// (three splitter warpgroups were tried and deadlock on long reductions -- open item, profiles/r01_notes.md)
+template <> struct Rings<64> { static constexpr int SB = 4, ACC_BUFS = 2, SPLIT_WGS = 2, FLUSH_WGS = 2, HELPER_REGS = 48, SPLIT_REGS = 80, FLUSH_REGS = 136, THREADS = 640; };
+template <> struct Rings<128> { static constexpr int SB = 2, ACC_BUFS = 1, SPLIT_WGS = 2, FLUSH_WGS = 2, HELPER_REGS = 40, SPLIT_REGS = 72, FLUSH_REGS = 144, THREADS = 640; };
 
 // position in a ring of arbitrary depth: slot index plus the parity of the number of completed laps
 struct RingPos {
@@ -127,7 +131,11 @@ __device__ __forceinline__ void mbarArrive(uint32_t bar) {
 __device__ __forceinline__ void mbarArriveExpectTx(uint32_t bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Spins on the phase with parity `parity`; a watchdog turns a protocol bug into a trap instead of a hung GPU.
+// first barrier wait that timed out: {barrier smem offset, parity, thread, block}; read by the host with NMFGPU_TC_DEBUG=1
+__device__ unsigned g_waitTimeout[4];
+
+// Spins on the phase with parity `parity`; a watchdog turns a protocol bug into a recorded timeout (the wait is
+// abandoned, the results are garbage, the next launch with NMFGPU_TC_DEBUG=1 reports it) instead of a hung GPU.
 __device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
 	uint32_t done = 0;
 	unsigned long long t0 = 0;
@@ -143,7 +151,14 @@ __device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
 			unsigned long long now;
 			asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
 			if (t0 == 0) t0 = now;
-			else if (now - t0 > 4000000000ull) __trap();   // 4 s without progress
+			else if (now - t0 > 2000000000ull) {            // 2 s without progress
+				if (atomicCAS(&g_waitTimeout[3], 0u, blockIdx.x + 1u) == 0u) {
+					g_waitTimeout[0] = bar;
+					g_waitTimeout[1] = parity;
+					g_waitTimeout[2] = threadIdx.x;
+				}
+				asm volatile("exit;");   // this thread gives up; the others follow within their own 2 s
+			}
 		}
 	}
 }
@@ -223,28 +238,29 @@ __device__ __forceinline__ void traceEvent(unsigned long long* trace, unsigned g
 }
 
 struct __align__(8) Barriers {
-	uint64_t vFull[4], vEmpty[4];          // V tile ring: TMA -> workers
-	uint64_t bFull[4], bEmpty[4];          // B stage ring: TMA -> MMA
-	uint64_t full[SLOTS], empty[SLOTS];    // A operand slots in tensor memory: workers -> MMA
-	uint64_t accFull[2], accEmpty[2];      // accumulator buffers: MMA -> workers
+	uint64_t vFull[SV], vEmpty[SV];        // V tile ring: TMA -> splitters
+	uint64_t bFull[4], bEmpty[4];          // B tile ring: TMA -> MMA
+	uint64_t full[SLOTS], empty[SLOTS];    // A operand slots in tensor memory: splitters -> MMA
+	uint64_t accFull[2], accEmpty[2];      // accumulator buffers: MMA -> flushers
 	uint32_t tmemBase;
 };
 
 // ---- the kernel ----------------------------------------------------------------------------------------
-// V_COLS_ARE_ROWS = true : W^T V (A rows are columns of V; a V tile in smem is two [128 cols][32 rows] halves, 128B swizzle)
-//                 = false: V H^T (A rows are rows of V;    a V tile in smem is [64 cols][128 rows], linear)
-// Counters: g = stage of this CTA (64 reduction elements of one 256-row pair tile), tile step t = 2 g + w for
-// A tile w; V ring slot = t mod SV, A slot = w, B slot = g mod SB.
+// V_COLS_ARE_ROWS = true : W^T V (A rows are columns of V; V tile in smem is [128 cols][32 rows], 128B swizzle)
+//                 = false: V H^T (A rows are rows of V;    V tile in smem is [32 cols][128 rows], linear)
+// Counters: g = stage of this CTA (32 reduction elements of one 256-row pair tile), tile step t = 2 g + w for
+// the A tile w of that stage; V ring slot = t mod 8, A slot = t mod 4, B slot = g mod SB.
 template <int KPM, bool V_COLS_ARE_ROWS>
-__global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_constant__ KParams p) {
-	constexpr int SV = Rings<KPM>::SV, SV_SHIFT = Rings<KPM>::SV_SHIFT, SB = Rings<KPM>::SB, ACC_BUFS = Rings<KPM>::ACC_BUFS;
-	constexpr int B_PART_BYTES = KPM * HALF_K * 4;            // one of {hi, lo} x {K half 0, 1}
-	constexpr int B_STAGE_BYTES = 4 * B_PART_BYTES;
+__global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const __grid_constant__ KParams p) {
+	using R = Rings<KPM>;
+	constexpr int SB = R::SB, ACC_BUFS = R::ACC_BUFS, SPLIT_WGS = R::SPLIT_WGS, FLUSH_WGS = R::FLUSH_WGS;
+	static_assert(4 + 4 * (SPLIT_WGS + FLUSH_WGS) == R::THREADS / 32, "warp roles");
+	constexpr int B_HALF_BYTES = KPM * STAGE_K * 4;
 	extern __shared__ unsigned char smemRaw[];
 	unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~(uintptr_t)1023);
 	unsigned char* vRing = smem;
 	unsigned char* bRing = smem + SV * V_STAGE_BYTES;
-	Barriers* bars = reinterpret_cast<Barriers*>(bRing + SB * B_STAGE_BYTES);
+	Barriers* bars = reinterpret_cast<Barriers*>(bRing + SB * 2 * B_HALF_BYTES);
 
 	const unsigned warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 	const unsigned F = p.flushStages;
@@ -264,7 +280,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 		}
 		for (int i = 0; i < 2; ++i) {
 			mbarInit(smemAddr(&bars->accFull[i]), 2);        // tcgen05.commit of both issuers' last MMAs of the chunk
-			mbarInit(smemAddr(&bars->accEmpty[i]), 8);       // the 8 worker warps have read their tiles' accumulators
+			mbarInit(smemAddr(&bars->accEmpty[i]), 4 * FLUSH_WGS);   // the flusher warps have read the accumulators
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -282,69 +298,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 	const uint32_t fullBar = barBase + offsetof(Barriers, full), emptyBar = barBase + offsetof(Barriers, empty);
 	const uint32_t accFullBar = barBase + offsetof(Barriers, accFull), accEmptyBar = barBase + offsetof(Barriers, accEmpty);
 
-	// register budget: 384 threads x 168; the four helper warps keep HELPER_REGS each and hand the rest to the workers
 	if (warp == 0) {
 		// ===== V producer =====
-		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS));
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::HELPER_REGS));
 		if (lane == 0) {
 			SegmentWalker walk(p, blockIdx.x);
 			Segment s;
 			unsigned t = 0;
 			const uint32_t vBase = smemAddr(vRing);
-			// L2 prefetch cursor: runs `prefetchStages` stages ahead of the loads, so a TMA load finds its tile in L2 and
-			// the shared-memory ring only has to cover the L2 latency, not the loaded HBM latency (3-4 us measured)
-			SegmentWalker ahead(p, blockIdx.x);
-			Segment sa;
-			unsigned la = 0;
-			bool more = ahead.next(sa);
-			auto prefetchOne = [&]() {
-				if (!more) return;
-				const int rA = (int)(sa.tile * PAIR_ROWS), kA = (int)((sa.stage0 + la) * STAGE_K);
-				if (V_COLS_ARE_ROWS) {
-					tmaPrefetchL2(&p.mapV, kA, rA);
-					tmaPrefetchL2(&p.mapV, kA + HALF_K, rA);
-					tmaPrefetchL2(&p.mapV, kA, rA + TILE_ROWS);
-					tmaPrefetchL2(&p.mapV, kA + HALF_K, rA + TILE_ROWS);
-				} else {
-					tmaPrefetchL2(&p.mapV, rA, kA);
-					tmaPrefetchL2(&p.mapV, rA + TILE_ROWS, kA);
-				}
-				if (++la == sa.len) {
-					la = 0;
-					more = ahead.next(sa);
-				}
-			};
-			for (unsigned i = 0; i < p.prefetchStages; ++i) prefetchOne();
 			while (walk.next(s)) {
 				const int rIdx = (int)(s.tile * PAIR_ROWS);
 				int kIdx = (int)(s.stage0 * STAGE_K);
 				for (unsigned ls = 0; ls < s.len; ++ls, kIdx += STAGE_K) {
-					if (p.prefetchStages) prefetchOne();
 #pragma unroll
 					for (int w = 0; w < 2; ++w, ++t) {
 						const unsigned sv = t & (SV - 1);
 						mbarWait(vEmptyBar + sv * 8, ((t >> SV_SHIFT) & 1) ^ 1);
 						const uint32_t full = vFullBar + sv * 8;
 						mbarArriveExpectTx(full, V_STAGE_BYTES);
-						const uint32_t dst = vBase + sv * V_STAGE_BYTES;
-						if (V_COLS_ARE_ROWS) {
-							tmaLoad2D(dst, &p.mapV, full, kIdx, rIdx + w * TILE_ROWS, POLICY_EVICT_FIRST);
-							tmaLoad2D(dst + V_HALF_BYTES, &p.mapV, full, kIdx + HALF_K, rIdx + w * TILE_ROWS, POLICY_EVICT_FIRST);
-						} else {
-							tmaLoad2D(dst, &p.mapV, full, rIdx + w * TILE_ROWS, kIdx, POLICY_EVICT_FIRST);
-						}
+						if (V_COLS_ARE_ROWS) tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, kIdx, rIdx + w * TILE_ROWS, POLICY_EVICT_FIRST);
+						else tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, rIdx + w * TILE_ROWS, kIdx, POLICY_EVICT_FIRST);
 					}
 				}
 			}
 		}
 	} else if (warp == 2) {
-		// ===== B producer (hi and lo tiles of W resp. H^T, two K halves each) =====
-		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS));
+		// ===== B producer (hi and lo tiles of W resp. H^T) =====
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::HELPER_REGS));
 		if (lane == 0) {
 			SegmentWalker walk(p, blockIdx.x);
 			Segment s;
 			RingPos b;
-			const uint32_t bytes = 4u * p.kp * HALF_K * 4u;
+			const uint32_t bytes = 2u * p.kp * STAGE_K * 4u;
 			const uint32_t bBase = smemAddr(bRing);
 			while (walk.next(s)) {
 				int kIdx = (int)(s.stage0 * STAGE_K);
@@ -352,11 +337,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 					mbarWait(bEmptyBar + b.idx * 8, b.lap ^ 1);
 					const uint32_t full = bFullBar + b.idx * 8;
 					mbarArriveExpectTx(full, bytes);
-					const uint32_t dst = bBase + b.idx * B_STAGE_BYTES;
+					const uint32_t dst = bBase + b.idx * 2 * B_HALF_BYTES;
 					tmaLoad2D(dst, &p.mapBhi, full, kIdx, 0, POLICY_EVICT_LAST);
-					tmaLoad2D(dst + B_PART_BYTES, &p.mapBhi, full, kIdx + HALF_K, 0, POLICY_EVICT_LAST);
-					tmaLoad2D(dst + 2 * B_PART_BYTES, &p.mapBlo, full, kIdx, 0, POLICY_EVICT_LAST);
-					tmaLoad2D(dst + 3 * B_PART_BYTES, &p.mapBlo, full, kIdx + HALF_K, 0, POLICY_EVICT_LAST);
+					tmaLoad2D(dst + B_HALF_BYTES, &p.mapBlo, full, kIdx, 0, POLICY_EVICT_LAST);
 				}
 			}
 		}
@@ -364,17 +347,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 		// ===== MMA issuers: warp 1 feeds A tile 0 of every stage, warp 3 A tile 1 (separate accumulators) =====
 		// Each warp walks its loop convergently so that every address and descriptor lives in uniform registers
 		// (a divergent single-thread loop costs ~140 cycles per MMA in R2UR traffic); one elected lane issues the
-		// 24 MMAs of a tile back to back.  Issuing blocks for about as long as the MMAs execute and every barrier
+		// 12 MMAs of a tile back to back.  Issuing blocks for about as long as the MMAs execute and every barrier
 		// probe costs ~100 cycles, so one issuer leaves the tensor pipe idle during its waits; two issuers cover
 		// each other's waits.
-		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS));
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::HELPER_REGS));
 		const unsigned w = warp == 1 ? 0u : 1u;
 		const bool leader = electOne();
 		// instruction descriptor: D fp32, A/B tf32, both K-major, N = kp, M = 128
 		const uint32_t iDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((p.kp >> 3) << 17) | ((TILE_ROWS >> 4) << 24);
 		const uint64_t bDesc0 = smemDescSw128(smemAddr(bRing));
 		const bool threePass = (p.passes & 0xFF) == 3;
-		const uint32_t aHi = tmem + A_BASE_COL + w * 128, aLo = aHi + 64;
 		SegmentWalker walk(p, blockIdx.x);
 		Segment s;
 		unsigned g = 0, gc = 0;
@@ -386,24 +368,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 					buf = gc % ACC_BUFS;
 					mbarWait(accEmptyBar + buf * 8, (((gc / ACC_BUFS) & 1) ^ 1));
 				}
+				const unsigned t = 2 * g + w, sl = t & (SLOTS - 1);
 				mbarWait(bFullBar + b.idx * 8, b.lap);
-				mbarWait(fullBar + w * 8, g & 1);
+				mbarWait(fullBar + sl * 8, (t >> SLOTS_SHIFT) & 1);
 				tcFenceAfter();
 				if (leader) {
+					const uint64_t dHi = bDesc0 + (uint64_t)((b.idx * 2 * B_HALF_BYTES) >> 4), dLo = dHi + (B_HALF_BYTES >> 4);
 					const uint32_t acc = tmem + (w * ACC_BUFS + buf) * KPM;
-					const uint64_t dB = bDesc0 + (uint64_t)((b.idx * B_STAGE_BYTES) >> 4);
+					const uint32_t aHi = tmem + A_BASE_COL + sl * 64, aLo = aHi + 32;
+					if (threePass) {
 #pragma unroll
-					for (int q = 0; q < STAGE_K / 8; ++q) {
-						// k-step q: A columns q*8.. ; B part (q / 4) of {hi, lo}, 32 bytes per k-step inside the swizzled row
-						const uint64_t dHi = dB + (uint64_t)(((q / 4) * B_PART_BYTES + (q % 4) * 32) >> 4);
-						const uint64_t dLo = dHi + (uint64_t)((2 * B_PART_BYTES) >> 4);
-						mmaTf32(acc, aHi + q * 8, dHi, iDesc, q == 0 ? (uint32_t)(inChunk != 0) : 1u);
-						if (threePass) {
-							mmaTf32(acc, aLo + q * 8, dHi, iDesc, 1);
-							mmaTf32(acc, aHi + q * 8, dLo, iDesc, 1);
+						for (int q = 0; q < STAGE_K / 8; ++q) {
+							mmaTf32(acc, aHi + q * 8, dHi + q * 2, iDesc, q == 0 ? (uint32_t)(inChunk != 0) : 1u);
+							mmaTf32(acc, aLo + q * 8, dHi + q * 2, iDesc, 1);
+							mmaTf32(acc, aHi + q * 8, dLo + q * 2, iDesc, 1);
 						}
+					} else {
+#pragma unroll
+						for (int q = 0; q < STAGE_K / 8; ++q) mmaTf32(acc, aHi + q * 8, dHi + q * 2, iDesc, q == 0 ? (uint32_t)(inChunk != 0) : 1u);
 					}
-					tcCommit(emptyBar + w * 8);
+					tcCommit(emptyBar + sl * 8);
 					tcCommit(bEmptyBar + b.idx * 8);
 				}
 				++inChunk;
@@ -415,143 +399,122 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 				__syncwarp();
 			}
 		}
-	} else if (warp >= 4) {
-		// ===== workers: V tile -> TF32 hi/lo -> TMEM A slot; accumulator flush; output =====
-		asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WORKER_REGS));
-		const unsigned wg = (warp - 4) / 4;                 // 0 or 1: the A tile of every stage this warpgroup owns
+	} else if (warp < 4 + 4 * SPLIT_WGS) {
+		// ===== splitters: V tile -> TF32 hi/lo -> TMEM A slot.  Tile steps go round robin over the warpgroups,
+		// so each has SPLIT_WGS tile times for its chain of barrier probes, shared-memory loads, tcgen05.st and
+		// wait::st (~250 cycles of latency alone).  They know nothing of tiles or chunks: only ring positions.
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::SPLIT_REGS));
+		const unsigned wgi = (warp - 4) / 4;
 		const unsigned row = (warp % 4) * 32 + lane;        // A row = TMEM lane owned by this thread
 		const uint32_t laneBase = ((warp % 4) * 32) << 16;
-		const unsigned kp = p.kp;
 		const float center = p.center;
-		const uint32_t aSlot = tmem + laneBase + A_BASE_COL + wg * 128;
-		float sum[KPM];
-#pragma unroll
-		for (int c = 0; c < KPM; ++c) sum[c] = 0.f;
-
-		// one K half (32 values of this thread's A row) of the tile in V ring slot sv
-		float v[HALF_K];
-		auto loadHalf = [&](unsigned sv, int h) {
+		const unsigned tEnd = 2 * (unsigned)(unitStart(blockIdx.x + 1, p.grid, p.units) - unitStart(blockIdx.x, p.grid, p.units));
+		float v[STAGE_K];
+		auto loadTile = [&](unsigned t) {
+			const unsigned sv = t & (SV - 1);
+			mbarWait(vFullBar + sv * 8, (t >> SV_SHIFT) & 1);
 			const unsigned char* tile = vRing + sv * V_STAGE_BYTES;
 			if (V_COLS_ARE_ROWS) {
-				// row `row` of the [128][32] half tile; 16-byte chunk c lives at chunk c ^ (row & 7)
-				const unsigned char* base = tile + h * V_HALF_BYTES + row * 128;
+				// row `row` of the [128][32] tile; 16-byte chunk c lives at chunk c ^ (row & 7)
+				const unsigned char* base = tile + row * 128;
 #pragma unroll
 				for (int c = 0; c < 8; ++c) {
 					const float4 x = *reinterpret_cast<const float4*>(base + ((c ^ (row & 7)) << 4));
 					v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
 				}
 			} else {
-				const float* base = reinterpret_cast<const float*>(tile) + h * HALF_K * TILE_ROWS + row;
+				const float* base = reinterpret_cast<const float*>(tile) + row;
 #pragma unroll
-				for (int j = 0; j < HALF_K; ++j) v[j] = base[j * TILE_ROWS];
+				for (int j = 0; j < STAGE_K; ++j) v[j] = base[j * TILE_ROWS];
 			}
-		};
-		// TF32 split of v[] into the A slot columns of K half h (hi at 32 h, lo at 64 + 32 h)
-		auto storeHalf = [&](int h) {
-			uint32_t hi[HALF_K], lo[HALF_K];
-#pragma unroll
-			for (int e = 0; e < HALF_K; ++e) splitValue(v[e] - center, hi[e], lo[e]);
-			tmemStore16(aSlot + 32 * h, hi);
-			tmemStore16(aSlot + 32 * h + 16, hi + 16);
-			tmemStore16(aSlot + 64 + 32 * h, lo);
-			tmemStore16(aSlot + 64 + 32 * h + 16, lo + 16);
-		};
-		auto waitTile = [&](unsigned g) {
-			const unsigned t = 2 * g + wg;
-			mbarWait(vFullBar + (t & (SV - 1)) * 8, (t >> SV_SHIFT) & 1);
-		};
-		// The loop is software pipelined: half 0 of the next stage's tile is read from shared memory while the
-		// tcgen05.st of this stage drain, so neither latency sits on the per-stage critical path.
-		auto processStage = [&](unsigned g, bool prefetchNext) {
-			const unsigned t = 2 * g + wg, sv = t & (SV - 1);
-			mbarWait(emptyBar + wg * 8, (g & 1) ^ 1);         // the issuer has consumed the previous content of the A slot
-			tcFenceAfter();
-			storeHalf(0);                                      // v[] holds half 0 (loaded by the previous iteration)
-			loadHalf(sv, 1);
+			// the tile is in registers: release the slot (one arrival per warp: 128 per-thread arrivals on one
+			// mbarrier serialise in the barrier unit and delay the TMA completions that share it)
 			__syncwarp();
-			if (lane == 0) mbarArrive(vEmptyBar + sv * 8);     // the whole tile is in registers / TMEM: release the smem slot
-			storeHalf(1);
-			if (prefetchNext) {
-				waitTile(g + 1);
-				loadHalf((t + 2) & (SV - 1), 0);
+			if (lane == 0) mbarArrive(vEmptyBar + sv * 8);
+		};
+		if (wgi < tEnd) loadTile(wgi);
+		for (unsigned t = wgi; t < tEnd; t += SPLIT_WGS) {
+			const unsigned sl = t & (SLOTS - 1);
+			mbarWait(emptyBar + sl * 8, ((t >> SLOTS_SHIFT) & 1) ^ 1);
+			tcFenceAfter();
+			const uint32_t aSlot = tmem + laneBase + A_BASE_COL + sl * 64;
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				uint32_t hi[16], lo[16];
+#pragma unroll
+				for (int e = 0; e < 16; ++e) splitValue(v[16 * h + e] - center, hi[e], lo[e]);
+				tmemStore16(aSlot + 16 * h, hi);
+				tmemStore16(aSlot + 32 + 16 * h, lo);
 			}
 			tmemWaitStore();
 			tcFenceBefore();
 			__syncwarp();
-			if (lane == 0) mbarArrive(fullBar + wg * 8);
-		};
-
-		auto flush = [&](unsigned gc) {
-			const unsigned buf = gc % ACC_BUFS;
-			mbarWait(accFullBar + buf * 8, (gc / ACC_BUFS) & 1);
-			tcFenceAfter();
-			const uint32_t acc = tmem + laneBase + (wg * ACC_BUFS + buf) * KPM;
+			if (lane == 0) mbarArrive(fullBar + sl * 8);
+			if (t + SPLIT_WGS < tEnd) loadTile(t + SPLIT_WGS);   // after the publish: a late V tile must not hold the A slot back
+		}
+	} else {
+		// ===== flushers: every chunk, add the tensor-core accumulators to the fp32 running sums; write the segment's
+		// partial product at its end.  Flusher warpgroup f owns the A tiles f, f + FLUSH_WGS, ...
+		asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R::FLUSH_REGS));
+		constexpr int TILES_PER_FLUSHER = 2 / FLUSH_WGS;
+		const unsigned fwg = (warp - 4 - 4 * SPLIT_WGS) / 4;
+		const unsigned row = (warp % 4) * 32 + lane;
+		const uint32_t laneBase = ((warp % 4) * 32) << 16;
+		const unsigned kp = p.kp;
+		float sum[TILES_PER_FLUSHER][KPM];
 #pragma unroll
-			for (int q = 0; q < KPM / 32; ++q) {
-				if (q * 32 < (int)kp) {
-					uint32_t r[32];
-					tmemLoad16(acc + q * 32, r);
-					if (q * 32 + 16 < (int)kp) tmemLoad16(acc + q * 32 + 16, r + 16);
-					tmemWaitLoad();
+		for (int i = 0; i < TILES_PER_FLUSHER; ++i)
 #pragma unroll
-					for (int e = 0; e < 16; ++e) sum[q * 32 + e] += __uint_as_float(r[e]);
-					if (q * 32 + 16 < (int)kp) {
-#pragma unroll
-						for (int e = 16; e < 32; ++e) sum[q * 32 + e] += __uint_as_float(r[e]);
-					}
-				}
-			}
-			tcFenceBefore();
-			__syncwarp();
-			if (lane == 0) mbarArrive(accEmptyBar + buf * 8);
-		};
+			for (int c = 0; c < KPM; ++c) sum[i][c] = 0.f;
 
 		SegmentWalker walk(p, blockIdx.x);
 		Segment s;
-		unsigned gBase = 0, gcBase = 0;
-		const unsigned totalStages = (unsigned)(walk.uEnd - walk.u);
-		if (totalStages > 0) {
-			waitTile(0);
-			loadHalf(wg & (SV - 1), 0);
-		}
+		unsigned gc = 0;
 		while (walk.next(s)) {
-			// chunk c of this segment covers local stages [c F, (c+1) F); both warpgroups flush every chunk
-			// (each its own tile).  With one A slot per warpgroup a worker is at most one stage ahead of its issuer,
-			// and the issuer cannot pass a chunk end before the flush when the accumulator is single-buffered:
-			// flush right after the last stage of the chunk in that case, one stage later otherwise.
-			constexpr unsigned LOOKAHEAD = ACC_BUFS == 2 ? 1 : 0;
 			const unsigned nChunks = (s.len + F - 1) / F;
-			unsigned nextChunk = 0;
-			unsigned flushAt = F - 1 + LOOKAHEAD;
-			for (unsigned ls = 0; ls < s.len; ++ls) {
-				processStage(gBase + ls, gBase + ls + 1 < totalStages);
-				if (ls >= flushAt && nextChunk + 1 < nChunks) {
-					flush(gcBase + nextChunk);
-					++nextChunk;
-					flushAt += F;
+			for (unsigned c = 0; c < nChunks; ++c, ++gc) {
+				const unsigned buf = gc % ACC_BUFS;
+				mbarWait(accFullBar + buf * 8, (gc / ACC_BUFS) & 1);
+				tcFenceAfter();
+#pragma unroll
+				for (int i = 0; i < TILES_PER_FLUSHER; ++i) {
+					const unsigned w = fwg + i * FLUSH_WGS;
+					const uint32_t acc = tmem + laneBase + (w * ACC_BUFS + buf) * KPM;
+#pragma unroll
+					for (int q = 0; q < KPM / 16; ++q) {
+						if (q * 16 < (int)kp) {
+							uint32_t r[16];
+							tmemLoad16(acc + q * 16, r);
+							tmemWaitLoad();
+#pragma unroll
+							for (int e = 0; e < 16; ++e) sum[i][q * 16 + e] += __uint_as_float(r[e]);
+						}
+					}
 				}
+				tcFenceBefore();
+				__syncwarp();
+				if (lane == 0) mbarArrive(accEmptyBar + buf * 8);
 			}
-			for (; nextChunk < nChunks; ++nextChunk) flush(gcBase + nextChunk);
-			gBase += s.len;
-			gcBase += nChunks;
-
-			// ---- output of this segment's partial product: every warpgroup owns the rows of its tile
+			// ---- output of this segment's partial product
 			float* out = p.out + (size_t)s.slot * p.slotStride;
-			const unsigned r = s.tile * PAIR_ROWS + wg * TILE_ROWS + row;
-			if (r < p.rowsA) {
-				if (V_COLS_ARE_ROWS) {
-					float4* dst = reinterpret_cast<float4*>(out + (size_t)r * p.ldOut);     // column r of N: kp contiguous values
 #pragma unroll
-					for (int c = 0; c < KPM / 4; ++c)
-						if (c * 4 < (int)kp) dst[c] = make_float4(sum[4 * c], sum[4 * c + 1], sum[4 * c + 2], sum[4 * c + 3]);
-				} else {
+			for (int i = 0; i < TILES_PER_FLUSHER; ++i) {
+				const unsigned r = s.tile * PAIR_ROWS + (fwg + i * FLUSH_WGS) * TILE_ROWS + row;
+				if (r < p.rowsA) {
+					if (V_COLS_ARE_ROWS) {
+						float4* dst = reinterpret_cast<float4*>(out + (size_t)r * p.ldOut);     // column r of N: kp contiguous values
 #pragma unroll
-					for (int c = 0; c < KPM; ++c)
-						if (c < (int)p.k) out[(size_t)c * p.ldOut + r] = sum[c];             // row r of N2: coalesced across the warp
+						for (int c = 0; c < KPM / 4; ++c)
+							if (c * 4 < (int)kp) dst[c] = make_float4(sum[i][4 * c], sum[i][4 * c + 1], sum[i][4 * c + 2], sum[i][4 * c + 3]);
+					} else {
+#pragma unroll
+						for (int c = 0; c < KPM; ++c)
+							if (c < (int)p.k) out[(size_t)c * p.ldOut + r] = sum[i][c];          // row r of N2: coalesced across the warp
+					}
 				}
-			}
 #pragma unroll
-			for (int c = 0; c < KPM; ++c) sum[c] = 0.f;
+				for (int c = 0; c < KPM; ++c) sum[i][c] = 0.f;
+			}
 		}
 	}
 
@@ -565,7 +528,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_stream_gemm(const __grid_co
 
 template <int KPM>
 size_t smemBytes() {
-	return 1024 + (size_t)Rings<KPM>::SV * V_STAGE_BYTES + (size_t)Rings<KPM>::SB * 4 * KPM * HALF_K * 4 + sizeof(Barriers);
+	return 1024 + (size_t)SV * V_STAGE_BYTES + (size_t)Rings<KPM>::SB * 2 * KPM * STAGE_K * 4 + sizeof(Barriers);
 }
 
 // ---- H -> H^T hi/lo ----------------------------------------------------------------------------------
@@ -741,8 +704,18 @@ void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, s
 	p.grid = prod.grid;
 	p.center = plan.center;
 	p.prefetchStages = plan.prefetchStages;
-	tc_stream_gemm<KPM, VC><<<prod.grid, NUM_THREADS, smem, stream>>>(p);
+	tc_stream_gemm<KPM, VC><<<prod.grid, Rings<KPM>::THREADS, smem, stream>>>(p);
 	CUDA_CHECK(cudaGetLastError());
+	if (getenv("NMFGPU_TC_DEBUG") != nullptr) {
+		unsigned rec[4] = {0, 0, 0, 0};
+		CUDA_CHECK(cudaStreamSynchronize(stream));
+		CUDA_CHECK(cudaMemcpyFromSymbol(rec, g_waitTimeout, sizeof(rec)));
+		if (rec[3] != 0) {
+			errorf("tc_stream_gemm<%d,%d>: barrier wait timed out: smem address 0x%x parity %u thread %u block %u", KPM, (int)VC, rec[0], rec[1], rec[2], rec[3] - 1);
+			const unsigned zero[4] = {0, 0, 0, 0};
+			CUDA_CHECK(cudaMemcpyToSymbol(g_waitTimeout, zero, sizeof(zero)));
+		}
+	}
 }
 
 }  // namespace
@@ -817,10 +790,10 @@ void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, si
 	plan.k = k;
 	plan.kp = (unsigned)roundUp(k, 16);
 	plan.passes = singlePass ? 1 : 3;
-	plan.prefetchStages = 4;
+	plan.prefetchStages = 0;
 	if (const char* e = getenv("NMFGPU_TC_PREFETCH")) plan.prefetchStages = (unsigned)strtol(e, nullptr, 10);   // tuning knob
 	if (const char* e = getenv("NMFGPU_TC_ABLATE")) plan.passes |= (unsigned)strtol(e, nullptr, 0) & 0xFF00;   // timing experiments only: results are garbage
-	plan.flushStages = 8;    // 512 reduction elements per chunk. Centred data: 5e-8 relative error for any value >= 2; all-positive worst case 5e-7 per stage
+	plan.flushStages = 16;   // 512 reduction elements per chunk. Centred data: 5e-8 relative error for any value >= 4; all-positive worst case 2.4e-7 per stage
 	if (const char* e = getenv("NMFGPU_TC_FLUSH_STAGES")) {   // tuning knob: 0 = accumulate whole segments inside the tensor core
 		const long v = strtol(e, nullptr, 10);
 		plan.flushStages = v <= 0 ? 0x40000000u : (unsigned)v;
@@ -839,14 +812,14 @@ void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, si
 	}
 	// W^T V: A rows = columns of V, reduction over m
 	planProduct(plan.wtv, n, m);
-	makeMap(plan.wtv.mapV, V, m, n, ldV, HALF_K, TILE_ROWS, true);
-	makeMap(plan.wtv.mapBhi, Whi, m, k, ldW, HALF_K, plan.kp, true);
-	makeMap(plan.wtv.mapBlo, Wlo, m, k, ldW, HALF_K, plan.kp, true);
+	makeMap(plan.wtv.mapV, V, m, n, ldV, STAGE_K, TILE_ROWS, true);
+	makeMap(plan.wtv.mapBhi, Whi, m, k, ldW, STAGE_K, plan.kp, true);
+	makeMap(plan.wtv.mapBlo, Wlo, m, k, ldW, STAGE_K, plan.kp, true);
 	// V H^T: A rows = rows of V, reduction over n
 	planProduct(plan.vht, m, n);
 	makeMap(plan.vht.mapV, V, m, n, ldV, TILE_ROWS, STAGE_K, false, false);   // 512-byte rows: promotion only costs bandwidth (tools/tma_stream_bench)
-	makeMap(plan.vht.mapBhi, HtHi, n, k, ldHt, HALF_K, plan.kp, true);
-	makeMap(plan.vht.mapBlo, HtLo, n, k, ldHt, HALF_K, plan.kp, true);
+	makeMap(plan.vht.mapBhi, HtHi, n, k, ldHt, STAGE_K, plan.kp, true);
+	makeMap(plan.vht.mapBlo, HtLo, n, k, ldHt, STAGE_K, plan.kp, true);
 }
 
 void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream) {

@@ -39,8 +39,8 @@ struct Plan {
 	unsigned m = 0, n = 0, k = 0;
 	unsigned kp = 0;               // rank padded to the UMMA N granularity (multiple of 16, <= 128)
 	unsigned passes = 3;           // 3 = 3xTF32, 1 = single-pass TF32 (diagnostic)
-	unsigned flushStages = 8; 
-	unsigned prefetchStages = 4;   // L2 prefetch distance of the V tiles, in stages     // reduction stages accumulated inside the tensor core before the fp32 flush
+	unsigned flushStages = 16;
+	unsigned prefetchStages = 0;   // L2 prefetch distance of the V tiles, in stages (measured: no gain, >4 hurts)     // reduction stages accumulated inside the tensor core before the fp32 flush
 	// Mean centring: the kernels multiply (V - center) instead of V, so the tensor-core accumulators hover around
 	// zero instead of growing monotonically.  The tensor core truncates its fp32 accumulator after every MMA; on
 	// the all-positive data of an NMF that is a systematic -2.4e-7 per accumulated stage, on centred data it is an
