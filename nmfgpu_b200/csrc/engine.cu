@@ -53,6 +53,9 @@ template <typename T>
 Engine<T>::~Engine() {
 	if (m_stream) {
 		cudaStreamSynchronize(m_stream);
+		for (auto& row : m_graphExec)
+			for (cudaGraphExec_t& g : row)
+				if (g) cudaGraphExecDestroy(g);
 		cudaStreamDestroy(m_stream);
 	}
 }
@@ -565,8 +568,44 @@ void Engine<T>::iterate(bool computeError) {
 	}
 }
 
+// Batches of iterations without residual go through a CUDA graph of TWO iterations (after two, the W/H ping-pong
+// buffers are back where they started, so the recorded pointers stay valid); one graph per buffer parity.
 template <typename T>
 void Engine<T>::iterateNoError(unsigned count) {
+	static const bool graphs = [] {
+		const char* e = getenv("NMFGPU_GRAPHS");
+		return e == nullptr || atoi(e) != 0;
+	}();
+	if (graphs && count >= 6 && getenv("NMFGPU_TC_DEBUG") == nullptr) {
+		cudaGraphExec_t& exec = m_graphExec[m_wCur][m_hCur];
+		if (exec == nullptr) {
+			iterate(false);   // an eager pair first: lazily set kernel attributes must not happen inside the capture
+			iterate(false);
+			count -= 2;
+			const unsigned long long before = m_launches;
+			cudaGraph_t graph = nullptr;
+			CUDA_CHECK(cudaStreamBeginCapture(m_stream, cudaStreamCaptureModeThreadLocal));
+			try {
+				iterate(false);
+				iterate(false);
+			} catch (...) {
+				cudaStreamEndCapture(m_stream, &graph);
+				if (graph) cudaGraphDestroy(graph);
+				throw;
+			}
+			CUDA_CHECK(cudaStreamEndCapture(m_stream, &graph));
+			m_graphLaunches = m_launches - before;
+			m_launches = before;   // recorded, not executed
+			const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+			cudaGraphDestroy(graph);
+			CUDA_CHECK(e);
+		}
+		while (count >= 2) {
+			CUDA_CHECK(cudaGraphLaunch(exec, m_stream));
+			m_launches += m_graphLaunches;
+			count -= 2;
+		}
+	}
 	for (unsigned i = 0; i < count; ++i) iterate(false);
 }
 

@@ -109,7 +109,8 @@ private:
 	T m_eps;
 	cudaStream_t m_stream = nullptr;
 	bool m_useTC = false;
-	unsigned long long m_launches = 0;
+	unsigned long long m_launches = 0, m_graphLaunches = 0;
+	cudaGraphExec_t m_graphExec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // two recorded iterations, per (W, H) buffer parity
 
 	size_t m_ldV = 0, m_ldW = 0, m_ldH = 0;
 	DeviceBuffer<T> m_V, m_W[2], m_H[2];

@@ -154,6 +154,14 @@ bool runFactorisation(NmfDescription<T>& desc, Engine<T>& engine, Summary* summa
 				interrupted = true;
 				break;
 			}
+			if (desc.callbackUserInterrupt == nullptr) {
+				// no callback to poll: the iterations before the next residual evaluation go out as one batch (CUDA graph)
+				const unsigned nextError = std::min(numIterations, (iteration + 9) / 10 * 10);
+				if (nextError > iteration) {
+					engine.iterateNoError(nextError - iteration);
+					iteration = nextError;
+				}
+			}
 			const bool computeError = iteration % 10 == 0 || iteration == numIterations;  // SingleGpuDispatcher.cpp:173
 			engine.iterate(computeError);
 			if (computeError) {

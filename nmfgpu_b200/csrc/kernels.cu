@@ -656,9 +656,14 @@ __global__ void __launch_bounds__(64) qr_solve_clamp_kernel(unsigned k, const T*
 
 inline void launchCheck() { CUDA_CHECK(cudaGetLastError()); }
 
+// opt-in to more than 48 KB of dynamic shared memory, once per kernel and size (never inside a stream capture)
 template <typename K>
 void allowSmem(K kernel, size_t bytes) {
-	if (bytes > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+	if (bytes <= 48 * 1024) return;
+	static size_t allowed = 0;   // one instance per kernel type K
+	if (bytes <= allowed) return;
+	CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+	allowed = bytes;
 }
 
 }  // namespace

@@ -61,7 +61,9 @@ template <int KPM> struct Rings;
 // tile steps), FLUSH_WGS warpgroups own the running sums.  Register budget: setmaxnreg only redistributes what the
 // CTA was launched with, 640 threads x 96 = 61440 (an .inc beyond that pool never returns):
 //   KPM  64: 128 x 48 + 2 x 128 x 80 + 2 x 128 x 136 = 61440      KPM 128: 128 x 40 + 2 x 128 x 72 + 2 x 128 x 144 = 60416
-// (three splitter warpgroups were tried and deadlock on long reductions -- open item, profiles/r01_notes.md)
+// SPLIT_WGS must divide the number of A slots: a warpgroup has to be the only writer of its slots, because the parity
+// wait on `empty` only tells two consecutive phases apart (three warpgroups on four slots let a fast one get two
+// phases ahead of a slow one and overwrite a slot that was never consumed -- seen as a deadlock, profiles/r01_notes.md)
 template <> struct Rings<64> { static constexpr int SB = 4, ACC_BUFS = 2, SPLIT_WGS = 2, FLUSH_WGS = 2, HELPER_REGS = 48, SPLIT_REGS = 80, FLUSH_REGS = 136, THREADS = 640; };
 template <> struct Rings<128> { static constexpr int SB = 2, ACC_BUFS = 1, SPLIT_WGS = 2, FLUSH_WGS = 2, HELPER_REGS = 40, SPLIT_REGS = 72, FLUSH_REGS = 144, THREADS = 640; };
 
@@ -131,8 +133,9 @@ __device__ __forceinline__ void mbarArrive(uint32_t bar) {
 __device__ __forceinline__ void mbarArriveExpectTx(uint32_t bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// first barrier wait that timed out: {barrier smem offset, parity, thread, block}; read by the host with NMFGPU_TC_DEBUG=1
-__device__ unsigned g_waitTimeout[4];
+// barrier waits that timed out: count, then up to 63 records {barrier smem address, parity, thread, block}; read by the
+// host with NMFGPU_TC_DEBUG=1
+__device__ unsigned g_waitTimeout[4 * 64];
 
 // Spins on the phase with parity `parity`; a watchdog turns a protocol bug into a recorded timeout (the wait is
 // abandoned, the results are garbage, the next launch with NMFGPU_TC_DEBUG=1 reports it) instead of a hung GPU.
@@ -152,10 +155,14 @@ __device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
 			asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
 			if (t0 == 0) t0 = now;
 			else if (now - t0 > 2000000000ull) {            // 2 s without progress
-				if (atomicCAS(&g_waitTimeout[3], 0u, blockIdx.x + 1u) == 0u) {
-					g_waitTimeout[0] = bar;
-					g_waitTimeout[1] = parity;
-					g_waitTimeout[2] = threadIdx.x;
+				if ((threadIdx.x & 31) == 0 || (threadIdx.x < 128)) {
+					const unsigned slot = atomicAdd(&g_waitTimeout[0], 1u) + 1u;
+					if (slot < 64) {
+						g_waitTimeout[4 * slot + 0] = bar;
+						g_waitTimeout[4 * slot + 1] = parity;
+						g_waitTimeout[4 * slot + 2] = threadIdx.x;
+						g_waitTimeout[4 * slot + 3] = blockIdx.x;
+					}
 				}
 				asm volatile("exit;");   // this thread gives up; the others follow within their own 2 s
 			}
@@ -255,6 +262,7 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 	using R = Rings<KPM>;
 	constexpr int SB = R::SB, ACC_BUFS = R::ACC_BUFS, SPLIT_WGS = R::SPLIT_WGS, FLUSH_WGS = R::FLUSH_WGS;
 	static_assert(4 + 4 * (SPLIT_WGS + FLUSH_WGS) == R::THREADS / 32, "warp roles");
+	static_assert(SLOTS % SPLIT_WGS == 0 && SV % SPLIT_WGS == 0, "every ring slot must have a single writer / reader warpgroup");
 	constexpr int B_HALF_BYTES = KPM * STAGE_K * 4;
 	extern __shared__ unsigned char smemRaw[];
 	unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~(uintptr_t)1023);
@@ -707,13 +715,16 @@ void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, s
 	tc_stream_gemm<KPM, VC><<<prod.grid, Rings<KPM>::THREADS, smem, stream>>>(p);
 	CUDA_CHECK(cudaGetLastError());
 	if (getenv("NMFGPU_TC_DEBUG") != nullptr) {
-		unsigned rec[4] = {0, 0, 0, 0};
+		static unsigned rec[4 * 64];
 		CUDA_CHECK(cudaStreamSynchronize(stream));
 		CUDA_CHECK(cudaMemcpyFromSymbol(rec, g_waitTimeout, sizeof(rec)));
-		if (rec[3] != 0) {
-			errorf("tc_stream_gemm<%d,%d>: barrier wait timed out: smem address 0x%x parity %u thread %u block %u", KPM, (int)VC, rec[0], rec[1], rec[2], rec[3] - 1);
-			const unsigned zero[4] = {0, 0, 0, 0};
-			CUDA_CHECK(cudaMemcpyToSymbol(g_waitTimeout, zero, sizeof(zero)));
+		if (rec[0] != 0) {
+			errorf("tc_stream_gemm<%d,%d>: %u barrier waits timed out", KPM, (int)VC, rec[0]);
+			for (unsigned i = 1; i <= rec[0] && i < 64; ++i)
+				if (rec[4 * i + 3] == rec[7])   // the block of the first record
+					errorf("  block %u warp %u: barrier +0x%x parity %u", rec[4 * i + 3], rec[4 * i + 2] / 32, rec[4 * i] & 0x3FF, rec[4 * i + 1]);
+			memset(rec, 0, sizeof(rec));
+			CUDA_CHECK(cudaMemcpyToSymbol(g_waitTimeout, rec, sizeof(rec)));
 		}
 	}
 }
