@@ -46,8 +46,8 @@ constexpr int V_STAGE_BYTES = TILE_ROWS * STAGE_K * 4;
 constexpr int PAIR_ROWS = 2 * TILE_ROWS;   // A rows per stream-K tile: two UMMA tiles that share their B tiles
 constexpr int SLOTS = 4;              // TMEM A operand ring, in tiles (64 columns each: 32 hi + 32 lo)
 constexpr int SLOTS_SHIFT = 2;
-constexpr int SV = 8;                 // shared-memory ring of V tiles (16 KB each): 4 stages of 2 tiles
-constexpr int SV_SHIFT = 3;
+constexpr int SVH = 5;                // shared-memory ring of V tiles (16 KB each): SVH slots per A tile (= per splitter warpgroup)
+constexpr int SV = 2 * SVH;
 constexpr int A_BASE_COL = 256;       // TMEM columns [0, 256): accumulators, [256, 512): A slots
 constexpr int NUM_THREADS = 640;      // 4 helper warps + 16 warps of splitters and flushers
 constexpr uint64_t POLICY_EVICT_FIRST = 0x12F0000000000000ull;
@@ -64,7 +64,7 @@ template <int KPM> struct Rings;
 // SPLIT_WGS must divide the number of A slots: a warpgroup has to be the only writer of its slots, because the parity
 // wait on `empty` only tells two consecutive phases apart (three warpgroups on four slots let a fast one get two
 // phases ahead of a slow one and overwrite a slot that was never consumed -- seen as a deadlock, profiles/r01_notes.md)
-template <> struct Rings<64> { static constexpr int SB = 4, ACC_BUFS = 2, SPLIT_WGS = 2, FLUSH_WGS = 2, HELPER_REGS = 48, SPLIT_REGS = 80, FLUSH_REGS = 136, THREADS = 640; };
+template <> struct Rings<64> { static constexpr int SB = 3, ACC_BUFS = 2, SPLIT_WGS = 2, FLUSH_WGS = 2, HELPER_REGS = 48, SPLIT_REGS = 80, FLUSH_REGS = 136, THREADS = 640; };
 template <> struct Rings<128> { static constexpr int SB = 2, ACC_BUFS = 1, SPLIT_WGS = 2, FLUSH_WGS = 2, HELPER_REGS = 40, SPLIT_REGS = 72, FLUSH_REGS = 144, THREADS = 640; };
 
 // position in a ring of arbitrary depth: slot index plus the parity of the number of completed laps
@@ -245,7 +245,7 @@ __device__ __forceinline__ void traceEvent(unsigned long long* trace, unsigned g
 }
 
 struct __align__(8) Barriers {
-	uint64_t vFull[SV], vEmpty[SV];        // V tile ring: TMA -> splitters
+	uint64_t vFull[SV], vEmpty[SV];        // V tile rings: TMA -> splitters (slot 2 i + w belongs to A tile w)
 	uint64_t bFull[4], bEmpty[4];          // B tile ring: TMA -> MMA
 	uint64_t full[SLOTS], empty[SLOTS];    // A operand slots in tensor memory: splitters -> MMA
 	uint64_t accFull[2], accEmpty[2];      // accumulator buffers: MMA -> flushers
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 	using R = Rings<KPM>;
 	constexpr int SB = R::SB, ACC_BUFS = R::ACC_BUFS, SPLIT_WGS = R::SPLIT_WGS, FLUSH_WGS = R::FLUSH_WGS;
 	static_assert(4 + 4 * (SPLIT_WGS + FLUSH_WGS) == R::THREADS / 32, "warp roles");
-	static_assert(SLOTS % SPLIT_WGS == 0 && SV % SPLIT_WGS == 0, "every ring slot must have a single writer / reader warpgroup");
+	static_assert(SPLIT_WGS == 2, "splitter warpgroup w owns the A slots {w, w + 2} and the V ring of A tile w");
 	constexpr int B_HALF_BYTES = KPM * STAGE_K * 4;
 	extern __shared__ unsigned char smemRaw[];
 	unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~(uintptr_t)1023);
@@ -309,24 +309,30 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 	if (warp == 0) {
 		// ===== V producer =====
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::HELPER_REGS));
-		if (lane == 0) {
+		if (lane < 2) {
+			// lane w loads the tiles of A tile w into that tile's own ring: a slow splitter warpgroup only ever holds
+			// back its own loads
+			const unsigned w = lane;
 			SegmentWalker walk(p, blockIdx.x);
 			Segment s;
-			unsigned t = 0;
+			RingPos v;
 			const uint32_t vBase = smemAddr(vRing);
 			while (walk.next(s)) {
-				const int rIdx = (int)(s.tile * PAIR_ROWS);
+				const int rIdx = (int)(s.tile * PAIR_ROWS + w * TILE_ROWS);
 				int kIdx = (int)(s.stage0 * STAGE_K);
-				for (unsigned ls = 0; ls < s.len; ++ls, kIdx += STAGE_K) {
-#pragma unroll
-					for (int w = 0; w < 2; ++w, ++t) {
-						const unsigned sv = t & (SV - 1);
-						mbarWait(vEmptyBar + sv * 8, ((t >> SV_SHIFT) & 1) ^ 1);
-						const uint32_t full = vFullBar + sv * 8;
-						mbarArriveExpectTx(full, V_STAGE_BYTES);
-						if (V_COLS_ARE_ROWS) tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, kIdx, rIdx + w * TILE_ROWS, POLICY_EVICT_FIRST);
-						else tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, rIdx + w * TILE_ROWS, kIdx, POLICY_EVICT_FIRST);
+				for (unsigned ls = 0; ls < s.len; ++ls, kIdx += STAGE_K, v.advance(SVH)) {
+					const unsigned sv = 2 * v.idx + w;
+					mbarWait(vEmptyBar + sv * 8, v.lap ^ 1);
+					const uint32_t full = vFullBar + sv * 8;
+#ifdef NMFGPU_TC_TRACE_BUILD
+					if (p.passes & 0x2000) {   // ablation: no V loads (timing experiments, results are garbage)
+						mbarArrive(full);
+						continue;
 					}
+#endif
+					mbarArriveExpectTx(full, V_STAGE_BYTES);
+					if (V_COLS_ARE_ROWS) tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, kIdx, rIdx, POLICY_EVICT_FIRST);
+					else tmaLoad2D(vBase + sv * V_STAGE_BYTES, &p.mapV, full, rIdx, kIdx, POLICY_EVICT_FIRST);
 				}
 			}
 		}
@@ -344,6 +350,12 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 				for (unsigned ls = 0; ls < s.len; ++ls, kIdx += STAGE_K, b.advance(SB)) {
 					mbarWait(bEmptyBar + b.idx * 8, b.lap ^ 1);
 					const uint32_t full = bFullBar + b.idx * 8;
+#ifdef NMFGPU_TC_TRACE_BUILD
+					if (p.passes & 0x1000) {   // ablation: no B loads
+						mbarArrive(full);
+						continue;
+					}
+#endif
 					mbarArriveExpectTx(full, bytes);
 					const uint32_t dst = bBase + b.idx * 2 * B_HALF_BYTES;
 					tmaLoad2D(dst, &p.mapBhi, full, kIdx, 0, POLICY_EVICT_LAST);
@@ -418,9 +430,11 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 		const float center = p.center;
 		const unsigned tEnd = 2 * (unsigned)(unitStart(blockIdx.x + 1, p.grid, p.units) - unitStart(blockIdx.x, p.grid, p.units));
 		float v[STAGE_K];
-		auto loadTile = [&](unsigned t) {
-			const unsigned sv = t & (SV - 1);
-			mbarWait(vFullBar + sv * 8, (t >> SV_SHIFT) & 1);
+		RingPos vpos;   // this warpgroup's position in its V ring (SPLIT_WGS == 2: warpgroup wgi reads the ring of A tile wgi)
+		auto loadTile = [&](unsigned) {
+			const unsigned sv = 2 * vpos.idx + wgi;
+			mbarWait(vFullBar + sv * 8, vpos.lap);
+			vpos.advance(SVH);
 			const unsigned char* tile = vRing + sv * V_STAGE_BYTES;
 			if (V_COLS_ARE_ROWS) {
 				// row `row` of the [128][32] tile; 16-byte chunk c lives at chunk c ^ (row & 7)
