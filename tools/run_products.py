@@ -20,6 +20,7 @@ ap.add_argument("--k", type=int, default=64)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--iters", type=int, default=0)
 ap.add_argument("--mode", default="auto")
+ap.add_argument("--algo", default="mu")
 ap.add_argument("--lib", default=None, help="alternative libnmfgpu64.so (A/B comparisons)")
 a = ap.parse_args()
 
@@ -30,7 +31,9 @@ L.set_precision(a.mode)
 dev = L.lib.nmfgpu_b200_device_alloc(a.m * a.n * 4)
 assert dev
 assert L.lib.nmfgpu_b200_device_uniform_f32(dev, a.m, a.n, a.m, 42, a.m, 0, 0) == 0
-s = api.Session(L, "mu", a.m, a.n, a.k, device_ptr=dev, ld_v=a.m)
+PARAMS = {"mu": {}, "gdcls": {"lambda": 0.01}, "als": {}, "acls": {"lambdaW": 0.01, "lambdaH": 0.01},
+          "ahcls": {"lambdaW": 0.01, "lambdaH": 0.01, "alphaW": 0.01, "alphaH": 0.01}, "nsnmf": {"theta": 0.5}}
+s = api.Session(L, a.algo, a.m, a.n, a.k, device_ptr=dev, ld_v=a.m, params=PARAMS[a.algo])
 s.set_factors(uniform_block(43, a.m, a.k), uniform_block(44, a.k, a.n))
 for _ in range(a.reps):
     _, _, t1, t2 = s.products(want_wtv=False, want_vht=False)
