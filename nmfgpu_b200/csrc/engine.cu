@@ -101,6 +101,7 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	m_Gsaved.allocate((size_t)k * k);
 	m_B.allocate((size_t)k * k);
 	m_qr.allocate((size_t)k * k + k);
+	m_inverse.allocate((size_t)k * k);
 
 	// tensor-core eligibility: fp32, rank that fits one UMMA N, TMA-compatible strides
 	m_useTC = false;
@@ -456,7 +457,7 @@ void Engine<T>::iterateLS(bool err) {
 	productWtV(m_W[m_wCur].get());
 	T* H = m_H[m_hCur].get();
 	kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, H, m_ldH, m_stream, m_slotsN, false, m_corrN);
-	kern::qrSolveClamp<T>(k, m_qr.get(), H, m_ldH, n, false, m_stream);
+	kern::qrSolveClamp<T>(k, m_qr.get(), H, m_ldH, n, false, m_stream, m_inverse.get());
 	m_launches += 4;
 	if (m_useTC) {
 		tc::splitTransposeH(k, n, reinterpret_cast<float*>(H), m_ldH, m_HtHi.get(), m_HtLo.get(), m_ldHt, m_stream);
@@ -500,7 +501,7 @@ void Engine<T>::iterateLS(bool err) {
 				kern::columnDots<T>(m, k, m_W[m_wCur].get(), m_ldW, Wnext, m_ldW, m_partN.get(), m_stream);
 				m_launches += 1;
 			}
-			kern::qrSolveClamp<T>(k, m_qr.get(), Wnext, m_ldW, m, true, m_stream);
+			kern::qrSolveClamp<T>(k, m_qr.get(), Wnext, m_ldW, m, true, m_stream, m_inverse.get());
 			m_wCur = 1 - m_wCur;
 			const unsigned blocks = kern::columnSquares<T>(m, k, m_W[m_wCur].get(), m_ldW, m_colSqPartials.get(), m_stream);
 			m_launches += 2;

@@ -115,7 +115,7 @@ private:
 	size_t m_ldV = 0, m_ldW = 0, m_ldH = 0;
 	DeviceBuffer<T> m_V, m_W[2], m_H[2];
 	int m_wCur = 0, m_hCur = 0;
-	DeviceBuffer<T> m_G, m_Gsaved, m_B, m_kkScratch, m_qr;
+	DeviceBuffer<T> m_G, m_Gsaved, m_B, m_kkScratch, m_qr, m_inverse;
 	DeviceBuffer<T> m_Npart, m_Ppart, m_smoothW, m_smoothH;
 	unsigned m_splitsN = 1, m_splitsP = 1, m_splitsGW = 1, m_splitsGH = 1;
 	size_t m_strideN = 0, m_strideP = 0;

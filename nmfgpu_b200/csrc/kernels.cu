@@ -543,49 +543,50 @@ __global__ void __launch_bounds__(256) qr_factor_kernel(unsigned k, const T* __r
 	T* a = reinterpret_cast<T*>(smem_raw);  // [k][k] column-major
 	T* tau = a + (size_t)k * k;
 	__shared__ T s_norm, s_tau, s_scale, s_beta;
-	__shared__ T red[256];
 	const unsigned tid = threadIdx.x;
 	for (unsigned idx = tid; idx < k * k; idx += 256) a[idx] = G[idx];
 	__syncthreads();
+	const unsigned lane = tid % 32, warp = tid / 32;
 	for (unsigned j = 0; j < k; ++j) {
 		T* col = a + (size_t)j * k;
-		T part = T(0);
-		for (unsigned i = j + tid; i < k; i += 256) part += col[i] * col[i];
-		red[tid] = part;
-		__syncthreads();
-		for (unsigned o = 128; o > 0; o >>= 1) {
-			if (tid < o) red[tid] += red[tid + o];
-			__syncthreads();
-		}
-		if (tid == 0) {
-			const T norm = sqrt(red[0]);
-			s_norm = norm;
-			if (norm == T(0)) {
-				s_tau = T(0);
-				s_scale = T(0);
-				s_beta = T(0);
-			} else {
-				const T alpha = col[j];
-				const T beta = alpha >= T(0) ? -norm : norm;
-				s_tau = (beta - alpha) / beta;
-				s_scale = T(1) / (alpha - beta);
-				s_beta = beta;
+		if (warp == 0) {   // Householder vector of column j: one warp, shuffle reduction
+			T part = T(0);
+			for (unsigned i = j + lane; i < k; i += 32) part += col[i] * col[i];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+			if (lane == 0) {
+				const T norm = sqrt(part);
+				s_norm = norm;
+				if (norm == T(0)) {
+					s_tau = T(0);
+					s_scale = T(0);
+					s_beta = T(0);
+				} else {
+					const T alpha = col[j];
+					const T beta = alpha >= T(0) ? -norm : norm;
+					s_tau = (beta - alpha) / beta;
+					s_scale = T(1) / (alpha - beta);
+					s_beta = beta;
+				}
+				tau[j] = s_tau;
 			}
-			tau[j] = s_tau;
 		}
 		__syncthreads();
 		if (s_norm != T(0)) {
 			for (unsigned i = j + 1 + tid; i < k; i += 256) col[i] *= s_scale;
 			__syncthreads();
 			if (tid == 0) col[j] = s_beta;
-			// apply the reflector to the trailing columns: one thread per column
-			for (unsigned c = j + 1 + tid; c < k; c += 256) {
+			// apply the reflector (v_j = 1, v_i = col[i]) to the trailing columns: one warp per column, lanes along the
+			// rows (contiguous in shared memory), so all 256 threads work and no access is bank-conflicted
+			const T tj = s_tau;
+			for (unsigned c = j + 1 + warp; c < k; c += 8) {
 				T* cc = a + (size_t)c * k;
-				T dot = cc[j];
-				for (unsigned i = j + 1; i < k; ++i) dot = fma(col[i], cc[i], dot);
-				dot *= s_tau;
-				cc[j] -= dot;
-				for (unsigned i = j + 1; i < k; ++i) cc[i] -= dot * col[i];
+				T part = T(0);
+				for (unsigned i = j + lane; i < k; i += 32) part = fma(i == j ? T(1) : col[i], cc[i], part);
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+				const T dot = part * tj;
+				for (unsigned i = j + lane; i < k; i += 32) cc[i] -= dot * (i == j ? T(1) : col[i]);
 			}
 		}
 		__syncthreads();
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(256) qr_factor_kernel(unsigned k, const T* __r
 // one thread per right-hand side; the vector lives in shared memory (stride k+1, conflict free)
 template <typename T>
 __global__ void __launch_bounds__(64) qr_solve_clamp_kernel(unsigned k, const T* __restrict__ factor, T* __restrict__ R, size_t ldr,
-                                                           unsigned nrhs, bool transposed) {
+                                                           unsigned nrhs, bool transposed, bool clamp) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	T* xs = reinterpret_cast<T*>(smem_raw);  // [64][k+1]
 	const unsigned tid = threadIdx.x;
@@ -639,7 +640,7 @@ __global__ void __launch_bounds__(64) qr_solve_clamp_kernel(unsigned k, const T*
 			const unsigned q = base + tid;
 			if (q < nrhs) {
 				const T v = xs[tid * ld + c];
-				R[(size_t)c * ldr + q] = v > T(0) ? v : T(0);
+				R[(size_t)c * ldr + q] = (v > T(0) || !clamp) ? v : T(0);
 			}
 		}
 	} else {
@@ -648,7 +649,7 @@ __global__ void __launch_bounds__(64) qr_solve_clamp_kernel(unsigned k, const T*
 			const unsigned q = base + qq;
 			if (q < nrhs) {
 				const T v = xs[qq * ld + c];
-				R[(size_t)q * ldr + c] = v > T(0) ? v : T(0);
+				R[(size_t)q * ldr + c] = (v > T(0) || !clamp) ? v : T(0);
 			}
 		}
 	}
@@ -664,6 +665,106 @@ void allowSmem(K kernel, size_t bytes) {
 	if (bytes <= allowed) return;
 	CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 	allowed = bytes;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Least-squares updates with the explicit k x k inverse M = R^-1 Q^T of the (regularised) Gram matrix:
+//   X (k x n) <- max(0, M X)          and          X (m x k) <- max(0, X M^T)
+// as register-tiled products (the same tiling as the multiplicative updates).  One thread per right-hand
+// side walking the Householder vectors (qr_solve_clamp_kernel) costs 2-4 ms at cfg 4; this costs ~0.1 ms.
+// ---------------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(256) apply_left_clamp(unsigned k, unsigned n, const float* __restrict__ M, float* __restrict__ X, size_t ldx) {
+	constexpr int COLS = 64, RPT = KP / 16, LDJ = COLS + 4;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float* Ms = reinterpret_cast<float*>(smem_raw);  // [KP t][KP r]: Ms[t*KP + r] = M[r + t*k]
+	float* Xs = Ms + KP * KP;                         // [KP t][LDJ]
+	const unsigned tid = threadIdx.x, j0 = blockIdx.x * COLS;
+	for (unsigned idx = tid; idx < KP * KP; idx += 256) {
+		const unsigned r = idx % KP, t = idx / KP;
+		Ms[idx] = (r < k && t < k) ? M[(size_t)t * k + r] : 0.f;
+	}
+	for (unsigned idx = tid; idx < COLS * KP; idx += 256) {
+		const unsigned t = idx % KP, j = idx / KP;
+		Xs[t * LDJ + j] = (j0 + j < n && t < k) ? X[(size_t)(j0 + j) * ldx + t] : 0.f;
+	}
+	__syncthreads();
+	const unsigned rx = tid % 16, jx = tid / 16;
+	float acc[RPT][4];
+#pragma unroll
+	for (int i = 0; i < RPT; ++i)
+#pragma unroll
+		for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+#pragma unroll 8
+	for (int t = 0; t < KP; ++t) {
+		float a[RPT];
+#pragma unroll
+		for (int i = 0; i < RPT; ++i) a[i] = Ms[t * KP + rx * RPT + i];
+		const float4 b = *reinterpret_cast<const float4*>(Xs + t * LDJ + jx * 4);
+#pragma unroll
+		for (int i = 0; i < RPT; ++i) {
+			acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+			acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+			acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+			acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+		}
+	}
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		const unsigned j = j0 + jx * 4 + q;
+#pragma unroll
+		for (int i = 0; i < RPT; ++i) {
+			const unsigned r = rx * RPT + i;
+			if (j < n && r < k) X[(size_t)j * ldx + r] = fmaxf(acc[i][q], 0.f);
+		}
+	}
+}
+
+template <int KP>
+__global__ void __launch_bounds__(256) apply_right_clamp(unsigned m, unsigned k, const float* __restrict__ M, float* __restrict__ X, size_t ldx) {
+	constexpr int ROWS = 128, CPT = KP / 8;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float* Xs = reinterpret_cast<float*>(smem_raw);  // [KP t][ROWS]
+	float* Bs = Xs + KP * ROWS;                       // [KP t][KP c]: Bs[t*KP + c] = M[c + t*k]  (= M^T[t, c])
+	const unsigned tid = threadIdx.x, i0 = blockIdx.x * ROWS;
+	for (unsigned idx = tid; idx < KP * ROWS; idx += 256) {
+		const unsigned r = idx % ROWS, t = idx / ROWS;
+		Xs[idx] = (i0 + r < m && t < k) ? X[(size_t)t * ldx + i0 + r] : 0.f;
+	}
+	for (unsigned idx = tid; idx < KP * KP; idx += 256) {
+		const unsigned c = idx % KP, t = idx / KP;
+		Bs[idx] = (c < k && t < k) ? M[(size_t)t * k + c] : 0.f;
+	}
+	__syncthreads();
+	const unsigned tx = tid % 32, ty = tid / 32;
+	float acc[4][CPT];
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+#pragma unroll
+		for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+	for (int t = 0; t < KP; ++t) {
+		const float4 a = *reinterpret_cast<const float4*>(Xs + t * ROWS + tx * 4);
+		float b[CPT];
+#pragma unroll
+		for (int j = 0; j < CPT; ++j) b[j] = Bs[t * KP + ty * CPT + j];
+#pragma unroll
+		for (int j = 0; j < CPT; ++j) {
+			acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
+			acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
+			acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
+			acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+		}
+	}
+	const unsigned r0 = i0 + tx * 4;
+#pragma unroll
+	for (int j = 0; j < CPT; ++j) {
+		const unsigned c = ty * CPT + j;
+		if (c >= k) continue;
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			if (r0 + i < m) X[(size_t)c * ldx + r0 + i] = fmaxf(acc[i][j], 0.f);
+	}
 }
 
 }  // namespace
@@ -868,11 +969,47 @@ void qrFactor(unsigned k, const T* G, T* factor, cudaStream_t stream) {
 }
 
 template <typename T>
-void qrSolveClamp(unsigned k, const T* factor, T* R, size_t ldr, unsigned nrhs, bool transposed, cudaStream_t stream) {
+static void qrSolveGeneric(unsigned k, const T* factor, T* R, size_t ldr, unsigned nrhs, bool transposed, bool clamp, cudaStream_t stream) {
 	const size_t smem = sizeof(T) * 64 * ((size_t)k + 1);
 	allowSmem(qr_solve_clamp_kernel<T>, smem);
-	qr_solve_clamp_kernel<T><<<ceilDiv(nrhs, 64), 64, smem, stream>>>(k, factor, R, ldr, nrhs, transposed);
+	qr_solve_clamp_kernel<T><<<ceilDiv(nrhs, 64), 64, smem, stream>>>(k, factor, R, ldr, nrhs, transposed, clamp);
 	launchCheck();
+}
+
+template <int KP>
+static void applyInverse(unsigned k, const float* M, float* R, size_t ldr, unsigned nrhs, bool transposed, cudaStream_t stream) {
+	if (transposed) {
+		const size_t smem = sizeof(float) * ((size_t)KP * KP + (size_t)KP * 128);
+		allowSmem(apply_right_clamp<KP>, smem);
+		apply_right_clamp<KP><<<ceilDiv(nrhs, 128), 256, smem, stream>>>(nrhs, k, M, R, ldr);
+	} else {
+		const size_t smem = sizeof(float) * ((size_t)KP * KP + (size_t)KP * (64 + 4));
+		allowSmem(apply_left_clamp<KP>, smem);
+		apply_left_clamp<KP><<<ceilDiv(nrhs, 64), 256, smem, stream>>>(k, nrhs, M, R, ldr);
+	}
+	launchCheck();
+}
+
+template <>
+void qrSolveClamp<float>(unsigned k, const float* factor, float* R, size_t ldr, unsigned nrhs, bool transposed, cudaStream_t stream, float* inverseScratch) {
+	if (inverseScratch == nullptr || k > 128 || nrhs < 4 * k) {
+		qrSolveGeneric<float>(k, factor, R, ldr, nrhs, transposed, true, stream);
+		return;
+	}
+	// M = R^-1 Q^T: the factorisation applied to the identity, then one tiled product per side
+	CUDA_CHECK(cudaMemsetAsync(inverseScratch, 0, (size_t)k * k * sizeof(float), stream));
+	add_constraint_kernel<float><<<dim3(ceilDiv(k, 128), k), 128, 0, stream>>>(k, inverseScratch, 0.f, 1.f);
+	launchCheck();
+	qrSolveGeneric<float>(k, factor, inverseScratch, k, k, false, false, stream);
+	if (k <= 16) applyInverse<16>(k, inverseScratch, R, ldr, nrhs, transposed, stream);
+	else if (k <= 32) applyInverse<32>(k, inverseScratch, R, ldr, nrhs, transposed, stream);
+	else if (k <= 64) applyInverse<64>(k, inverseScratch, R, ldr, nrhs, transposed, stream);
+	else applyInverse<128>(k, inverseScratch, R, ldr, nrhs, transposed, stream);
+}
+
+template <>
+void qrSolveClamp<double>(unsigned k, const double* factor, double* R, size_t ldr, unsigned nrhs, bool transposed, cudaStream_t stream, double*) {
+	qrSolveGeneric<double>(k, factor, R, ldr, nrhs, transposed, true, stream);
 }
 
 void splitTf32(unsigned rows, unsigned cols, const float* X, size_t ldx, float* hi, float* lo, size_t ldo, cudaStream_t stream) {
@@ -896,7 +1033,7 @@ void splitTf32(unsigned rows, unsigned cols, const float* X, size_t ldx, float* 
 	template void smoothRight<T>(unsigned, unsigned, const T*, size_t, T*, size_t, T, cudaStream_t);                                      \
 	template void smoothLeft<T>(unsigned, unsigned, const T*, size_t, T*, size_t, T, cudaStream_t);                                       \
 	template void qrFactor<T>(unsigned, const T*, T*, cudaStream_t);                                                                      \
-	template void qrSolveClamp<T>(unsigned, const T*, T*, size_t, unsigned, bool, cudaStream_t);
+
 NMF_INSTANTIATE(float)
 NMF_INSTANTIATE(double)
 #undef NMF_INSTANTIATE

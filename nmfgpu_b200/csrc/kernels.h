@@ -103,7 +103,8 @@ void smoothLeft(unsigned k, unsigned n, const T* H, size_t ldh, T* Y, size_t ldy
 template <typename T>
 void qrFactor(unsigned k, const T* G, T* factor, cudaStream_t stream);
 template <typename T>
-void qrSolveClamp(unsigned k, const T* factor, T* R, size_t ldr, unsigned nrhs, bool transposed, cudaStream_t stream);
+void qrSolveClamp(unsigned k, const T* factor, T* R, size_t ldr, unsigned nrhs, bool transposed, cudaStream_t stream,
+                  T* inverseScratch = nullptr);   // k*k values: fp32 goes through the explicit inverse R^-1 Q^T and a tiled product
 
 // TF32 hi/lo split of a dense block: hi = rn_tf32(x), lo = x - hi
 void splitTf32(unsigned rows, unsigned cols, const float* X, size_t ldx, float* hi, float* lo, size_t ldo, cudaStream_t stream);
