@@ -14,7 +14,7 @@ def load(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIBRARY
+    p = path or os.environ.get("NMFGPU_LIB") or LIBRARY   # NMFGPU_LIB: load another build (A/B and bisecting tools)
     if not os.path.exists(p):
         raise RuntimeError("%s not found: build it with `python -m nmfgpu_b200.build` (nvcc, sm_100a). "
                            "nmfgpu_b200 has no CPU fallback." % p)

@@ -15,12 +15,18 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIBRARY = os.path.join(LIBDIR, "libnmfgpu64.so")
+# diagnostic variants: NMFGPU_BUILD_EXTRA="-DNMFGPU_TC_CHECK_BUILD ..." NMFGPU_BUILD_OUT=tools/bin/lib_x.so build next to
+# the product library (own object directory), and tools load them through NMFGPU_LIB
+if os.environ.get("NMFGPU_BUILD_OUT"):
+    LIBRARY = os.path.abspath(os.environ["NMFGPU_BUILD_OUT"])
+    OBJDIR = os.path.join(LIBDIR, "obj_" + os.path.basename(LIBRARY).replace(".", "_"))
 
 SOURCES = ["api.cpp", "host.cpp", "dist.cpp", "engine.cu", "kernels.cu", "tc_gemm.cu", "kmeans.cu", "sparse.cu",
            "init_kernels.cu", "session.cu"]
 
 # NMFGPU_TC_TRACE_BUILD=1 compiles the timeline / ablation hooks of tc_gemm.cu in (diagnostic builds only)
 EXTRA = ["-DNMFGPU_TC_TRACE_BUILD"] if os.environ.get("NMFGPU_TC_TRACE_BUILD") else []
+EXTRA += os.environ.get("NMFGPU_BUILD_EXTRA", "").split()
 NVCC_FLAGS = EXTRA + ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unknown-pragmas", "-DNMFGPU_EXPORTING",
               "-I", os.path.join(os.path.dirname(HERE), "include")]

@@ -312,6 +312,8 @@ void Engine<T>::gramH(const T* H, size_t ldh, T* B) {
 template <typename T>
 void Engine<T>::productWtV(const T* W) {
 	if (m_useTC) {
+		static const bool poison = getenv("NMFGPU_TC_POISON") != nullptr;   // debugging: an unwritten slot shows up as NaN
+		if (poison) CUDA_CHECK(cudaMemsetAsync(m_Npart.get(), 0xFF, m_Npart.bytes(), m_stream));
 		tc::gemmWtV(m_tc->plan, reinterpret_cast<float*>(m_Npart.get()), m_ldH, m_strideN, m_stream);
 	} else {
 		kern::gemmTN<T>(m_cfg.m, m_cfg.k, m_cfg.n, W, m_ldW, m_V.get(), m_ldV, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_stream);
@@ -322,6 +324,8 @@ void Engine<T>::productWtV(const T* W) {
 template <typename T>
 void Engine<T>::productVHt(const T* H, size_t ldh) {
 	if (m_useTC) {
+		static const bool poison = getenv("NMFGPU_TC_POISON") != nullptr;
+		if (poison) CUDA_CHECK(cudaMemsetAsync(m_Ppart.get(), 0xFF, m_Ppart.bytes(), m_stream));
 		tc::gemmVHt(m_tc->plan, reinterpret_cast<float*>(m_Ppart.get()), m_ldW, m_strideP, m_stream);
 	} else {
 		kern::gemmNT<T>(m_cfg.m, m_cfg.n, m_cfg.k, m_V.get(), m_ldV, H, ldh, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, m_stream);

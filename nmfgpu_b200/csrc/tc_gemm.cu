@@ -435,22 +435,29 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 			const unsigned sv = 2 * vpos.idx + wgi;
 			mbarWait(vFullBar + sv * 8, vpos.lap);
 			vpos.advance(SVH);
-			const unsigned char* tile = vRing + sv * V_STAGE_BYTES;
+			const uint32_t tile = smemAddr(vRing) + sv * V_STAGE_BYTES;
 			if (V_COLS_ARE_ROWS) {
 				// row `row` of the [128][32] tile; 16-byte chunk c lives at chunk c ^ (row & 7)
-				const unsigned char* base = tile + row * 128;
+				const uint32_t base = tile + row * 128;
 #pragma unroll
-				for (int c = 0; c < 8; ++c) {
-					const float4 x = *reinterpret_cast<const float4*>(base + ((c ^ (row & 7)) << 4));
-					v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
-				}
+				for (int c = 0; c < 8; ++c)
+					asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+					             : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3])
+					             : "r"(base + ((c ^ (row & 7)) << 4))
+					             : "memory");
 			} else {
-				const float* base = reinterpret_cast<const float*>(tile) + row;
+				const uint32_t base = tile + row * 4;
 #pragma unroll
-				for (int j = 0; j < STAGE_K; ++j) v[j] = base[j * TILE_ROWS];
+				for (int j = 0; j < STAGE_K; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[j]) : "r"(base + j * TILE_ROWS * 4) : "memory");
 			}
-			// the tile is in registers: release the slot (one arrival per warp: 128 per-thread arrivals on one
-			// mbarrier serialise in the barrier unit and delay the TMA completions that share it)
+			// Release the slot only after the loads have been PERFORMED.  Issue order is not enough: an LDS that is still
+			// queued behind TMA writes and MMA operand reads when the arrive reaches the barrier lets the producer refill
+			// the slot under it, and for W^T V the refill is fast (256-byte L2 promotion: every second stage of a column
+			// tile is already in L2).  Seen as a few A rows of ~1e-3 of the tile stages carrying wrong data, differently on
+			// every run, in W^T V only (tools/race_check.py, profiles/r01_notes.md finding 10).  The CTA-scope fence makes every thread wait for
+			// its loads; then one arrival per warp (128 per-thread arrivals on one mbarrier serialise in the barrier unit
+			// and delay the TMA completions that share it).
+			asm volatile("fence.acq_rel.cta;" ::: "memory");
 			__syncwarp();
 			if (lane == 0) mbarArrive(vEmptyBar + sv * 8);
 		};
@@ -460,6 +467,8 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 			mbarWait(emptyBar + sl * 8, ((t >> SLOTS_SHIFT) & 1) ^ 1);
 			tcFenceAfter();
 			const uint32_t aSlot = tmem + laneBase + A_BASE_COL + sl * 64;
+			// ptxas guards the source registers of a tcgen05.st with a read scoreboard, so hi/lo may be reused for the
+			// second half without waiting for the first stores
 #pragma unroll
 			for (int h = 0; h < 2; ++h) {
 				uint32_t hi[16], lo[16];

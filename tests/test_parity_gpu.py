@@ -116,7 +116,8 @@ def test_golden_traces(L):
         np.testing.assert_allclose(r["H"].sum(axis=1), g["h_rowsum"], rtol=2e-3)
 
 
-@pytest.mark.parametrize("shape", [(1000, 500, 10), (777, 333, 64), (4100, 1300, 128), (260, 130, 7), (2048, 4096, 32)])
+@pytest.mark.parametrize("shape", [(1000, 500, 10), (777, 333, 64), (4100, 1300, 128), (260, 130, 7), (2048, 4096, 32),
+                                   (33, 17, 3), (128, 128, 128), (5000, 129, 65), (20000, 5000, 64), (64, 3000, 1)])
 @pytest.mark.parametrize("precision", ["auto", "fp32"])
 def test_v_sized_products(L, shape, precision):
     """W^T V and V H^T (the two hot kernels) against numpy fp64, ragged shapes included."""
@@ -136,6 +137,50 @@ def test_v_sized_products(L, shape, precision):
     tol = 5e-7 if precision == "auto" else 2e-6
     assert rel(wtv, W64.T @ V64) <= tol
     assert rel(vht, V64 @ H64.T) <= tol
+
+
+@pytest.mark.parametrize("shape", [(20000, 5000, 64), (60000, 2000, 48), (20000, 6000, 128)])
+def test_products_are_deterministic(L, shape):
+    """static stream-K slots and no atomics: repeated products must agree bit for bit (any difference is a
+    synchronisation bug; long reductions with many CTAs per tile are the sensitive case, tools/race_check.py)"""
+    m, n, k = shape
+    V, W0, H0 = dense_inputs(m, n, k, seed=11)
+    first = None
+    for _ in range(4):
+        s = api.Session(L, "mu", m, n, k, V=V)
+        try:
+            s.set_factors(W0, H0)
+            wtv, vht, _, _ = s.products()
+        finally:
+            s.close()
+        if first is None:
+            first = (wtv.copy(), vht.copy())
+        else:
+            np.testing.assert_array_equal(wtv, first[0])
+            np.testing.assert_array_equal(vht, first[1])
+
+
+def test_batched_iterations_match_single_steps(L):
+    """iterations issued as CUDA-graph batches (session_iterate) == the same number of single steps"""
+    V, W0, H0 = dense_inputs(3000, 1500, 24, seed=3)
+    out = []
+    for batched in (True, False):
+        s = api.Session(L, "mu", 3000, 1500, 24, V=V)
+        try:
+            s.set_factors(W0, H0)
+            if batched:
+                s.iterate(25)
+            else:
+                for _ in range(25):
+                    s.iterate(1)
+            f, _ = s.iterate_with_error()
+            W, H = s.get_factors()
+            out.append((f, W, H))
+        finally:
+            s.close()
+    assert out[0][0] == out[1][0]
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_array_equal(out[0][2], out[1][2])
 
 
 def test_single_pass_tf32_is_not_enough(L):
