@@ -18,6 +18,11 @@ struct NcclApi {
 	ncclResult_t (*getUniqueId)(ncclUniqueId*) = nullptr;
 	ncclResult_t (*commInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*allReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*allGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*groupStart)() = nullptr;
+	ncclResult_t (*groupEnd)() = nullptr;
 	ncclResult_t (*commDestroy)(ncclComm_t) = nullptr;
 	const char* (*getErrorString)(ncclResult_t) = nullptr;
 };
@@ -36,10 +41,16 @@ NcclApi& api() {
 		a.getUniqueId = reinterpret_cast<decltype(a.getUniqueId)>(dlsym(a.handle, "ncclGetUniqueId"));
 		a.commInitRank = reinterpret_cast<decltype(a.commInitRank)>(dlsym(a.handle, "ncclCommInitRank"));
 		a.allReduce = reinterpret_cast<decltype(a.allReduce)>(dlsym(a.handle, "ncclAllReduce"));
+		a.allGather = reinterpret_cast<decltype(a.allGather)>(dlsym(a.handle, "ncclAllGather"));
+		a.send = reinterpret_cast<decltype(a.send)>(dlsym(a.handle, "ncclSend"));
+		a.recv = reinterpret_cast<decltype(a.recv)>(dlsym(a.handle, "ncclRecv"));
+		a.groupStart = reinterpret_cast<decltype(a.groupStart)>(dlsym(a.handle, "ncclGroupStart"));
+		a.groupEnd = reinterpret_cast<decltype(a.groupEnd)>(dlsym(a.handle, "ncclGroupEnd"));
 		a.commDestroy = reinterpret_cast<decltype(a.commDestroy)>(dlsym(a.handle, "ncclCommDestroy"));
 		a.getErrorString = reinterpret_cast<decltype(a.getErrorString)>(dlsym(a.handle, "ncclGetErrorString"));
 	});
-	if (!a.handle || !a.getUniqueId || !a.commInitRank || !a.allReduce || !a.commDestroy)
+	if (!a.handle || !a.getUniqueId || !a.commInitRank || !a.allReduce || !a.commDestroy || !a.allGather || !a.send || !a.recv || !a.groupStart ||
+	    !a.groupEnd)
 		throw EngineError(ResultType::ErrorExternalLibrary, "NCCL (libnccl.so.2) could not be loaded");
 	return a;
 }
@@ -91,6 +102,21 @@ void Communicator::allReduceSum(float* buffer, size_t count, cudaStream_t stream
 void Communicator::allReduceSum(double* buffer, size_t count, cudaStream_t stream) {
 	if (m_world <= 1) return;
 	ncclCheck(api().allReduce(buffer, buffer, count, ncclDouble, ncclSum, static_cast<ncclComm_t>(m_comm), stream), "ncclAllReduce");
+	++m_calls;
+}
+
+void Communicator::allGather(const float* send, float* recv, size_t countPerRank, cudaStream_t stream) {
+	if (m_world <= 1) return;
+	ncclCheck(api().allGather(send, recv, countPerRank, ncclFloat, static_cast<ncclComm_t>(m_comm), stream), "ncclAllGather");
+	++m_calls;
+}
+
+void Communicator::exchange(const std::vector<Transfer>& sends, const std::vector<Transfer>& recvs, cudaStream_t stream) {
+	if (m_world <= 1) return;
+	ncclCheck(api().groupStart(), "ncclGroupStart");
+	for (const Transfer& t : sends) ncclCheck(api().send(t.buffer, t.count, ncclFloat, t.peer, static_cast<ncclComm_t>(m_comm), stream), "ncclSend");
+	for (const Transfer& t : recvs) ncclCheck(api().recv(t.buffer, t.count, ncclFloat, t.peer, static_cast<ncclComm_t>(m_comm), stream), "ncclRecv");
+	ncclCheck(api().groupEnd(), "ncclGroupEnd");
 	++m_calls;
 }
 

@@ -1,10 +1,16 @@
 // dist.h -- column-sharded multi-GPU execution (the reference is single-GPU only).
 //
 // One process per GPU.  Rank g holds V[:, J_g] and H[:, J_g]; W and the k x k Gram matrices are
-// replicated.  Per iteration exactly two buffers cross NVLink: the m x k partial V H^T and the k x k
-// partial H H^T (plus one scalar on error iterations).  NCCL is resolved with dlopen at the time a
-// communicator is created, so the single-GPU library has no NCCL dependency.
+// replicated.  Two dataflows (engine.cu):
+//   all-reduce  : per iteration the m x k partial V H^T and the k x k partial H H^T are all-reduced and every rank
+//                 repeats the W update (all algorithms);
+//   row owners  : every rank additionally holds the row block V[I_g, :] (built once from the column shards by a
+//                 grouped send/recv), so V[I_g, :] H^T needs no reduction; per iteration H (k x n) and the
+//                 updated row blocks of W (m x k) are all-gathered and k*k + k statistics all-reduced (MU).
+// NCCL is resolved with dlopen at the time a communicator is created, so the single-GPU library has no NCCL dependency.
 #pragma once
+#include <vector>
+
 #include "common.h"
 
 namespace nmfgpu {
@@ -25,6 +31,15 @@ public:
 
 	void allReduceSum(float* buffer, size_t count, cudaStream_t stream);
 	void allReduceSum(double* buffer, size_t count, cudaStream_t stream);
+	// recv[r * countPerRank ...] <- send of rank r (equal counts on every rank)
+	void allGather(const float* send, float* recv, size_t countPerRank, cudaStream_t stream);
+	// one grouped point-to-point exchange: every send/recv pair of the group proceeds concurrently
+	struct Transfer {
+		float* buffer;
+		size_t count;
+		int peer;
+	};
+	void exchange(const std::vector<Transfer>& sends, const std::vector<Transfer>& recvs, cudaStream_t stream);
 	double allReduceSumHost(double value);  // blocking; used once per error iteration
 	unsigned long long calls() const { return m_calls; }
 

@@ -166,6 +166,146 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	synchronize();
 	std::copy(m_hostSecond.get(), m_hostSecond.get() + n, m_vtvSorted.begin());
 	std::sort(m_vtvSorted.begin(), m_vtvSorted.end());
+	setupRowOwners();
+}
+
+// ---- row-owner dataflow for column shards (dist.h) ----------------------------------------------------------
+// The all-reduce dataflow repeats the whole W update on every rank and moves 2 x 4mk bytes per rank and iteration.
+// Here rank g also keeps the row block V[I_g, :] (one grouped send/recv of the column shards at setup; V is then
+// resident twice, 2 x 4mn/G bytes per GPU), so that
+//   H update : columns J_g from W^T V[:, J_g] as before, then all-gather of H (4kn bytes),
+//   W update : rows I_g from V[I_g, :] H^T -- no reduction --, all-reduce of k*k + k statistics of the un-normalised
+//              block (Gram matrix, whose diagonal holds the column norms, and column sums), all-gather of the unit-column
+//              blocks (4mk bytes).
+// Every W-side kernel works on m/G rows; W^T W falls out of the statistics.  Needs equal column shards.
+template <typename T>
+void Engine<T>::setupRowOwners() {
+	Communicator* comm = m_cfg.comm;
+	if (comm == nullptr || comm->worldSize() <= 1) return;
+	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
+	const unsigned G = (unsigned)comm->worldSize(), rank = (unsigned)comm->rank();
+	const unsigned N = comm->globalColumns();
+	const unsigned mrPad = (unsigned)roundUp(ceilDiv(m, G), 256);
+	const char* mode = getenv("NMFGPU_DIST_MODE");
+	bool ok = std::is_same<T, float>::value && m_useTC && m_cfg.algorithm == NmfAlgorithm::Multiplicative && !m_cfg.constantW &&
+	          !(mode != nullptr && strcmp(mode, "allreduce") == 0) && (unsigned long long)n * G == N && comm->columnOffset() == rank * n &&
+	          (unsigned long long)(G - 1) * mrPad < m;
+	if (ok) {
+		const unsigned r0 = rank * mrPad, mr = std::min(mrPad, m - r0);
+		ok = tc::shapeSupported(mr, N, k, roundUp(mr, 32), m_ldW);
+	}
+	// every rank must take the same path: the collectives of the two dataflows do not match
+	if (comm->allReduceSumHost(ok ? 1.0 : 0.0) != (double)G) return;
+
+	m_rowOwners = true;
+	m_globalN = N;
+	m_mrPad = mrPad;
+	m_r0 = rank * mrPad;
+	m_mr = std::min(mrPad, m - m_r0);
+	m_ldVr = roundUp(m_mr, 32);
+	auto rowsOf = [&](unsigned g) { return std::min(mrPad, m - g * mrPad); };
+
+	// ---- V[I_g, :] from the column shards: rank g sends V[I_h, J_g] to every h, packed with the receiver's leading dimension
+	m_Vr.allocate(m_ldVr * N);
+	m_Vr.zero(m_stream);
+	{
+		size_t total = 0;
+		for (unsigned h = 0; h < G; ++h)
+			if (h != rank) total += roundUp(rowsOf(h), 32) * n;
+		DeviceBuffer<float> pack;
+		pack.allocate(total);
+		pack.zero(m_stream);
+		std::vector<Communicator::Transfer> sends, recvs;
+		size_t at = 0;
+		const float* V = reinterpret_cast<const float*>(m_V.get());
+		for (unsigned h = 0; h < G; ++h) {
+			const size_t ldh = roundUp(rowsOf(h), 32);
+			if (h == rank) {
+				CUDA_CHECK(cudaMemcpy2DAsync(m_Vr.get() + m_ldVr * ((size_t)rank * n), m_ldVr * sizeof(float), V + m_r0, m_ldV * sizeof(float),
+				                             (size_t)m_mr * sizeof(float), n, cudaMemcpyDeviceToDevice, m_stream));
+				continue;
+			}
+			CUDA_CHECK(cudaMemcpy2DAsync(pack.get() + at, ldh * sizeof(float), V + (size_t)h * mrPad, m_ldV * sizeof(float),
+			                             (size_t)rowsOf(h) * sizeof(float), n, cudaMemcpyDeviceToDevice, m_stream));
+			sends.push_back({pack.get() + at, ldh * n, (int)h});
+			recvs.push_back({m_Vr.get() + m_ldVr * ((size_t)h * n), m_ldVr * n, (int)h});
+			at += ldh * n;
+		}
+		comm->exchange(sends, recvs, m_stream);
+		synchronize();
+	}
+
+	// ---- operands and plan of V[I_g, :] H^T
+	m_ldHtFull = roundUp(N, 32);
+	m_Hfull.allocate(m_ldH * N);
+	m_HtHiFull.allocate(m_ldHtFull * k);
+	m_HtLoFull.allocate(m_ldHtFull * k);
+	m_Hfull.zero(m_stream);
+	m_HtHiFull.zero(m_stream);
+	m_HtLoFull.zero(m_stream);
+	m_tcR.reset(new TcPlan());
+	const float center = tc::meanOf(m_Vr.get(), m_mr, N, m_ldVr, m_stream);
+	tc::makePlan(m_tcR->plan, m_mr, N, k, m_Vr.get(), m_ldVr, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, m_ldW, m_HtHiFull.get(), m_HtLoFull.get(),
+	             m_ldHtFull, m_cfg.precision == Precision::Tf32x1, center);
+	m_splitsPr = m_tcR->plan.vht.maxSlots;
+	m_ldPr = roundUp(m_mr, 32);
+	m_stridePr = m_ldPr * k;
+	m_PpartR.allocate(m_stridePr * m_splitsPr);
+	m_stat.allocate((size_t)k * k + 128);
+	m_Wblk.allocate((size_t)mrPad * k);
+	m_Wgath.allocate((size_t)mrPad * k * G);
+	m_splitsGHfull = kern::effectiveSplits(N, pickSplits(ceilDiv(k, 64) * ceilDiv(k, 64), N));
+	m_splitsGWrows = kern::effectiveSplits(m_mr, pickSplits(ceilDiv(k, 64) * ceilDiv(k, 64), m_mr));
+	m_kkScratch.allocate((size_t)k * k * std::max(std::max(m_splitsGW, m_splitsGH), std::max(m_splitsGHfull, m_splitsGWrows)));
+}
+
+// everything the W update derives from H: the full matrix, its transposed TF32 split, H H^T and the centring term
+template <typename T>
+void Engine<T>::gatherH() {
+	const unsigned k = m_cfg.k, N = m_globalN;
+	m_cfg.comm->allGather(reinterpret_cast<const float*>(m_H[m_hCur].get()), m_Hfull.get(), m_ldH * m_cfg.n, m_stream);
+	tc::splitTransposeH(k, N, m_Hfull.get(), m_ldH, m_HtHiFull.get(), m_HtLoFull.get(), m_ldHtFull, m_stream);
+	const T* H = reinterpret_cast<const T*>(m_Hfull.get());
+	kern::gemmNT<T>(k, N, k, H, m_ldH, H, m_ldH, m_kkScratch.get(), k, m_splitsGHfull, (size_t)k * k, m_stream);
+	kern::sumSplits<T>(k, k, m_kkScratch.get(), k, m_splitsGHfull, (size_t)k * k, m_B.get(), k, m_stream);
+	tc::refreshCorrectionH(m_tcR->plan, m_Hfull.get(), m_ldH, m_stream);
+	m_launches += 5;
+}
+
+template <typename T>
+void Engine<T>::iterateMURowOwners(bool err) {
+	const unsigned n = m_cfg.n, k = m_cfg.k;
+	Communicator* comm = m_cfg.comm;
+	// ---- H <- H o (W^T V) / ((W^T W) H + eps) on the columns of this rank (MU.h:164-198); m_G is up to date
+	productWtV(m_W[m_wCur].get());
+	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_eps,
+	                 err ? m_partN.get() : nullptr, nullptr, nullptr, m_ldHt, m_stream, m_slotsN, m_corrN);
+	m_launches += 1;
+	m_hCur = 1 - m_hCur;
+	gatherH();
+	if (err) {
+		kern::traceKK<T>(k, m_B.get(), m_G.get(), m_partK.get(), m_stream);                 // tr(HH^T W^T W) MU.h:203-216
+		m_launches += 1;
+	}
+
+	// ---- W <- W o (V H^T) / (W (H H^T) + eps) on the rows of this rank (MU.h:200-248)
+	float* stat = m_stat.get();
+	tc::gemmVHt(m_tcR->plan, m_PpartR.get(), m_ldPr, m_stridePr, m_stream);
+	T* Wnext = m_W[1 - m_wCur].get();
+	kern::updateW<T>(m_mr, k, m_B.get(), m_W[m_wCur].get() + m_r0, Wnext + m_r0, m_ldW, reinterpret_cast<const T*>(m_PpartR.get()), m_ldPr, m_splitsPr,
+	                 m_stridePr, m_eps, m_colSqPartials.get(), m_stream, m_tcR->plan.vht.slotCount, reinterpret_cast<const T*>(m_tcR->plan.corrP));
+	// statistics of the un-normalised block: Gram matrix (its diagonal = the column sums of squares) and column sums
+	kern::gemmTN<T>(m_mr, k, k, Wnext + m_r0, m_ldW, Wnext + m_r0, m_ldW, m_kkScratch.get(), k, m_splitsGWrows, (size_t)k * k, m_stream);
+	kern::sumSplits<T>(k, k, m_kkScratch.get(), k, m_splitsGWrows, (size_t)k * k, reinterpret_cast<T*>(stat), k, m_stream);
+	tc::columnSums(m_tc->plan, reinterpret_cast<const float*>(Wnext) + m_r0, m_mr, m_ldW, stat + (size_t)k * k, m_stream);
+	comm->allReduceSum(stat, (size_t)k * k + k, m_stream);
+	kern::finishStats(k, stat, m_tc->plan.center, reinterpret_cast<float*>(m_G.get()), m_tc->plan.corrN, m_stream);
+	kern::scalePackRows(m_mr, m_mrPad, k, reinterpret_cast<const float*>(Wnext) + m_r0, m_ldW, stat, m_Wblk.get(), m_stream);
+	comm->allGather(m_Wblk.get(), m_Wgath.get(), (size_t)m_mrPad * k, m_stream);
+	kern::unpackSplit(m_cfg.m, k, m_mrPad, m_Wgath.get(), reinterpret_cast<float*>(Wnext), m_ldW, m_Whi.get(), m_Wlo.get(), m_stream);
+	m_launches += 10;
+	m_wCur = 1 - m_wCur;
+	if (err) resolveError(n);
 }
 
 // ---- initial factors --------------------------------------------------------------------------------
@@ -273,6 +413,10 @@ void Engine<T>::finishInitialisation() {
 	tc::splitTransposeH(m_cfg.k, m_cfg.n, H, m_ldH, m_HtHi.get(), m_HtLo.get(), m_ldHt, m_stream);
 	operandChangedW(m_W[m_wCur].get());
 	operandChangedH(m_H[m_hCur].get());
+	if (m_rowOwners) {   // what the iteration keeps up to date itself: W^T W and everything derived from the full H
+		gramW(m_W[m_wCur].get(), m_G.get());
+		gatherH();
+	}
 }
 
 // the tensor-core products read hi/lo copies of W resp. H; their rank-one centring terms follow the same values
@@ -563,7 +707,7 @@ void Engine<T>::resolveError(unsigned secondLen) {
 template <typename T>
 void Engine<T>::iterate(bool computeError) {
 	switch (m_cfg.algorithm) {
-	case NmfAlgorithm::Multiplicative: iterateMU(computeError); break;
+	case NmfAlgorithm::Multiplicative: m_rowOwners ? iterateMURowOwners(computeError) : iterateMU(computeError); break;
 	case NmfAlgorithm::nsNMF: iterateNsNMF(computeError); break;
 	case NmfAlgorithm::GDCLS:
 	case NmfAlgorithm::ALS:

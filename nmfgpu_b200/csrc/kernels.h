@@ -109,6 +109,15 @@ void qrSolveClamp(unsigned k, const T* factor, T* R, size_t ldr, unsigned nrhs, 
 // TF32 hi/lo split of a dense block: hi = rn_tf32(x), lo = x - hi
 void splitTf32(unsigned rows, unsigned cols, const float* X, size_t ldx, float* hi, float* lo, size_t ldo, cudaStream_t stream);
 
+// ---- row-owner multi-GPU dataflow (engine.cu, dist.h) ---------------------------------------------------
+// stat = [W_un^T W_un (k x k), column sums of W_un (k)] summed over all ranks:  G <- Gram of the unit-column matrix,
+// corrN <- center * column sums of the unit-column matrix (the centring term of W^T V, tc_gemm.h)
+void finishStats(unsigned k, const float* stat, float center, float* G, float* corrN, cudaStream_t stream);
+// block (k columns of rowsPadded values) <- this rank's rows of W scaled to unit columns; zero beyond `rows`
+void scalePackRows(unsigned rows, unsigned rowsPadded, unsigned k, const float* W, size_t ldw, const float* stat, float* block, cudaStream_t stream);
+// W and its TF32 hi/lo split (m x k) <- the all-gathered blocks
+void unpackSplit(unsigned m, unsigned k, unsigned rowsPadded, const float* gathered, float* W, size_t ldw, float* hi, float* lo, cudaStream_t stream);
+
 // |x| and max(0,x) variants for the k-means based initialisations (KMeansStrategy.cpp:31-40)
 template <typename T>
 void absInPlace(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream_t stream);

@@ -776,6 +776,13 @@ void refreshCorrectionW(Plan& plan, const float* W, size_t ldW, cudaStream_t str
 	CUDA_CHECK(cudaGetLastError());
 }
 
+void columnSums(Plan& plan, const float* W, unsigned rows, size_t ldW, float* out, cudaStream_t stream) {
+	const unsigned chunk = ceilDiv(rows, SUM_SLICES);
+	column_sums_stage1<<<dim3(plan.k, SUM_SLICES), 256, 0, stream>>>(rows, plan.k, W, ldW, chunk, plan.sumScratch);
+	sums_stage2<<<1, 128, 0, stream>>>(plan.k, SUM_SLICES, plan.sumScratch, 1.f, out);
+	CUDA_CHECK(cudaGetLastError());
+}
+
 void refreshCorrectionH(Plan& plan, const float* H, size_t ldH, cudaStream_t stream) {
 	const unsigned chunk = ceilDiv(plan.n, ROW_SUM_SLICES);
 	row_sums_stage1<<<ROW_SUM_SLICES, 256, 0, stream>>>(plan.k, plan.n, H, ldH, chunk, plan.sumScratch);
