@@ -277,7 +277,9 @@ def run_ours(args, rank, world, local):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "dense fp32 100000x10000, k=64, MU Frobenius, CopyExisting init (BASELINE configs[1])",
                        "arithmetic": "3xTF32 tcgen05 (fp32-equivalent)" if roof and roof["uses_tensor_cores"] else "fp32 SIMT",
-                       "parallelism": "column shards x%d, NCCL all-reduce of V H^T and H H^T" % world if world > 1 else "single GPU",
+                       "parallelism": ("single GPU" if world == 1 else
+                                       "column shards x%d + row blocks of V, NCCL all-gather of H and W, all-reduce of k*k+k statistics" % world
+                                       if info1.row_owners else "column shards x%d, NCCL all-reduce of V H^T and H H^T" % world),
                        "l2": "input (4 GB) larger than the 126 MB L2; no flush needed"},
             "effective_tflops": flops_per_iteration(M, N, K) * value / 1e12,
             "hbm_roofline_iterations_per_s": 1.0 / ((8.0 * M * N + 16.0 * K * (M + N)) / (peaks()[0] * 1e9)) * world,

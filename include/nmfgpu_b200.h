@@ -30,6 +30,7 @@ typedef struct nmfgpu_b200_session_info {
 	unsigned long long kernel_launches;   /* kernels launched by this session so far */
 	unsigned long long collective_calls;  /* NCCL all-reduces issued so far */
 	size_t ld_v, ld_w, ld_h;
+	int row_owners;                   /* 1 when column shards run the row-owner dataflow (all-gather of H and W), 0 for all-reduce */
 } nmfgpu_b200_session_info;
 
 /* 0 = auto (tensor cores when the shape allows), 1 = exact SIMT fp32, 2 = force 3xTF32, 3 = 1xTF32 (diagnostic).
@@ -39,7 +40,10 @@ int nmfgpu_b200_set_precision(int mode);
 
 /* ---- multi-GPU: rank 0 creates the id, every rank passes it to dist_init after nmfgpu_initialize() and
  * nmfgpu_choose_gpu().  From then on inputMatrix / outputMatrixH of nmfgpu_compute_* describe this rank's
- * column shard (columnOffset .. columnOffset + inputMatrix.columns of globalColumns); W is replicated. */
+ * column shard (columnOffset .. columnOffset + inputMatrix.columns of globalColumns); W is replicated.
+ * MU on the tensor-core path with equal shards runs the row-owner dataflow (every rank also keeps a row block of V,
+ * built once from the shards; per iteration H and W are all-gathered), everything else all-reduces V H^T and H H^T;
+ * NMFGPU_DIST_MODE=allreduce forces the latter. */
 int nmfgpu_b200_dist_unique_id(void* out128);
 int nmfgpu_b200_dist_init(int rank, int world_size, const void* unique_id128);
 int nmfgpu_b200_dist_set_shard(unsigned global_columns, unsigned column_offset);

@@ -132,7 +132,7 @@ class NamedValue(ctypes.Structure):
 class SessionInfo(ctypes.Structure):
     _fields_ = [("uses_tensor_cores", c_int), ("splits_wtv", c_uint), ("splits_vht", c_uint),
                 ("kernel_launches", ctypes.c_ulonglong), ("collective_calls", ctypes.c_ulonglong),
-                ("ld_v", c_size_t), ("ld_w", c_size_t), ("ld_h", c_size_t)]
+                ("ld_v", c_size_t), ("ld_w", c_size_t), ("ld_h", c_size_t), ("row_owners", c_int)]
 
 
 C_SYMBOLS = ["nmfgpu_initialize", "nmfgpu_finalize", "nmfgpu_version", "nmfgpu_set_verbosity", "nmfgpu_create_summary",

@@ -77,6 +77,7 @@ public:
 	cudaStream_t stream() const { return m_stream; }
 	const EngineConfig& config() const { return m_cfg; }
 	bool usesTensorCores() const { return m_useTC; }
+	bool rowOwners() const { return m_rowOwners; }
 	unsigned long long kernelLaunches() const { return m_launches; }
 	unsigned splitsWtV() const { return m_splitsN; }
 	unsigned splitsVHt() const { return m_splitsP; }

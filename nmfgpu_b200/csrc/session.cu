@@ -222,6 +222,7 @@ NMFGPU_EXPORT int nmfgpu_b200_session_get_info(nmfgpu_b200_session* s, nmfgpu_b2
 	info->ld_v = s->engine->ldV();
 	info->ld_w = s->engine->ldW();
 	info->ld_h = s->engine->ldH();
+	info->row_owners = s->engine->rowOwners() ? 1 : 0;
 	return 0;
 }
 
