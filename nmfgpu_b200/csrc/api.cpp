@@ -72,6 +72,8 @@ ResultType computeImpl(NmfDescription<T>& desc, ISummary* summary) {
 	cfg.constantW = desc.useConstantBasisVectors;
 	cfg.precision = ctx->precision;
 	cfg.comm = (ctx->comm && ctx->comm->worldSize() > 1) ? ctx->comm.get() : nullptr;
+	cfg.needsDenseV = desc.initMethod == NmfInitializationMethod::MeanColumns || desc.initMethod == NmfInitializationMethod::KMeansAndRandomValues ||
+	                  desc.initMethod == NmfInitializationMethod::KMeansAndAbsoluteWTV || desc.initMethod == NmfInitializationMethod::KMeansAndNonNegativeWTV;
 
 	// required named parameters per algorithm (Interface.cpp:237-336)
 	const Parameter* p = desc.parameters;

@@ -74,7 +74,15 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	m_ldW = roundUp(m, 32);
 	m_ldH = roundUp(k, 32);
 
-	if (vOnDevice) {
+	decideSparse(V, vOnDevice);
+	if (m_sparse) {
+		sparse::ingest(V, m_S, m_stream);
+		m_ldV = 0;
+		m_Wt.allocate(m_ldH * m);
+		m_Pt.allocate(m_ldH * m);
+		m_Wt.zero(m_stream);
+		m_Pt.zero(m_stream);
+	} else if (vOnDevice) {
 		if (V.format != StorageFormat::Dense) throw EngineError(ResultType::ErrorInvalidArgument, "device-resident V must be dense");
 		m_ldV = V.dense.leadingDimension;
 		m_V.adopt(V.dense.values, m_ldV * n);
@@ -105,7 +113,7 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 
 	// tensor-core eligibility: fp32, rank that fits one UMMA N, TMA-compatible strides
 	m_useTC = false;
-	if (std::is_same<T, float>::value && m_cfg.precision != Precision::Exact) {
+	if (std::is_same<T, float>::value && m_cfg.precision != Precision::Exact && !m_sparse) {
 		const bool ok = tc::shapeSupported(m, n, k, m_ldV, m_ldW) && (reinterpret_cast<uintptr_t>(m_V.get()) % 16 == 0);
 		if (!ok && (m_cfg.precision == Precision::Tf32x3 || m_cfg.precision == Precision::Tf32x1))
 			throw EngineError(ResultType::ErrorInvalidArgument, "tensor-core precision requested for an unsupported shape");
@@ -135,6 +143,8 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 		m_splitsP = m_tc->plan.vht.maxSlots;
 		m_slotsN = m_tc->plan.wtv.slotCount;
 		m_slotsP = m_tc->plan.vht.slotCount;
+	} else if (m_sparse) {
+		m_splitsN = m_splitsP = 1;   // a gather product is complete when it is written
 	} else {
 		m_splitsN = kern::effectiveSplits(m, pickSplits(ceilDiv(k, 64) * ceilDiv(n, 64), m));
 		m_splitsP = kern::effectiveSplits(n, pickSplits(ceilDiv(m, 64) * ceilDiv(k, 64), n));
@@ -160,13 +170,29 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	}
 
 	// tr(V^T V) per column, sorted ascending on the host (MU.h:117-125)
-	kern::columnDots<T>(m, n, m_V.get(), m_ldV, m_V.get(), m_ldV, m_partN.get(), m_stream);
+	if (m_sparse) sparse::majorSquares<T>(n, m_S.colPtr.get(), m_S.cscVal.get(), m_partN.get(), m_stream);
+	else kern::columnDots<T>(m, n, m_V.get(), m_ldV, m_V.get(), m_ldV, m_partN.get(), m_stream);
 	m_vtvSorted.resize(n);
 	CUDA_CHECK(cudaMemcpyAsync(m_hostSecond.get(), m_partN.get(), n * sizeof(T), cudaMemcpyDeviceToHost, m_stream));
 	synchronize();
 	std::copy(m_hostSecond.get(), m_hostSecond.get() + n, m_vtvSorted.begin());
 	std::sort(m_vtvSorted.begin(), m_vtvSorted.end());
 	setupRowOwners();
+}
+
+// Sparse inputs run compressed when densifying is wasteful or impossible (spmm.h); the reference always densifies.
+template <typename T>
+void Engine<T>::decideSparse(const MatrixDescription<T>& V, bool vOnDevice) {
+	m_sparse = false;
+	if (vOnDevice || V.format == StorageFormat::Dense || m_cfg.needsDenseV || m_cfg.k > 128) return;
+	if (const char* e = getenv("NMFGPU_SPARSE")) {
+		m_sparse = atoi(e) != 0;
+		return;
+	}
+	const double cells = (double)m_cfg.m * (double)m_cfg.n;
+	size_t freeBytes = 0, totalBytes = 0;
+	CUDA_CHECK(cudaMemGetInfo(&freeBytes, &totalBytes));
+	m_sparse = (double)V.csr.nnz <= 0.02 * cells || cells * sizeof(T) > 0.5 * (double)freeBytes;
 }
 
 // ---- row-owner dataflow for column shards (dist.h) ----------------------------------------------------------
@@ -378,11 +404,13 @@ void Engine<T>::randomH(unsigned seed) {
 
 template <typename T>
 void Engine<T>::meanColumnsW(unsigned seed) {
+	if (m_sparse) throw EngineError(ResultType::ErrorInvalidArgument, "MeanColumns initialisation needs the dense matrix (NMFGPU_SPARSE=0)");
 	init::meanColumns<T>(m_cfg.m, m_cfg.n, m_cfg.k, m_V.get(), m_ldV, m_W[m_wCur].get(), m_ldW, seed, m_stream);
 }
 
 template <typename T>
 void Engine<T>::kmeansW(unsigned seed) {
+	if (m_sparse) throw EngineError(ResultType::ErrorInvalidArgument, "k-means initialisation needs the dense matrix (NMFGPU_SPARSE=0)");
 	// k-means on the data columns; the centroids become W (KMeansStrategy.cpp:54-58: 100 rounds, 0.5 %)
 	DeviceBuffer<unsigned> membership;
 	membership.allocate(m_cfg.n);
@@ -394,6 +422,13 @@ void Engine<T>::kmeansW(unsigned seed) {
 template <typename T>
 void Engine<T>::hFromWtV(bool absolute) {
 	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
+	if (m_sparse) {
+		productWtV(m_W[m_wCur].get());
+		kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, 1, m_strideN, m_H[m_hCur].get(), m_ldH, m_stream);
+		if (absolute) kern::absInPlace<T>(k, n, m_H[m_hCur].get(), m_ldH, m_stream);
+		else kern::clampNonNegative<T>(k, n, m_H[m_hCur].get(), m_ldH, m_stream);
+		return;
+	}
 	const unsigned splits = kern::effectiveSplits(m, std::min(m_splitsN, 16u));
 	// m_Npart has room for m_splitsN slices; reuse them
 	const unsigned use = std::min(splits, m_splitsN);
@@ -455,7 +490,11 @@ void Engine<T>::gramH(const T* H, size_t ldh, T* B) {
 
 template <typename T>
 void Engine<T>::productWtV(const T* W) {
-	if (m_useTC) {
+	if (m_sparse) {   // N[:, j] = sum over the entries of column j of v * W[i, :]: gathers rows of the row-major copy of W
+		sparse::transpose<T>(m_cfg.m, m_cfg.k, W, m_ldW, m_Wt.get(), m_ldH, m_stream);
+		sparse::spmmGather<T>(m_cfg.n, m_cfg.k, m_S.colPtr.get(), m_S.rowIdx.get(), m_S.cscVal.get(), m_Wt.get(), m_ldH, m_Npart.get(), m_ldH, m_stream);
+		m_launches += 1;
+	} else if (m_useTC) {
 		static const bool poison = getenv("NMFGPU_TC_POISON") != nullptr;   // debugging: an unwritten slot shows up as NaN
 		if (poison) CUDA_CHECK(cudaMemsetAsync(m_Npart.get(), 0xFF, m_Npart.bytes(), m_stream));
 		tc::gemmWtV(m_tc->plan, reinterpret_cast<float*>(m_Npart.get()), m_ldH, m_strideN, m_stream);
@@ -467,7 +506,11 @@ void Engine<T>::productWtV(const T* W) {
 
 template <typename T>
 void Engine<T>::productVHt(const T* H, size_t ldh) {
-	if (m_useTC) {
+	if (m_sparse) {   // P[i, :] = sum over the entries of row i of v * H[:, j]: gathers columns of H, then back to column-major
+		sparse::spmmGather<T>(m_cfg.m, m_cfg.k, m_S.rowPtr.get(), m_S.colIdx.get(), m_S.csrVal.get(), H, ldh, m_Pt.get(), m_ldH, m_stream);
+		sparse::transpose<T>(m_cfg.k, m_cfg.m, m_Pt.get(), m_ldH, m_Ppart.get(), m_ldW, m_stream);
+		m_launches += 1;
+	} else if (m_useTC) {
 		static const bool poison = getenv("NMFGPU_TC_POISON") != nullptr;
 		if (poison) CUDA_CHECK(cudaMemsetAsync(m_Ppart.get(), 0xFF, m_Ppart.bytes(), m_stream));
 		tc::gemmVHt(m_tc->plan, reinterpret_cast<float*>(m_Ppart.get()), m_ldW, m_strideP, m_stream);

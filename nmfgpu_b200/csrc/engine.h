@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.h"
+#include "spmm.h"
 
 namespace nmfgpu {
 namespace b200 {
@@ -41,6 +42,7 @@ struct EngineConfig {
 	AlgorithmParams params;
 	Precision precision = Precision::Auto;
 	Communicator* comm = nullptr;
+	bool needsDenseV = false;               // the initialisation reads V as a dense matrix (k-means, mean columns): no sparse execution
 };
 
 template <typename T>
@@ -78,6 +80,7 @@ public:
 	const EngineConfig& config() const { return m_cfg; }
 	bool usesTensorCores() const { return m_useTC; }
 	bool rowOwners() const { return m_rowOwners; }
+	bool sparseExecution() const { return m_sparse; }
 	unsigned long long kernelLaunches() const { return m_launches; }
 	unsigned splitsWtV() const { return m_splitsN; }
 	unsigned splitsVHt() const { return m_splitsP; }
@@ -139,6 +142,13 @@ private:
 	size_t m_ldHt = 0;
 	struct TcPlan;
 	std::unique_ptr<TcPlan> m_tc;
+
+	// sparse execution (spmm.h): V stays compressed (CSR + CSC), the two V-sized products are gathers.  Chosen for sparse
+	// inputs below 2 % density or too large to densify; NMFGPU_SPARSE=1 / 0 forces / forbids it.
+	bool m_sparse = false;
+	sparse::DeviceSparse<T> m_S;
+	DeviceBuffer<T> m_Wt, m_Pt;   // row-major W (the gather operand of W^T V) and row-major V H^T, leading dimension m_ldH
+	void decideSparse(const MatrixDescription<T>& V, bool vOnDevice);
 
 	// row-owner dataflow (dist.h): this rank also holds V[I, :] for its row block I = [m_r0, m_r0 + m_mr) and updates
 	// only those rows of W; m_tcR plans V[I, :] H^T over all columns

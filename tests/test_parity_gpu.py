@@ -274,6 +274,82 @@ def test_sparse_input_formats(L, fmt, base):
     np.testing.assert_array_equal(r["H"], d["H"])
 
 
+def _sparse_desc(D, fmt, base):
+    import scipy.sparse as sp
+    m, n = D.shape
+    if fmt == "csr":
+        S = sp.csr_matrix(D)
+        a, b = S.indptr.astype(np.int32) + base, S.indices.astype(np.int32) + base
+        return api.sparse_description(api.StorageFormat.CSR, m, n, S.data.astype(D.dtype), a, b, base), (a, b, S)
+    if fmt == "csc":
+        S = sp.csc_matrix(D)
+        a, b = S.indptr.astype(np.int32) + base, S.indices.astype(np.int32) + base
+        return api.sparse_description(api.StorageFormat.CSC, m, n, S.data.astype(D.dtype), a, b, base), (a, b, S)
+    S = sp.coo_matrix(D)
+    perm = np.random.default_rng(3).permutation(S.nnz)      # COO entries in arbitrary order
+    a, b = S.row[perm].astype(np.int32) + base, S.col[perm].astype(np.int32) + base
+    vals = np.ascontiguousarray(S.data[perm].astype(D.dtype))
+    return api.sparse_description(api.StorageFormat.COO, m, n, vals, a, b, base), (a, b, vals)
+
+
+SPARSE_PARAMS = {"mu": {}, "gdcls": {"lambda": 0.01}, "nsnmf": {"theta": 0.5}, "als": {},
+                 "ahcls": {"lambdaW": 0.01, "lambdaH": 0.01, "alphaW": 0.01, "alphaH": 0.01}}
+
+
+@pytest.mark.parametrize("fmt,base,algo,k", [("csr", 0, "mu", 10), ("csc", 1, "mu", 37), ("coo", 1, "mu", 100), ("csr", 1, "gdcls", 16),
+                                            ("csc", 0, "nsnmf", 64), ("coo", 0, "ahcls", 24), ("csr", 0, "als", 128)])
+def test_sparse_execution_matches_dense_and_oracle(L, monkeypatch, fmt, base, algo, k):
+    """the compressed execution (csrc/spmm.cu: CSR/CSC gathers instead of densifying) against the dense execution of the
+    same input and against the fp64 oracle; tolerance: fp32 sums in a different order (1e-4 on factors as for the dense
+    SIMT path, 2e-5 on the residual)"""
+    rng = np.random.default_rng(5)
+    m, n = 700, 450
+    D = ((rng.random((m, n)) < 0.03) * (0.1 + rng.random((m, n)))).astype(np.float32)
+    D[:, 7] = 0          # an empty column and an empty row
+    D[13, :] = 0
+    _, W0, H0 = planted_inputs(m, n, k, seed=2)
+    desc, keep = _sparse_desc(D, fmt, base)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NMFGPU_SPARSE", mode)
+        out[mode] = L.compute(None, k, algorithm=algo, W0=W0, H0=H0, iterations=20, params=SPARSE_PARAMS[algo],
+                              sparse=(desc, np.dtype(np.float32)))
+        assert out[mode]["rc"] == ResultType.Success
+    o = orc.run_nmf(algo, D, W0, H0, 20, params=SPARSE_PARAMS[algo])
+    tol = 5e-3 if algo in ("als", "ahcls") else 2e-4     # the least-squares family amplifies rounding (see test_reference_*)
+    for r in out.values():
+        assert abs(r["frobenius"] - o["frob"][-1]) / o["frob"][-1] <= (2e-3 if algo in ("als", "ahcls") else 2e-5)
+        assert rel(r["W"], o["W"]) <= tol and rel(r["H"], o["H"]) <= tol
+    assert rel(out["1"]["W"], out["0"]["W"]) <= tol and rel(out["1"]["H"], out["0"]["H"]) <= tol
+
+
+def test_sparse_execution_double_and_auto_policy(L, monkeypatch):
+    """fp64 entry point on the compressed path; without NMFGPU_SPARSE a 1 % dense input runs compressed, a 10 % one densified
+    (both must agree with the oracle either way)"""
+    monkeypatch.delenv("NMFGPU_SPARSE", raising=False)
+    rng = np.random.default_rng(6)
+    m, n, k = 500, 640, 12
+    for density in (0.01, 0.10):
+        D = ((rng.random((m, n)) < density) * (0.1 + rng.random((m, n))))
+        _, W0, H0 = planted_inputs(m, n, k, seed=3, dtype=np.float64)
+        desc, keep = _sparse_desc(D, "csr", 0)
+        r = L.compute(None, k, W0=W0, H0=H0, iterations=20, sparse=(desc, np.dtype(np.float64)))
+        o = orc.run_nmf("mu", D, W0, H0, 20)
+        assert r["rc"] == ResultType.Success
+        assert abs(r["frobenius"] - o["frob"][-1]) / o["frob"][-1] <= 1e-10
+        assert rel(r["W"], o["W"]) <= 1e-9 and rel(r["H"], o["H"]) <= 1e-9
+
+
+def test_sparse_execution_rejects_dense_initialisations(L, monkeypatch):
+    monkeypatch.setenv("NMFGPU_SPARSE", "1")
+    rng = np.random.default_rng(8)
+    D = ((rng.random((300, 200)) < 0.02) * rng.random((300, 200))).astype(np.float32)
+    desc, keep = _sparse_desc(D, "csr", 0)
+    # k-means needs the dense matrix: the engine densifies instead of running compressed, and succeeds
+    r = L.compute(None, 4, init=api.NmfInitializationMethod.KMeansAndRandomValues, iterations=10, seed=3, sparse=(desc, np.dtype(np.float32)))
+    assert r["rc"] == ResultType.Success
+
+
 def test_kmeans_bit_exact_vs_oracle(L):
     rng = np.random.default_rng(7)
     m, n, k = 1000, 600, 8     # ceil(1000/32)=32 even: full row coverage
