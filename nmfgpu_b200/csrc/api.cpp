@@ -109,9 +109,16 @@ ResultType computeImpl(NmfDescription<T>& desc, ISummary* summary) {
 			errorf("[ERROR] No usable CUDA device (#%d): the NMF engine has no CPU fallback.\n", ctx->deviceId);
 			return ResultType::ErrorDeviceSelection;
 		}
-		Engine<T> engine(cfg);
-		engine.setup(desc.inputMatrix, false);
-		const bool finished = runFactorisation<T>(desc, engine, static_cast<Summary*>(summary));
+		PhaseTimer timer;
+		bool finished = false;
+		{
+			Engine<T> engine(cfg);
+			engine.setup(desc.inputMatrix, false);
+			timer.mark("setup (alloc, H2D, plans)");
+			finished = runFactorisation<T>(desc, engine, static_cast<Summary*>(summary));
+			timer.mark("runs (init, loop, store)");
+		}
+		timer.mark("teardown");
 		return finished ? ResultType::Success : ResultType::ErrorUserInterrupt;
 	} catch (const EngineError& e) {
 		errorf("[ERROR] %s\n", e.what());
@@ -207,6 +214,7 @@ NMFGPU_EXPORT ResultType finalize() {
 	if (t_context == nullptr) return ResultType::ErrorNotInitialized;
 	delete t_context;
 	t_context = nullptr;
+	releasePooledMemory();   // device and pinned blocks kept between calls (common.h) go back to the driver
 	return ResultType::Success;
 }
 

@@ -3,6 +3,8 @@
 // and source/common/Memory.h with the documented ResultType behaviour (the
 // reference only logs CUDA failures and carries on; here they surface as return codes).
 #pragma once
+#include <chrono>
+#include <cstdlib>
 
 #include <cuda_runtime.h>
 
@@ -39,6 +41,17 @@ inline void cudaCheck(cudaError_t e, const char* expr, const char* file, int lin
 #define CUDA_CHECK(expr) ::nmfgpu::b200::cudaCheck((expr), #expr, __FILE__, __LINE__)
 
 // ---- buffers --------------------------------------------------------------------
+// Device and pinned blocks are recycled between calls on the same device (host.cpp): cudaMalloc / cudaFree of the
+// 4 GB input and the ~40 scratch buffers of a compute() call cost ~100 ms, a quarter of a 100-iteration run.  A block
+// goes back to the pool when its buffer dies and is handed out again for a request of exactly the same size; everything
+// is returned to the driver by nmfgpu_finalize(), or earlier when an allocation fails.  NMFGPU_POOL=0 switches the pool
+// off (every buffer is then freed before compute() returns, as in the reference, SingleGpuDispatcher.cpp:237-238).
+void* pooledDeviceAlloc(size_t bytes);
+void pooledDeviceFree(void* p, size_t bytes);
+void* pooledPinnedAlloc(size_t bytes);
+void pooledPinnedFree(void* p, size_t bytes);
+void releasePooledMemory();
+
 template <typename T>
 class DeviceBuffer {
 	T* m_ptr = nullptr;
@@ -53,7 +66,7 @@ public:
 	void allocate(size_t count) {
 		release();
 		if (count == 0) return;
-		CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&m_ptr), count * sizeof(T)));
+		m_ptr = static_cast<T*>(pooledDeviceAlloc(count * sizeof(T)));
 		m_count = count;
 		m_owned = true;
 	}
@@ -65,7 +78,7 @@ public:
 		m_owned = false;
 	}
 	void release() {
-		if (m_ptr && m_owned) cudaFree(m_ptr);
+		if (m_ptr && m_owned) pooledDeviceFree(m_ptr, m_count * sizeof(T));
 		m_ptr = nullptr;
 		m_count = 0;
 	}
@@ -88,14 +101,11 @@ public:
 	void allocate(size_t count) {
 		release();
 		if (count == 0) return;
-		if (cudaMallocHost(reinterpret_cast<void**>(&m_ptr), count * sizeof(T)) != cudaSuccess) {
-			cudaGetLastError();
-			throw EngineError(ResultType::ErrorNotEnoughHostMemory, "cudaMallocHost failed");
-		}
+		m_ptr = static_cast<T*>(pooledPinnedAlloc(count * sizeof(T)));
 		m_count = count;
 	}
 	void release() {
-		if (m_ptr) cudaFreeHost(m_ptr);
+		if (m_ptr) pooledPinnedFree(m_ptr, m_count * sizeof(T));
 		m_ptr = nullptr;
 		m_count = 0;
 	}
@@ -105,6 +115,23 @@ public:
 
 inline size_t roundUp(size_t x, size_t to) { return (x + to - 1) / to * to; }
 inline unsigned ceilDiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+// NMFGPU_TIMING=1: wall-clock milliseconds of the host-visible phases of a compute() call on stderr (each mark
+// synchronises the device first, so the run itself gets slower; a diagnostic, not a profiler)
+class PhaseTimer {
+	bool m_on;
+	std::chrono::steady_clock::time_point m_last;
+
+public:
+	PhaseTimer() : m_on(getenv("NMFGPU_TIMING") != nullptr), m_last(std::chrono::steady_clock::now()) {}
+	void mark(const char* what) {
+		if (!m_on) return;
+		cudaDeviceSynchronize();
+		const auto now = std::chrono::steady_clock::now();
+		errorf("[timing] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - m_last).count());
+		m_last = now;
+	}
+};
 
 }  // namespace b200
 }  // namespace nmfgpu

@@ -69,6 +69,7 @@ template <typename T>
 void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
 	if (k == 0 || m == 0 || n == 0) throw EngineError(ResultType::ErrorInvalidArgument, "empty problem");
+	PhaseTimer timer;
 	// leading dimensions padded to 32 elements, as the reference's DeviceMatrix (Matrix.h:450-452):
 	// keeps cuRAND-initialised factors bit-identical and every column 128-byte aligned for TMA.
 	m_ldW = roundUp(m, 32);
@@ -99,6 +100,7 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 		}
 	}
 
+	timer.mark("  V on the device");
 	for (int b = 0; b < 2; ++b) {
 		m_W[b].allocate(m_ldW * k);
 		m_W[b].zero(m_stream);
@@ -120,6 +122,7 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 		m_useTC = ok;
 	}
 
+	timer.mark("  factor buffers");
 	// split-K plans of the two V-sized products and of the Gram products
 	if (m_useTC) {
 		m_tc.reset(new TcPlan());
@@ -149,6 +152,7 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 		m_splitsN = kern::effectiveSplits(m, pickSplits(ceilDiv(k, 64) * ceilDiv(n, 64), m));
 		m_splitsP = kern::effectiveSplits(n, pickSplits(ceilDiv(m, 64) * ceilDiv(k, 64), n));
 	}
+	timer.mark("  mean of V, TMA plans");
 	m_splitsGW = kern::effectiveSplits(m, pickSplits(ceilDiv(k, 64) * ceilDiv(k, 64), m));
 	m_splitsGH = kern::effectiveSplits(n, pickSplits(ceilDiv(k, 64) * ceilDiv(k, 64), n));
 	m_strideN = m_ldH * n;
@@ -169,6 +173,7 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 		m_smoothH.zero(m_stream);
 	}
 
+	timer.mark("  scratch buffers");
 	// tr(V^T V) per column, sorted ascending on the host (MU.h:117-125)
 	if (m_sparse) sparse::majorSquares<T>(n, m_S.colPtr.get(), m_S.cscVal.get(), m_partN.get(), m_stream);
 	else kern::columnDots<T>(m, n, m_V.get(), m_ldV, m_V.get(), m_ldV, m_partN.get(), m_stream);
@@ -177,6 +182,7 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	synchronize();
 	std::copy(m_hostSecond.get(), m_hostSecond.get() + n, m_vtvSorted.begin());
 	std::sort(m_vtvSorted.begin(), m_vtvSorted.end());
+	timer.mark("  tr(V^T V)");
 	setupRowOwners();
 }
 

@@ -1,6 +1,9 @@
 // host.cpp -- logging, summary and the run loop (see host.h).
 #include "host.h"
 
+#include <map>
+#include <mutex>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -34,6 +37,97 @@ void errorf(const char* fmt, ...) {
 	vfprintf(stderr, fmt, ap);
 	va_end(ap);
 	fflush(stderr);
+}
+
+// ---- block pool (common.h) --------------------------------------------------------------------------------------
+namespace {
+struct BlockPool {
+	std::mutex lock;
+	std::multimap<std::pair<int, size_t>, void*> device, pinned;   // (device ordinal, bytes) -> free blocks
+	bool enabled() {
+		static const bool on = [] {
+			const char* e = getenv("NMFGPU_POOL");
+			return e == nullptr || atoi(e) != 0;
+		}();
+		return on;
+	}
+	static int ordinal() {
+		int dev = 0;
+		cudaGetDevice(&dev);
+		return dev;
+	}
+};
+BlockPool& pool() {
+	static BlockPool p;
+	return p;
+}
+void* takeBlock(std::multimap<std::pair<int, size_t>, void*>& blocks, size_t bytes) {
+	std::lock_guard<std::mutex> guard(pool().lock);
+	auto it = blocks.find({BlockPool::ordinal(), bytes});
+	if (it == blocks.end()) return nullptr;
+	void* p = it->second;
+	blocks.erase(it);
+	return p;
+}
+}  // namespace
+
+void* pooledDeviceAlloc(size_t bytes) {
+	if (pool().enabled())
+		if (void* p = takeBlock(pool().device, bytes)) return p;
+	void* p = nullptr;
+	cudaError_t e = cudaMalloc(&p, bytes);
+	if (e == cudaErrorMemoryAllocation) {   // give the pooled blocks back and try once more
+		cudaGetLastError();
+		releasePooledMemory();
+		e = cudaMalloc(&p, bytes);
+	}
+	CUDA_CHECK(e);
+	return p;
+}
+
+void pooledDeviceFree(void* p, size_t bytes) {
+	if (!pool().enabled()) {
+		cudaFree(p);
+		return;
+	}
+	cudaDeviceSynchronize();   // what cudaFree would have done: nothing in flight may still use the block when it is handed out again
+	std::lock_guard<std::mutex> guard(pool().lock);
+	pool().device.insert({{BlockPool::ordinal(), bytes}, p});
+}
+
+void* pooledPinnedAlloc(size_t bytes) {
+	if (pool().enabled())
+		if (void* p = takeBlock(pool().pinned, bytes)) return p;
+	void* p = nullptr;
+	if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+		cudaGetLastError();
+		throw EngineError(ResultType::ErrorNotEnoughHostMemory, "cudaMallocHost failed");
+	}
+	return p;
+}
+
+void pooledPinnedFree(void* p, size_t bytes) {
+	if (!pool().enabled()) {
+		cudaFreeHost(p);
+		return;
+	}
+	std::lock_guard<std::mutex> guard(pool().lock);
+	pool().pinned.insert({{BlockPool::ordinal(), bytes}, p});
+}
+
+void releasePooledMemory() {
+	std::lock_guard<std::mutex> guard(pool().lock);
+	int current = 0;
+	cudaGetDevice(&current);
+	for (auto& kv : pool().device) {
+		cudaSetDevice(kv.first.first);
+		cudaFree(kv.second);
+	}
+	for (auto& kv : pool().pinned) cudaFreeHost(kv.second);
+	pool().device.clear();
+	pool().pinned.clear();
+	cudaSetDevice(current);
+	cudaGetLastError();
 }
 
 // ---- summary ------------------------------------------------------------------------------------------------
@@ -142,8 +236,10 @@ bool runFactorisation(NmfDescription<T>& desc, Engine<T>& engine, Summary* summa
 			else logf(Verbosity::Summary, " | Iteration |     Frobenius     |       RMSD       |       Delta      | Elapsed Time |   Status   |\n");
 			logf(Verbosity::Summary, "%s", rule);
 		}
+		PhaseTimer timer;
 		initialiseRun(desc, engine, nextSeed);
 		engine.synchronize();
+		timer.mark("  initial factors");
 
 		const auto started = std::chrono::high_resolution_clock::now();
 		long long elapsedMs = 0;
@@ -178,6 +274,7 @@ bool runFactorisation(NmfDescription<T>& desc, Engine<T>& engine, Summary* summa
 			}
 		}
 		iteration = std::min(iteration, numIterations);  // SingleGpuDispatcher.cpp:205
+		timer.mark("  iterations");
 
 		char t[32];
 		formatDuration(t, elapsedMs);
@@ -194,6 +291,7 @@ bool runFactorisation(NmfDescription<T>& desc, Engine<T>& engine, Summary* summa
 					summary->insert(rec);
 				}
 				engine.store(desc.outputMatrixW, desc.outputMatrixH);
+				timer.mark("  store W, H");
 				bestError = engine.frobenius();
 			}
 			status = stored ? "Stored" : "Discarded";

@@ -703,8 +703,9 @@ void planProduct(Product& prod, unsigned rowsA, unsigned kdim) {
 			if (2 * t + h < tiles128) counts[2 * t + h] = (unsigned char)(last - first + 1);
 		prod.maxSlots = std::max(prod.maxSlots, last - first + 1);
 	}
-	if (prod.slotCount) cudaFree(prod.slotCount);
-	CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&prod.slotCount), tiles128));
+	if (prod.slotCount) pooledDeviceFree(prod.slotCount, prod.slotCountBytes);
+	prod.slotCountBytes = roundUp(tiles128, 256);
+	prod.slotCount = static_cast<unsigned char*>(pooledDeviceAlloc(prod.slotCountBytes));
 	CUDA_CHECK(cudaMemcpy(prod.slotCount, counts.data(), tiles128, cudaMemcpyHostToDevice));
 }
 
@@ -756,12 +757,12 @@ void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, s
 
 float meanOf(const float* V, unsigned m, unsigned n, size_t ldV, cudaStream_t stream) {
 	double* partial = nullptr;
-	CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&partial), (size_t)n * sizeof(double)));
+	partial = static_cast<double*>(pooledDeviceAlloc((size_t)n * sizeof(double)));
 	column_sums_stage1<<<dim3(n, 1), 256, 0, stream>>>(m, n, V, ldV, m, partial);
 	std::vector<double> host(n);
 	const cudaError_t e = cudaMemcpyAsync(host.data(), partial, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream);
 	const cudaError_t e2 = cudaStreamSynchronize(stream);
-	cudaFree(partial);
+	pooledDeviceFree(partial, (size_t)n * sizeof(double));
 	CUDA_CHECK(e);
 	CUDA_CHECK(e2);
 	double total = 0.0;
@@ -791,9 +792,9 @@ void refreshCorrectionH(Plan& plan, const float* H, size_t ldH, cudaStream_t str
 }
 
 Plan::~Plan() {
-	if (corrN) cudaFree(corrN);
-	if (corrP) cudaFree(corrP);
-	if (sumScratch) cudaFree(sumScratch);
+	if (corrN) pooledDeviceFree(corrN, 128 * sizeof(float));
+	if (corrP) pooledDeviceFree(corrP, 128 * sizeof(float));
+	if (sumScratch) pooledDeviceFree(sumScratch, (size_t)ROW_SUM_SLICES * 128 * sizeof(double));
 	if (trace != nullptr) {
 		// diagnostic timeline of CTA 0 of the LAST product launched: one line per stage with the clock64 stamps
 		// worker{tile landed, split done, slot free, slot published}, MMA{operands ready, stage issued}
@@ -812,8 +813,8 @@ Plan::~Plan() {
 		}
 		cudaFree(trace);
 	}
-	if (wtv.slotCount) cudaFree(wtv.slotCount);
-	if (vht.slotCount) cudaFree(vht.slotCount);
+	if (wtv.slotCount) pooledDeviceFree(wtv.slotCount, wtv.slotCountBytes);
+	if (vht.slotCount) pooledDeviceFree(vht.slotCount, vht.slotCountBytes);
 }
 
 bool shapeSupported(unsigned m, unsigned n, unsigned k, size_t ldV, size_t ldW) {
@@ -841,9 +842,9 @@ void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, si
 	}
 	plan.center = center;
 	if (plan.corrN == nullptr) {
-		CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&plan.corrN), 128 * sizeof(float)));
-		CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&plan.corrP), 128 * sizeof(float)));
-		CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&plan.sumScratch), (size_t)ROW_SUM_SLICES * 128 * sizeof(double)));
+		plan.corrN = static_cast<float*>(pooledDeviceAlloc(128 * sizeof(float)));
+		plan.corrP = static_cast<float*>(pooledDeviceAlloc(128 * sizeof(float)));
+		plan.sumScratch = static_cast<double*>(pooledDeviceAlloc((size_t)ROW_SUM_SLICES * 128 * sizeof(double)));
 		CUDA_CHECK(cudaMemset(plan.corrN, 0, 128 * sizeof(float)));
 		CUDA_CHECK(cudaMemset(plan.corrP, 0, 128 * sizeof(float)));
 	}

@@ -30,6 +30,7 @@ struct Product {
 	unsigned grid = 0;             // persistent CTAs
 	unsigned maxSlots = 1;         // partial products a consumer may have to add per tile
 	unsigned char* slotCount = nullptr;   // device, [tiles]
+	size_t slotCountBytes = 0;
 	alignas(64) unsigned char mapV[128];  // TMA descriptors (CUtensorMap)
 	alignas(64) unsigned char mapBhi[128];
 	alignas(64) unsigned char mapBlo[128];
