@@ -37,6 +37,13 @@ unsigned pickSplits(unsigned tiles, unsigned reduceLen) {
 	s = std::min(s, std::max(1u, reduceLen / 256));
 	return std::max(1u, s);
 }
+// The k x k Gram products are latency bound (one 64 x 64 tile, a long reduction): four CTAs per SM hide the load
+// latency that one CTA of 8 warps cannot (measured: 28 % FMA utilisation at one CTA per SM), slices down to 64 steps.
+unsigned pickGramSplits(unsigned tiles, unsigned reduceLen) {
+	unsigned s = ceilDiv(4 * 148, std::max(1u, tiles));
+	s = std::min(s, std::max(1u, reduceLen / 64));
+	return std::max(1u, s);
+}
 }  // namespace
 
 template <typename T>
@@ -47,11 +54,51 @@ struct Engine<T>::TcPlan {
 template <typename T>
 Engine<T>::Engine(const EngineConfig& cfg) : m_cfg(cfg), m_eps(std::numeric_limits<T>::epsilon()) {
 	CUDA_CHECK(cudaStreamCreateWithFlags(&m_stream, cudaStreamNonBlocking));
+	m_profile = getenv("NMFGPU_PROFILE_ITERATION") != nullptr;
+}
+
+template <typename T>
+void Engine<T>::stamp(const char* what) {
+	if (!m_profile || m_stamps.size() > 4000) return;
+	cudaEvent_t e;
+	CUDA_CHECK(cudaEventCreate(&e));
+	CUDA_CHECK(cudaEventRecord(e, m_stream));
+	m_stamps.push_back({what, e});
+}
+
+// average in-stream duration of every step over the stamped iterations (the first two iterations are warm-up)
+template <typename T>
+void Engine<T>::reportStamps() {
+	if (m_stamps.empty()) return;
+	cudaStreamSynchronize(m_stream);
+	std::vector<std::pair<const char*, double>> sums;
+	unsigned iterations = 0;
+	for (size_t i = 1; i < m_stamps.size(); ++i) {
+		if (strcmp(m_stamps[i - 1].first, "begin") == 0) ++iterations;
+		if (strcmp(m_stamps[i].first, "begin") == 0 || iterations <= 2) continue;
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, m_stamps[i - 1].second, m_stamps[i].second);
+		bool found = false;
+		for (auto& s : sums)
+			if (s.first == m_stamps[i].first) {
+				s.second += ms;
+				found = true;
+			}
+		if (!found) sums.push_back({m_stamps[i].first, ms});
+	}
+	const double count = iterations > 2 ? iterations - 2 : 1;
+	double total = 0.0;
+	for (auto& s : sums) total += s.second / count;
+	for (auto& s : sums) errorf("[iteration] %-28s %8.1f us\n", s.first, 1000.0 * s.second / count);
+	errorf("[iteration] %-28s %8.1f us over %u iterations\n", "total", 1000.0 * total, (unsigned)count);
+	for (auto& s : m_stamps) cudaEventDestroy(s.second);
+	m_stamps.clear();
 }
 
 template <typename T>
 Engine<T>::~Engine() {
 	if (m_stream) {
+		reportStamps();
 		cudaStreamSynchronize(m_stream);
 		for (auto& row : m_graphExec)
 			for (cudaGraphExec_t& g : row)
@@ -153,14 +200,16 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 		m_splitsP = kern::effectiveSplits(n, pickSplits(ceilDiv(m, 64) * ceilDiv(k, 64), n));
 	}
 	timer.mark("  mean of V, TMA plans");
-	m_splitsGW = kern::effectiveSplits(m, pickSplits(ceilDiv(k, 64) * ceilDiv(k, 64), m));
-	m_splitsGH = kern::effectiveSplits(n, pickSplits(ceilDiv(k, 64) * ceilDiv(k, 64), n));
+	m_splitsGW = kern::effectiveSplits(m, pickGramSplits(ceilDiv(k, 64) * ceilDiv(k, 64), m));
+	m_splitsGH = kern::effectiveSplits(n, pickGramSplits(ceilDiv(k, 64) * ceilDiv(k, 64), n));
 	m_strideN = m_ldH * n;
 	m_strideP = m_ldW * k;
 	m_Npart.allocate(m_strideN * m_splitsN);
 	m_Ppart.allocate(m_strideP * (m_splitsP + 1));  // +1: slot for the summed / all-reduced product
 	m_kkScratch.allocate((size_t)k * k * std::max(m_splitsGW, m_splitsGH));
 	m_colSqPartials.allocate((size_t)ceilDiv(m, 128) * k);
+	m_colSumPartials.allocate((size_t)ceilDiv(m, 128) * k);
+	m_rowSumPartials.allocate((size_t)ceilDiv(n, 64) * k);
 	m_colSq.allocate(k);
 	m_partN.allocate(std::max(n, k));
 	m_partK.allocate(k);
@@ -286,8 +335,8 @@ void Engine<T>::setupRowOwners() {
 	m_stat.allocate((size_t)k * k + 128);
 	m_Wblk.allocate((size_t)mrPad * k);
 	m_Wgath.allocate((size_t)mrPad * k * G);
-	m_splitsGHfull = kern::effectiveSplits(N, pickSplits(ceilDiv(k, 64) * ceilDiv(k, 64), N));
-	m_splitsGWrows = kern::effectiveSplits(m_mr, pickSplits(ceilDiv(k, 64) * ceilDiv(k, 64), m_mr));
+	m_splitsGHfull = kern::effectiveSplits(N, pickGramSplits(ceilDiv(k, 64) * ceilDiv(k, 64), N));
+	m_splitsGWrows = kern::effectiveSplits(m_mr, pickGramSplits(ceilDiv(k, 64) * ceilDiv(k, 64), m_mr));
 	m_kkScratch.allocate((size_t)k * k * std::max(std::max(m_splitsGW, m_splitsGH), std::max(m_splitsGHfull, m_splitsGWrows)));
 }
 
@@ -527,12 +576,15 @@ void Engine<T>::productVHt(const T* H, size_t ldh) {
 }
 
 template <typename T>
-void Engine<T>::normaliseW(unsigned blocks) {
-	kern::finishColumnNorms<T>(m_cfg.k, blocks, m_colSqPartials.get(), m_colSq.get(), m_stream);
+void Engine<T>::normaliseW(unsigned blocks, bool haveColumnSums) {
+	// with the per-block column sums of the update kernel the centring term of W^T V falls out of the norm kernel
+	const bool fused = haveColumnSums && m_useTC;
+	kern::finishColumnNorms<T>(m_cfg.k, blocks, m_colSqPartials.get(), m_colSq.get(), m_stream, fused ? m_colSumPartials.get() : nullptr,
+	                           fused ? m_tc->plan.center : 0.f, fused ? m_tc->plan.corrN : nullptr);
 	kern::scaleColumns<T>(m_cfg.m, m_cfg.k, m_W[m_wCur].get(), m_ldW, m_colSq.get(), m_useTC ? m_Whi.get() : nullptr,
 	                      m_useTC ? m_Wlo.get() : nullptr, m_stream);
 	m_launches += 2;
-	operandChangedW(m_W[m_wCur].get());
+	if (!fused) operandChangedW(m_W[m_wCur].get());
 }
 
 // W <- W o P / (W B + eps) then unit columns; P is read as split partials, or -- with column shards --
@@ -554,10 +606,10 @@ void Engine<T>::multiplicativeW(const T* B) {
 		corr = nullptr;
 	}
 	const unsigned blocks = kern::updateW<T>(m_cfg.m, m_cfg.k, B, m_W[m_wCur].get(), m_W[1 - m_wCur].get(), m_ldW, P, m_ldW, splits, m_strideP,
-	                                         m_eps, m_colSqPartials.get(), m_stream, slots, corr);
+	                                         m_eps, m_colSqPartials.get(), m_stream, slots, corr, m_useTC ? m_colSumPartials.get() : nullptr);
 	m_launches += 1;
 	m_wCur = 1 - m_wCur;
-	normaliseW(blocks);
+	normaliseW(blocks, true);
 }
 
 // ---- MU -------------------------------------------------------------------------------------------------
@@ -567,22 +619,33 @@ void Engine<T>::iterateMU(bool err) {
 	float* htHi = m_useTC ? m_HtHi.get() : nullptr;
 	float* htLo = m_useTC ? m_HtLo.get() : nullptr;
 
+	stamp("begin");
 	gramW(m_W[m_wCur].get(), m_G.get());                                                    // A = W^T W      MU.h:168/176
+	stamp("gram W^T W");
 	productWtV(m_W[m_wCur].get());                                                          // N = W^T V      MU.h:187
+	stamp("product W^T V");
 	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_eps,
-	                 err ? m_partN.get() : nullptr, htHi, htLo, m_ldHt, m_stream, m_slotsN, m_corrN);   // H update  MU.h:181-197
+	                 err ? m_partN.get() : nullptr, htHi, htLo, m_ldHt, m_stream, m_slotsN, m_corrN,
+	                 m_useTC ? m_rowSumPartials.get() : nullptr);                           // H update  MU.h:181-197
 	m_launches += 1;
 	m_hCur = 1 - m_hCur;
-	operandChangedH(m_H[m_hCur].get());
+	if (m_useTC) {   // centring term of V H^T from the row sums the update kernel left per 64-column block
+		kern::finishPartialSums(k, ceilDiv(n, 64), reinterpret_cast<const float*>(m_rowSumPartials.get()), m_tc->plan.center, m_tc->plan.corrP, m_stream);
+		m_launches += 1;
+	}
+	stamp("update H (+ row sums)");
 
 	gramH(m_H[m_hCur].get(), m_ldH, m_B.get());                                             // B = H H^T      MU.h:208/231
+	stamp("gram H H^T");
 	if (err) {
 		kern::traceKK<T>(k, m_B.get(), m_G.get(), m_partK.get(), m_stream);                 // tr(HH^T W^T W) MU.h:203-216
 		m_launches += 1;
 	}
 	if (!m_cfg.constantW) {
 		productVHt(m_H[m_hCur].get(), m_ldH);                                               // N2 = V H^T     MU.h:240
+		stamp("product V H^T");
 		multiplicativeW(m_B.get());                                                         // MU.h:235-247
+		stamp("update W, norms, scale");
 	}
 	if (err) resolveError(n);
 }

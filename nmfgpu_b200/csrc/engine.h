@@ -107,10 +107,18 @@ private:
 	void gramH(const T* H, size_t ldh, T* B);                  // B = H H^T (all-reduced over shards)
 	void productWtV(const T* W);                               // m_Npart / m_splitsN <- W^T V
 	void productVHt(const T* H, size_t ldh);                   // m_Ppart / m_splitsP <- V H^T (all-reduced)
-	void normaliseW(unsigned blocks);
+	void normaliseW(unsigned blocks, bool haveColumnSums = false);
 	void operandChangedW(const T* W);                          // refresh what the tensor-core products derive from W resp. H
 	void operandChangedH(const T* H);
 	void multiplicativeW(const T* B);                          // W <- W o P / (W B + eps), normalise
+
+	// NMFGPU_PROFILE_ITERATION=1: CUDA events between the steps of MU iterations run through iterate() (not the graph
+	// batches), in-stream durations on stderr when the engine is destroyed.  ncu flushes the caches between kernels, which
+	// triples the time of the small kernels; this does not.
+	void stamp(const char* what);
+	void reportStamps();
+	std::vector<std::pair<const char*, cudaEvent_t>> m_stamps;
+	bool m_profile = false;
 
 	EngineConfig m_cfg;
 	T m_eps;
@@ -130,7 +138,7 @@ private:
 	const unsigned char* m_slotsP = nullptr;
 	const T* m_corrN = nullptr;   // rank-one terms of the mean-centred tensor-core products (tc_gemm.h), device, [k]
 	const T* m_corrP = nullptr;
-	DeviceBuffer<T> m_colSqPartials, m_colSq;
+	DeviceBuffer<T> m_colSqPartials, m_colSumPartials, m_rowSumPartials, m_colSq;
 	DeviceBuffer<T> m_partN, m_partK;
 	PinnedBuffer<T> m_hostSecond, m_hostThird;
 	std::vector<T> m_vtvSorted;

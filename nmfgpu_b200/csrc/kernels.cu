@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(256) update_h_reg(unsigned k, unsigned n, cons
                                                    float* __restrict__ Hout, size_t ldh, const float* __restrict__ Npart, size_t ldn,
                                                    unsigned splits, size_t splitStride, float eps, float* __restrict__ tracePartials,
                                                    float* __restrict__ HtHi, float* __restrict__ HtLo, size_t ldht,
-                                                   const unsigned char* __restrict__ tileSlots, const float* __restrict__ corr) {
+                                                   const unsigned char* __restrict__ tileSlots, const float* __restrict__ corr,
+                                                   float* __restrict__ rowSumPartials) {
 	constexpr int COLS = 64, RPT = KP / 16, LDJ = COLS + 4;
 	const unsigned j0 = blockIdx.x * COLS;
 	if (tileSlots != nullptr) splits = tileSlots[j0 >> 7];
@@ -200,8 +201,42 @@ __global__ void __launch_bounds__(256) update_h_reg(unsigned k, unsigned n, cons
 		const unsigned t = idx % KP, j = idx / KP;
 		Hs[t * LDJ + j] = (j0 + j < n && t < k) ? Hin[(size_t)(j0 + j) * ldh + t] : 0.f;
 	}
-	__syncthreads();
 	const unsigned rx = tid % 16, jx = tid / 16;      // rows rx*RPT.., columns jx*4..
+	// the numerators (sum of the partial products + centring term) are fetched before the product: their latency hides behind it
+	// (slot loop outside, entries inside: all loads of a slot are in flight together -- with the loops the other way round
+	// every entry pays its own chain of `splits` memory latencies)
+	float numv[RPT][4];
+#pragma unroll
+	for (int q = 0; q < 4; ++q)
+#pragma unroll
+		for (int i = 0; i < RPT; ++i) numv[i][q] = (corr != nullptr && rx * RPT + i < k) ? corr[rx * RPT + i] : 0.f;
+	for (unsigned sl = 0; sl < splits; ++sl) {
+		const float* slot = Npart + sl * splitStride;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const unsigned j = j0 + jx * 4 + q;
+			if (j < n) {
+				if (RPT % 4 == 0 && rx * RPT + RPT <= k) {
+#pragma unroll
+					for (int i = 0; i < RPT; i += 4) {
+						const float4 x = *reinterpret_cast<const float4*>(slot + (size_t)j * ldn + rx * RPT + i);
+						numv[i][q] += x.x; numv[i + 1][q] += x.y; numv[i + 2][q] += x.z; numv[i + 3][q] += x.w;
+					}
+				} else {
+#pragma unroll
+					for (int i = 0; i < RPT; ++i)
+						if (rx * RPT + i < k) numv[i][q] += slot[(size_t)j * ldn + rx * RPT + i];
+				}
+			}
+		}
+	}
+#pragma unroll
+	for (int q = 0; q < 4; ++q)
+		if (j0 + jx * 4 + q >= n) {
+#pragma unroll
+			for (int i = 0; i < RPT; ++i) numv[i][q] = 0.f;
+		}
+	__syncthreads();
 	float acc[RPT][4];
 #pragma unroll
 	for (int i = 0; i < RPT; ++i)
@@ -210,8 +245,16 @@ __global__ void __launch_bounds__(256) update_h_reg(unsigned k, unsigned n, cons
 #pragma unroll 8
 	for (int t = 0; t < KP; ++t) {
 		float a[RPT];
+		if (RPT % 4 == 0) {
 #pragma unroll
-		for (int i = 0; i < RPT; ++i) a[i] = Gs[t * KP + rx * RPT + i];
+			for (int i = 0; i < RPT; i += 4) {
+				const float4 g = *reinterpret_cast<const float4*>(Gs + t * KP + rx * RPT + i);
+				a[i] = g.x; a[i + 1] = g.y; a[i + 2] = g.z; a[i + 3] = g.w;
+			}
+		} else {
+#pragma unroll
+			for (int i = 0; i < RPT; ++i) a[i] = Gs[t * KP + rx * RPT + i];
+		}
 		const float4 b = *reinterpret_cast<const float4*>(Hs + t * LDJ + jx * 4);
 #pragma unroll
 		for (int i = 0; i < RPT; ++i) {
@@ -221,7 +264,8 @@ __global__ void __launch_bounds__(256) update_h_reg(unsigned k, unsigned n, cons
 			acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
 		}
 	}
-	float hn[RPT][4];
+	// epilogue: the new values replace the old ones in the H tile (every thread overwrites exactly the entries it read),
+	// then H, the transposed TF32 split and the row sums leave shared memory with coalesced stores
 #pragma unroll
 	for (int q = 0; q < 4; ++q) {
 		const unsigned j = j0 + jx * 4 + q;
@@ -229,16 +273,10 @@ __global__ void __launch_bounds__(256) update_h_reg(unsigned k, unsigned n, cons
 #pragma unroll
 		for (int i = 0; i < RPT; ++i) {
 			const unsigned r = rx * RPT + i;
-			float num = 0.f, h = 0.f;
-			if (j < n && r < k) {
-				num = corr != nullptr ? corr[r] : 0.f;
-				for (unsigned sl = 0; sl < splits; ++sl) num += Npart[sl * splitStride + (size_t)j * ldn + r];
-				h = Hs[r * LDJ + jx * 4 + q];
-			}
-			const float v = h * num / (acc[i][q] + eps);
-			hn[i][q] = v;
+			const float num = numv[i][q];
+			const float v = Hs[r * LDJ + jx * 4 + q] * num / (acc[i][q] + eps);   // padding entries: 0 * 0 / eps = 0
+			Hs[r * LDJ + jx * 4 + q] = v;
 			tr = fmaf(v, num, tr);
-			if (j < n && r < k) Hout[(size_t)j * ldh + r] = v;
 		}
 		tr += __shfl_xor_sync(0xffffffffu, tr, 1);
 		tr += __shfl_xor_sync(0xffffffffu, tr, 2);
@@ -246,22 +284,43 @@ __global__ void __launch_bounds__(256) update_h_reg(unsigned k, unsigned n, cons
 		tr += __shfl_xor_sync(0xffffffffu, tr, 8);
 		if (tracePartials != nullptr && rx == 0 && j < n) tracePartials[j] = tr;
 	}
+	__syncthreads();
+	for (unsigned idx = tid; idx < COLS * KP; idx += 256) {
+		const unsigned t = idx % KP, j = idx / KP;
+		if (j0 + j < n && t < k) Hout[(size_t)(j0 + j) * ldh + t] = Hs[t * LDJ + j];
+	}
 	if (HtHi != nullptr) {
-#pragma unroll
-		for (int i = 0; i < RPT; ++i) {
-			const unsigned r = rx * RPT + i;
-			if (r >= k) continue;
-#pragma unroll
-			for (int q = 0; q < 4; ++q) {
-				const unsigned j = j0 + jx * 4 + q;
-				if (j < n) {
-					const float hi = tf32_hi(hn[i][q]);
-					HtHi[(size_t)r * ldht + j] = hi;
-					HtLo[(size_t)r * ldht + j] = hn[i][q] - hi;
-				}
+		for (unsigned idx = tid; idx < COLS * KP; idx += 256) {
+			const unsigned j = idx % COLS, r = idx / COLS;
+			if (r < k && j0 + j < n) {
+				const float v = Hs[r * LDJ + j];
+				const float hi = tf32_hi(v);
+				HtHi[(size_t)r * ldht + j0 + j] = hi;
+				HtLo[(size_t)r * ldht + j0 + j] = v - hi;
 			}
 		}
 	}
+	if (rowSumPartials != nullptr) {   // row sums of the new H over this block's columns (centring term of V H^T, tc_gemm.h)
+		const unsigned lane = tid % 32;
+		for (unsigned r = tid / 32; r < k; r += 8) {
+			float sum = Hs[r * LDJ + lane] + Hs[r * LDJ + 32 + lane];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+			if (lane == 0) rowSumPartials[(size_t)blockIdx.x * k + r] = sum;
+		}
+	}
+}
+
+// out[r] = scale * sum over the blocks of partials[b * count + r]: one warp per entry, lanes stride the blocks, fixed order
+__global__ void __launch_bounds__(256) finish_partial_sums_kernel(unsigned count, unsigned blocks, const float* __restrict__ partials, float scale,
+                                                                 float* __restrict__ out) {
+	const unsigned r = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+	if (r >= count) return;
+	double acc = 0.0;
+	for (unsigned b = lane; b < blocks; b += 32) acc += (double)partials[(size_t)b * count + r];
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if (lane == 0) out[r] = (float)((double)scale * acc);
 }
 
 template <typename T>
@@ -324,7 +383,8 @@ template <int KP>
 __global__ void __launch_bounds__(256) update_w_reg(unsigned m, unsigned k, const float* __restrict__ B, const float* __restrict__ Win,
                                                    float* __restrict__ Wout, size_t ldw, const float* __restrict__ Ppart, size_t ldp,
                                                    unsigned splits, size_t splitStride, float eps, float* __restrict__ colSqPartials,
-                                                   const unsigned char* __restrict__ tileSlots, const float* __restrict__ corr) {
+                                                   const unsigned char* __restrict__ tileSlots, const float* __restrict__ corr,
+                                                   float* __restrict__ colSumPartials) {
 	constexpr int ROWS = 128, CPT = KP / 8;
 	if (tileSlots != nullptr) splits = tileSlots[blockIdx.x];
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -351,8 +411,16 @@ __global__ void __launch_bounds__(256) update_w_reg(unsigned m, unsigned k, cons
 	for (int t = 0; t < KP; ++t) {
 		const float4 a = *reinterpret_cast<const float4*>(Ws + t * ROWS + tx * 4);
 		float b[CPT];
+		if (CPT % 4 == 0) {
 #pragma unroll
-		for (int j = 0; j < CPT; ++j) b[j] = Bs[t * KP + ty * CPT + j];
+			for (int j = 0; j < CPT; j += 4) {
+				const float4 x = *reinterpret_cast<const float4*>(Bs + t * KP + ty * CPT + j);
+				b[j] = x.x; b[j + 1] = x.y; b[j + 2] = x.z; b[j + 3] = x.w;
+			}
+		} else {
+#pragma unroll
+			for (int j = 0; j < CPT; ++j) b[j] = Bs[t * KP + ty * CPT + j];
+		}
 #pragma unroll
 		for (int j = 0; j < CPT; ++j) {
 			acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
@@ -365,7 +433,7 @@ __global__ void __launch_bounds__(256) update_w_reg(unsigned m, unsigned k, cons
 #pragma unroll
 	for (int j = 0; j < CPT; ++j) {
 		const unsigned c = ty * CPT + j;
-		float s2 = 0.f;
+		float s2 = 0.f, s1 = 0.f;
 		if (c < k) {   // warp-uniform
 			const float base = corr != nullptr ? corr[c] : 0.f;
 			float p[4] = {base, base, base, base};
@@ -394,10 +462,17 @@ __global__ void __launch_bounds__(256) update_w_reg(unsigned m, unsigned k, cons
 				}
 			}
 			s2 = (wn[0] * wn[0] + wn[1] * wn[1]) + (wn[2] * wn[2] + wn[3] * wn[3]);
+			s1 = (wn[0] + wn[1]) + (wn[2] + wn[3]);
 		}
 #pragma unroll
-		for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-		if (tx == 0 && c < k) colSqPartials[(size_t)blockIdx.x * k + c] = s2;
+		for (int o = 16; o > 0; o >>= 1) {
+			s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+			s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+		}
+		if (tx == 0 && c < k) {
+			colSqPartials[(size_t)blockIdx.x * k + c] = s2;
+			if (colSumPartials != nullptr) colSumPartials[(size_t)blockIdx.x * k + c] = s1;
+		}
 	}
 }
 
@@ -421,18 +496,32 @@ __global__ void __launch_bounds__(128) column_squares_kernel(unsigned m, unsigne
 
 // one block per column; fixed-order tree over the row-block partials
 template <typename T>
-__global__ void __launch_bounds__(256) finish_norms_kernel(unsigned k, unsigned blocks, const T* __restrict__ partials, T* __restrict__ colSq) {
+__global__ void __launch_bounds__(256) finish_norms_kernel(unsigned k, unsigned blocks, const T* __restrict__ partials, T* __restrict__ colSq,
+                                                           const T* __restrict__ sumPartials, float center, float* __restrict__ corrOut) {
 	__shared__ T red[256];
+	__shared__ double redSum[256];
 	const unsigned c = blockIdx.x;
 	T s = T(0);
-	for (unsigned b = threadIdx.x; b < blocks; b += 256) s += partials[(size_t)b * k + c];
+	double s1 = 0.0;
+	for (unsigned b = threadIdx.x; b < blocks; b += 256) {
+		s += partials[(size_t)b * k + c];
+		if (sumPartials != nullptr) s1 += (double)sumPartials[(size_t)b * k + c];
+	}
 	red[threadIdx.x] = s;
+	redSum[threadIdx.x] = s1;
 	__syncthreads();
 	for (unsigned o = 128; o > 0; o >>= 1) {
-		if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		if (threadIdx.x < o) {
+			red[threadIdx.x] += red[threadIdx.x + o];
+			redSum[threadIdx.x] += redSum[threadIdx.x + o];
+		}
 		__syncthreads();
 	}
-	if (threadIdx.x == 0) colSq[c] = red[0];
+	if (threadIdx.x == 0) {
+		colSq[c] = red[0];
+		// centring term of W^T V for the unit-column matrix that scale_columns writes next (tc_gemm.h)
+		if (corrOut != nullptr) corrOut[c] = (float)((double)center * (red[0] > T(0) ? redSum[0] / sqrt((double)red[0]) : redSum[0]));
+	}
 }
 
 template <typename T>
@@ -787,8 +876,16 @@ __global__ void __launch_bounds__(256) apply_right_clamp(unsigned m, unsigned k,
 	for (int t = 0; t < KP; ++t) {
 		const float4 a = *reinterpret_cast<const float4*>(Xs + t * ROWS + tx * 4);
 		float b[CPT];
+		if (CPT % 4 == 0) {
 #pragma unroll
-		for (int j = 0; j < CPT; ++j) b[j] = Bs[t * KP + ty * CPT + j];
+			for (int j = 0; j < CPT; j += 4) {
+				const float4 x = *reinterpret_cast<const float4*>(Bs + t * KP + ty * CPT + j);
+				b[j] = x.x; b[j + 1] = x.y; b[j + 2] = x.z; b[j + 3] = x.w;
+			}
+		} else {
+#pragma unroll
+			for (int j = 0; j < CPT; ++j) b[j] = Bs[t * KP + ty * CPT + j];
+		}
 #pragma unroll
 		for (int j = 0; j < CPT; ++j) {
 			acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
@@ -870,31 +967,35 @@ static void updateHGeneric(unsigned k, unsigned n, const T* G, const T* Hin, T* 
 template <int KP>
 static void updateHReg(unsigned k, unsigned n, const float* G, const float* Hin, float* Hout, size_t ldh, const float* Npart, size_t ldn,
                        unsigned splits, size_t splitStride, float eps, float* tracePartials, float* HtHi, float* HtLo, size_t ldht,
-                       cudaStream_t stream, const unsigned char* tileSlots, const float* corr) {
+                       cudaStream_t stream, const unsigned char* tileSlots, const float* corr, float* rowSumPartials) {
 	const size_t smem = sizeof(float) * ((size_t)KP * KP + (size_t)KP * (64 + 4));
 	allowSmem(update_h_reg<KP>, smem);
 	update_h_reg<KP><<<ceilDiv(n, 64), 256, smem, stream>>>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials,
-	                                                          HtHi, HtLo, ldht, tileSlots, corr);
+	                                                          HtHi, HtLo, ldht, tileSlots, corr, rowSumPartials);
 	launchCheck();
 }
 
 template <>
 void updateH<float>(unsigned k, unsigned n, const float* G, const float* Hin, float* Hout, size_t ldh, const float* Npart, size_t ldn,
                     unsigned splits, size_t splitStride, float eps, float* tracePartials, float* HtHi, float* HtLo, size_t ldht,
-                    cudaStream_t stream, const unsigned char* tileSlots, const float* corr) {
+                    cudaStream_t stream, const unsigned char* tileSlots, const float* corr, float* rowSumPartials) {
 #define NMF_ARGS k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials, HtHi, HtLo, ldht, stream, tileSlots, corr
-	if (k <= 16) updateHReg<16>(NMF_ARGS);
-	else if (k <= 32) updateHReg<32>(NMF_ARGS);
-	else if (k <= 64) updateHReg<64>(NMF_ARGS);
-	else if (k <= 128) updateHReg<128>(NMF_ARGS);
-	else updateHGeneric<float>(NMF_ARGS);
+	if (k <= 16) updateHReg<16>(NMF_ARGS, rowSumPartials);
+	else if (k <= 32) updateHReg<32>(NMF_ARGS, rowSumPartials);
+	else if (k <= 64) updateHReg<64>(NMF_ARGS, rowSumPartials);
+	else if (k <= 128) updateHReg<128>(NMF_ARGS, rowSumPartials);
+	else {
+		if (rowSumPartials != nullptr) throw EngineError(ResultType::ErrorInvalidArgument, "row-sum partials need a rank <= 128");
+		updateHGeneric<float>(NMF_ARGS);
+	}
 #undef NMF_ARGS
 }
 
 template <>
 void updateH<double>(unsigned k, unsigned n, const double* G, const double* Hin, double* Hout, size_t ldh, const double* Npart,
                      size_t ldn, unsigned splits, size_t splitStride, double eps, double* tracePartials, float* HtHi, float* HtLo,
-                     size_t ldht, cudaStream_t stream, const unsigned char* tileSlots, const double* corr) {
+                     size_t ldht, cudaStream_t stream, const unsigned char* tileSlots, const double* corr, double* rowSumPartials) {
+	if (rowSumPartials != nullptr) throw EngineError(ResultType::ErrorInvalidArgument, "row-sum partials are an fp32 feature");
 	updateHGeneric<double>(k, n, G, Hin, Hout, ldh, Npart, ldn, splits, splitStride, eps, tracePartials, HtHi, HtLo, ldht, stream, tileSlots, corr);
 }
 
@@ -915,24 +1016,26 @@ void absInPlace(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream_t str
 template <int KP>
 static unsigned updateWReg(unsigned m, unsigned k, const float* B, const float* Win, float* Wout, size_t ldw, const float* Ppart,
                            size_t ldp, unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream,
-                           const unsigned char* tileSlots, const float* corr) {
+                           const unsigned char* tileSlots, const float* corr, float* colSumPartials) {
 	const size_t smem = sizeof(float) * ((size_t)KP * KP + (size_t)KP * 128);
 	allowSmem(update_w_reg<KP>, smem);
 	const unsigned blocks = ceilDiv(m, 128);
-	update_w_reg<KP><<<blocks, 256, smem, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots, corr);
+	update_w_reg<KP><<<blocks, 256, smem, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots, corr, colSumPartials);
 	launchCheck();
 	return blocks;
 }
 
 template <>
 unsigned updateW<float>(unsigned m, unsigned k, const float* B, const float* Win, float* Wout, size_t ldw, const float* Ppart, size_t ldp,
-                        unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream, const unsigned char* tileSlots, const float* corr) {
-#define NMF_ARGS m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, stream, tileSlots, corr
+                        unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream, const unsigned char* tileSlots, const float* corr,
+                        float* colSumPartials) {
+#define NMF_ARGS m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, stream, tileSlots, corr, colSumPartials
 	if (k <= 16) return updateWReg<16>(NMF_ARGS);
 	if (k <= 32) return updateWReg<32>(NMF_ARGS);
 	if (k <= 64) return updateWReg<64>(NMF_ARGS);
 	if (k <= 128) return updateWReg<128>(NMF_ARGS);
 #undef NMF_ARGS
+	if (colSumPartials != nullptr) throw EngineError(ResultType::ErrorInvalidArgument, "column-sum partials need a rank <= 128");
 	const unsigned blocks = ceilDiv(m, 128);
 	update_w_generic<float><<<blocks, 128, 0, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots, corr);
 	launchCheck();
@@ -942,7 +1045,8 @@ unsigned updateW<float>(unsigned m, unsigned k, const float* B, const float* Win
 template <>
 unsigned updateW<double>(unsigned m, unsigned k, const double* B, const double* Win, double* Wout, size_t ldw, const double* Ppart,
                          size_t ldp, unsigned splits, size_t splitStride, double eps, double* colSqPartials, cudaStream_t stream,
-                         const unsigned char* tileSlots, const double* corr) {
+                         const unsigned char* tileSlots, const double* corr, double* colSumPartials) {
+	if (colSumPartials != nullptr) throw EngineError(ResultType::ErrorInvalidArgument, "column-sum partials are an fp32 feature");
 	const unsigned blocks = ceilDiv(m, 128);
 	update_w_generic<double><<<blocks, 128, 0, stream>>>(m, k, B, Win, Wout, ldw, Ppart, ldp, splits, splitStride, eps, colSqPartials, tileSlots, corr);
 	launchCheck();
@@ -950,8 +1054,14 @@ unsigned updateW<double>(unsigned m, unsigned k, const double* B, const double* 
 }
 
 template <typename T>
-void finishColumnNorms(unsigned k, unsigned blocks, const T* colSqPartials, T* colSq, cudaStream_t stream) {
-	finish_norms_kernel<T><<<k, 256, 0, stream>>>(k, blocks, colSqPartials, colSq);
+void finishColumnNorms(unsigned k, unsigned blocks, const T* colSqPartials, T* colSq, cudaStream_t stream, const T* colSumPartials, float center,
+                       float* corrOut) {
+	finish_norms_kernel<T><<<k, 256, 0, stream>>>(k, blocks, colSqPartials, colSq, colSumPartials, center, corrOut);
+	launchCheck();
+}
+
+void finishPartialSums(unsigned count, unsigned blocks, const float* partials, float scale, float* out, cudaStream_t stream) {
+	finish_partial_sums_kernel<<<ceilDiv(count, 8), 256, 0, stream>>>(count, blocks, partials, scale, out);
 	launchCheck();
 }
 
@@ -1082,7 +1192,7 @@ void splitTf32(unsigned rows, unsigned cols, const float* X, size_t ldx, float* 
 	template void sumSplits<T>(unsigned, unsigned, const T*, size_t, unsigned, size_t, T*, size_t, cudaStream_t, const unsigned char*, bool, const T*); \
 	template void clampNonNegative<T>(unsigned, unsigned, T*, size_t, cudaStream_t);                                                      \
 	template void absInPlace<T>(unsigned, unsigned, T*, size_t, cudaStream_t);                                                            \
-	template void finishColumnNorms<T>(unsigned, unsigned, const T*, T*, cudaStream_t);                                                   \
+	template void finishColumnNorms<T>(unsigned, unsigned, const T*, T*, cudaStream_t, const T*, float, float*);                                                   \
 	template unsigned columnSquares<T>(unsigned, unsigned, const T*, size_t, T*, cudaStream_t);                                           \
 	template void scaleColumns<T>(unsigned, unsigned, T*, size_t, const T*, float*, float*, cudaStream_t);                                \
 	template void columnDots<T>(unsigned, unsigned, const T*, size_t, const T*, size_t, T*, cudaStream_t);                                \

@@ -47,7 +47,10 @@ void sumSplits(unsigned rows, unsigned cols, const T* src, size_t ldsrc, unsigne
 template <typename T>
 void updateH(unsigned k, unsigned n, const T* G, const T* Hin, T* Hout, size_t ldh, const T* Npart, size_t ldn, unsigned splits,
              size_t splitStride, T eps, T* tracePartials, float* HtHi, float* HtLo, size_t ldht, cudaStream_t stream,
-             const unsigned char* tileSlots = nullptr, const T* corr = nullptr);
+             const unsigned char* tileSlots = nullptr, const T* corr = nullptr, T* rowSumPartials = nullptr);
+// rowSumPartials (fp32, rank <= 128): [ceil(n / 64)][k] row sums of Hout per 64-column block, for the centring term of V H^T;
+// finishPartialSums adds them up: out[r] = scale * sum_b partials[b * count + r] (fp64 accumulation, fixed order)
+void finishPartialSums(unsigned count, unsigned blocks, const float* partials, float scale, float* out, cudaStream_t stream);
 
 // Hout = max(0, N) after N was overwritten by the least-squares solve (GDCLS.h:206-209)
 template <typename T>
@@ -60,11 +63,13 @@ void clampNonNegative(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream
 template <typename T>
 unsigned updateW(unsigned m, unsigned k, const T* B, const T* Win, T* Wout, size_t ldw, const T* Ppart, size_t ldp, unsigned splits,
                  size_t splitStride, T eps, T* colSqPartials, cudaStream_t stream, const unsigned char* tileSlots = nullptr,
-                 const T* corr = nullptr);
+                 const T* corr = nullptr, T* colSumPartials = nullptr);   // colSumPartials: per-block column sums of Wout (fp32, rank <= 128)
 
 // colSq[c] = sum_b colSqPartials[b][c] (fixed order) ; used by scaleColumns
+// With colSumPartials also corrOut[c] = center * (column sum of the unit-column matrix), the centring term of W^T V (tc_gemm.h)
 template <typename T>
-void finishColumnNorms(unsigned k, unsigned blocks, const T* colSqPartials, T* colSq, cudaStream_t stream);
+void finishColumnNorms(unsigned k, unsigned blocks, const T* colSqPartials, T* colSq, cudaStream_t stream, const T* colSumPartials = nullptr,
+                       float center = 0.f, float* corrOut = nullptr);
 
 // per-block column sums of squares of an m x k matrix (for paths that do not go through updateW)
 template <typename T>

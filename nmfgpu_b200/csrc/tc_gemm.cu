@@ -635,12 +635,15 @@ __global__ void __launch_bounds__(256) row_sums_stage1(unsigned rows, unsigned c
 		partial[(size_t)blockIdx.x * rows + r] = acc;
 	}
 }
-__global__ void sums_stage2(unsigned count, unsigned slices, const double* __restrict__ partial, float scale, float* __restrict__ out) {
-	const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output entry, lanes stride the slices (a single thread walking 128 slices is a chain of 128 L2 latencies)
+__global__ void __launch_bounds__(256) sums_stage2(unsigned count, unsigned slices, const double* __restrict__ partial, float scale, float* __restrict__ out) {
+	const unsigned x = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
 	if (x >= count) return;
 	double acc = 0.0;
-	for (unsigned s = 0; s < slices; ++s) acc += partial[(size_t)s * count + x];
-	out[x] = (float)((double)scale * acc);
+	for (unsigned s = lane; s < slices; s += 32) acc += partial[(size_t)s * count + x];
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if (lane == 0) out[x] = (float)((double)scale * acc);
 }
 constexpr unsigned SUM_SLICES = 32, ROW_SUM_SLICES = 128;
 
@@ -773,21 +776,21 @@ float meanOf(const float* V, unsigned m, unsigned n, size_t ldV, cudaStream_t st
 void refreshCorrectionW(Plan& plan, const float* W, size_t ldW, cudaStream_t stream) {
 	const unsigned chunk = ceilDiv(plan.m, SUM_SLICES);
 	column_sums_stage1<<<dim3(plan.k, SUM_SLICES), 256, 0, stream>>>(plan.m, plan.k, W, ldW, chunk, plan.sumScratch);
-	sums_stage2<<<1, 128, 0, stream>>>(plan.k, SUM_SLICES, plan.sumScratch, plan.center, plan.corrN);
+	sums_stage2<<<ceilDiv(plan.k, 8), 256, 0, stream>>>(plan.k, SUM_SLICES, plan.sumScratch, plan.center, plan.corrN);
 	CUDA_CHECK(cudaGetLastError());
 }
 
 void columnSums(Plan& plan, const float* W, unsigned rows, size_t ldW, float* out, cudaStream_t stream) {
 	const unsigned chunk = ceilDiv(rows, SUM_SLICES);
 	column_sums_stage1<<<dim3(plan.k, SUM_SLICES), 256, 0, stream>>>(rows, plan.k, W, ldW, chunk, plan.sumScratch);
-	sums_stage2<<<1, 128, 0, stream>>>(plan.k, SUM_SLICES, plan.sumScratch, 1.f, out);
+	sums_stage2<<<ceilDiv(plan.k, 8), 256, 0, stream>>>(plan.k, SUM_SLICES, plan.sumScratch, 1.f, out);
 	CUDA_CHECK(cudaGetLastError());
 }
 
 void refreshCorrectionH(Plan& plan, const float* H, size_t ldH, cudaStream_t stream) {
 	const unsigned chunk = ceilDiv(plan.n, ROW_SUM_SLICES);
 	row_sums_stage1<<<ROW_SUM_SLICES, 256, 0, stream>>>(plan.k, plan.n, H, ldH, chunk, plan.sumScratch);
-	sums_stage2<<<1, 128, 0, stream>>>(plan.k, ROW_SUM_SLICES, plan.sumScratch, plan.center, plan.corrP);
+	sums_stage2<<<ceilDiv(plan.k, 8), 256, 0, stream>>>(plan.k, ROW_SUM_SLICES, plan.sumScratch, plan.center, plan.corrP);
 	CUDA_CHECK(cudaGetLastError());
 }
 
