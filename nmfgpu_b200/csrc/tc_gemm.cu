@@ -25,6 +25,8 @@
 
 #include <cuda.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -86,6 +88,7 @@ struct KParams {
 	unsigned long long* trace;   // optional timeline of CTA 0 (NMFGPU_TC_TRACE), nullptr otherwise
 	unsigned long long ldOut, slotStride, units;
 	unsigned rowsA, k, kp, tiles, stagesPerTile, flushStages, passes, grid;
+	unsigned chunks, chunkStages;   // reduction chunks (tc_gemm.h): `units` = tiles * chunkStages units per chunk
 	float center;   // subtracted from every element of V before the split (see tc_gemm.h)
 	unsigned prefetchStages;   // how many stages ahead of the TMA loads the V tiles are prefetched into L2
 };
@@ -103,20 +106,31 @@ struct Segment {
 	unsigned tile, stage0, len, slot;
 };
 
+// Every CTA takes the same share [units * cta / grid, units * (cta + 1) / grid) of EVERY chunk, one chunk after the other
+// (tc_gemm.h), so all CTAs sweep the same part of the reduction range at the same time.  The last chunk of a tile may be
+// padded; a segment that lies entirely in the padding has len 0 and still owns a slot (it writes zeros).
 struct SegmentWalker {
-	unsigned long long u, uEnd, units;
-	unsigned stagesPerTile, grid, cta;
+	unsigned long long u, uBegin, uEnd, units;
+	unsigned stagesPerTile, chunkStages, chunks, chunk, grid, cta;
 	__device__ SegmentWalker(const KParams& p, unsigned ctaIdx)
-	    : u(unitStart(ctaIdx, p.grid, p.units)), uEnd(unitStart(ctaIdx + 1, p.grid, p.units)), units(p.units), stagesPerTile(p.stagesPerTile),
-	      grid(p.grid), cta(ctaIdx) {}
+	    : u(unitStart(ctaIdx, p.grid, p.units)), uBegin(u), uEnd(unitStart(ctaIdx + 1, p.grid, p.units)), units(p.units),
+	      stagesPerTile(p.stagesPerTile), chunkStages(p.chunkStages), chunks(p.chunks), chunk(0), grid(p.grid), cta(ctaIdx) {}
 	__device__ bool next(Segment& s) {
-		if (u >= uEnd) return false;
-		s.tile = (unsigned)(u / stagesPerTile);
-		s.stage0 = (unsigned)(u % stagesPerTile);
-		const unsigned long long room = stagesPerTile - s.stage0;
-		s.len = (unsigned)((uEnd - u) < room ? (uEnd - u) : room);
-		s.slot = cta - ctaOfUnit((unsigned long long)s.tile * stagesPerTile, grid, units);
-		u += s.len;
+		if (u >= uEnd) {
+			if (++chunk >= chunks || uBegin >= uEnd) return false;
+			u = uBegin;
+		}
+		s.tile = (unsigned)(u / chunkStages);
+		const unsigned a = (unsigned)(u % chunkStages);
+		const unsigned long long room = chunkStages - a;
+		const unsigned len = (unsigned)((uEnd - u) < room ? (uEnd - u) : room);
+		s.stage0 = chunk * chunkStages + a;
+		s.len = s.stage0 >= stagesPerTile ? 0u : (len < stagesPerTile - s.stage0 ? len : stagesPerTile - s.stage0);
+		// the CTAs that share a tile are the same in every chunk: `perTile` partial products per chunk
+		const unsigned long long f = (unsigned long long)s.tile * chunkStages;
+		const unsigned firstCta = ctaOfUnit(f, grid, units), perTile = ctaOfUnit(f + chunkStages - 1, grid, units) - firstCta + 1;
+		s.slot = chunk * perTile + (cta - firstCta);
+		u += len;
 		return true;
 	}
 };
@@ -428,7 +442,12 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 		const unsigned row = (warp % 4) * 32 + lane;        // A row = TMEM lane owned by this thread
 		const uint32_t laneBase = ((warp % 4) * 32) << 16;
 		const float center = p.center;
-		const unsigned tEnd = 2 * (unsigned)(unitStart(blockIdx.x + 1, p.grid, p.units) - unitStart(blockIdx.x, p.grid, p.units));
+		unsigned tEnd = 0;   // tile steps of this CTA: two per real stage
+		{
+			SegmentWalker walk(p, blockIdx.x);
+			Segment s;
+			while (walk.next(s)) tEnd += 2 * s.len;
+		}
 		float v[STAGE_K];
 		RingPos vpos;   // this warpgroup's position in its V ring (SPLIT_WGS == 2: warpgroup wgi reads the ring of A tile wgi)
 		auto loadTile = [&](unsigned) {
@@ -690,21 +709,30 @@ int smCount() {
 	return sms;
 }
 
-void planProduct(Product& prod, unsigned rowsA, unsigned kdim) {
+void planProduct(Product& prod, unsigned rowsA, unsigned kdim, unsigned kp) {
 	prod.tiles = ceilDiv(rowsA, PAIR_ROWS);
 	prod.stagesPerTile = ceilDiv(kdim, STAGE_K);
-	const unsigned long long units = (unsigned long long)prod.tiles * prod.stagesPerTile;
+	// reduction chunks: the hi/lo copies of the small operand that one chunk reads should sit in L2 (~12 MB) while all CTAs
+	// sweep that chunk; at least 64 stages per chunk and at most 8 chunks (every chunk adds partial products per tile)
+	const double operandBytes = 2.0 * kdim * kp * 4.0;
+	unsigned chunks = (unsigned)std::min(8.0, std::max(1.0, std::ceil(operandBytes / 12.0e6)));
+	chunks = std::max(1u, std::min(chunks, prod.stagesPerTile / 64));
+	if (const char* e = getenv("NMFGPU_TC_CHUNKS")) chunks = std::max(1u, std::min((unsigned)atoi(e), prod.stagesPerTile));   // tuning knob
+	prod.chunkStages = ceilDiv(prod.stagesPerTile, chunks);
+	prod.chunks = ceilDiv(prod.stagesPerTile, prod.chunkStages);
+	const unsigned long long units = (unsigned long long)prod.tiles * prod.chunkStages;   // per chunk
 	prod.grid = (unsigned)std::min<unsigned long long>(units, (unsigned long long)smCount());
 	// consumers index the counts by 128-wide tile (kernels.h), the stream-K tiles are 256 wide
 	const unsigned tiles128 = ceilDiv(rowsA, TILE_ROWS);
 	std::vector<unsigned char> counts(tiles128);
 	prod.maxSlots = 1;
 	for (unsigned t = 0; t < prod.tiles; ++t) {
-		const unsigned first = ctaOfUnit((unsigned long long)t * prod.stagesPerTile, prod.grid, units);
-		const unsigned last = ctaOfUnit((unsigned long long)(t + 1) * prod.stagesPerTile - 1, prod.grid, units);
+		const unsigned long long f = (unsigned long long)t * prod.chunkStages;
+		const unsigned slots = prod.chunks * (ctaOfUnit(f + prod.chunkStages - 1, prod.grid, units) - ctaOfUnit(f, prod.grid, units) + 1);
+		if (slots > 255) throw EngineError(ResultType::ErrorInvalidArgument, "more than 255 partial products per tile");
 		for (unsigned h = 0; h < 2; ++h)
-			if (2 * t + h < tiles128) counts[2 * t + h] = (unsigned char)(last - first + 1);
-		prod.maxSlots = std::max(prod.maxSlots, last - first + 1);
+			if (2 * t + h < tiles128) counts[2 * t + h] = (unsigned char)slots;
+		prod.maxSlots = std::max(prod.maxSlots, slots);
 	}
 	if (prod.slotCount) pooledDeviceFree(prod.slotCount, prod.slotCountBytes);
 	prod.slotCountBytes = roundUp(tiles128, 256);
@@ -728,7 +756,9 @@ void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, s
 	p.trace = plan.trace;
 	p.ldOut = ldOut;
 	p.slotStride = slotStride;
-	p.units = (unsigned long long)prod.tiles * prod.stagesPerTile;
+	p.units = (unsigned long long)prod.tiles * prod.chunkStages;   // per chunk
+	p.chunks = prod.chunks;
+	p.chunkStages = prod.chunkStages;
 	p.rowsA = rowsA;
 	p.k = plan.k;
 	p.kp = plan.kp;
@@ -856,12 +886,12 @@ void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, si
 		CUDA_CHECK(cudaMemset(plan.trace, 0, TRACE_STAGES * TRACE_EVENTS * sizeof(unsigned long long)));
 	}
 	// W^T V: A rows = columns of V, reduction over m
-	planProduct(plan.wtv, n, m);
+	planProduct(plan.wtv, n, m, plan.kp);
 	makeMap(plan.wtv.mapV, V, m, n, ldV, STAGE_K, TILE_ROWS, true);
 	makeMap(plan.wtv.mapBhi, Whi, m, k, ldW, STAGE_K, plan.kp, true);
 	makeMap(plan.wtv.mapBlo, Wlo, m, k, ldW, STAGE_K, plan.kp, true);
 	// V H^T: A rows = rows of V, reduction over n
-	planProduct(plan.vht, m, n);
+	planProduct(plan.vht, m, n, plan.kp);
 	makeMap(plan.vht.mapV, V, m, n, ldV, TILE_ROWS, STAGE_K, false, false);   // 512-byte rows: promotion only costs bandwidth (tools/tma_stream_bench)
 	makeMap(plan.vht.mapBhi, HtHi, n, k, ldHt, STAGE_K, plan.kp, true);
 	makeMap(plan.vht.mapBlo, HtLo, n, k, ldHt, STAGE_K, plan.kp, true);

@@ -27,6 +27,11 @@ namespace tc {
 struct Product {
 	unsigned tiles = 0;            // 128-row tiles of the A operand
 	unsigned stagesPerTile = 0;    // reduction stages (32 elements) per tile
+	// Reduction chunks: the reduction range is cut into `chunks` pieces of chunkStages stages and the units are ordered
+	// chunk-major, so at any time all CTAs read the same piece of the small operand (W for W^T V) and it stays in L2.
+	// Without chunks every CTA walks its own part of the whole range, W hi/lo (51 MB at 100 000 x 64) keep getting evicted
+	// by the stream of V and W^T V fetched 0.55 GB of W from DRAM per launch (ncu: 26 % misses on the evict_last lines).
+	unsigned chunks = 1, chunkStages = 0;
 	unsigned grid = 0;             // persistent CTAs
 	unsigned maxSlots = 1;         // partial products a consumer may have to add per tile
 	unsigned char* slotCount = nullptr;   // device, [tiles]
