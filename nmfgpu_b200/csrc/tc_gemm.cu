@@ -717,6 +717,10 @@ void planProduct(Product& prod, unsigned rowsA, unsigned kdim, unsigned kp) {
 	const double operandBytes = 2.0 * kdim * kp * 4.0;
 	unsigned chunks = (unsigned)std::min(8.0, std::max(1.0, std::ceil(operandBytes / 12.0e6)));
 	chunks = std::max(1u, std::min(chunks, prod.stagesPerTile / 64));
+	// every chunk multiplies the partial products a tile receives (one per CTA that shares the tile), and the consumers
+	// walk them one after the other: no more than ~24 per tile (8 GPUs: 5 tiles on 148 CTAs are 30 per chunk already)
+	const unsigned perTile = ceilDiv((unsigned)smCount(), prod.tiles) + 1;
+	chunks = std::max(1u, std::min(chunks, 24u / perTile));
 	if (const char* e = getenv("NMFGPU_TC_CHUNKS")) chunks = std::max(1u, std::min((unsigned)atoi(e), prod.stagesPerTile));   // tuning knob
 	prod.chunkStages = ceilDiv(prod.stagesPerTile, chunks);
 	prod.chunks = ceilDiv(prod.stagesPerTile, prod.chunkStages);
