@@ -68,6 +68,45 @@ for (m, n, k, iters) in shapes:
         failed |= not ok
         print("rank %d %s %-9s W %.2e  H %.2e  residual %.9g vs %.9g (%.1e)  collectives %d  %s"
               % (rank, (m, n, k), mode, eW, eH, f2, f1, ef, calls, "ok" if ok else "MISMATCH"), flush=True)
+
+# ---- compressed execution of a sparse input (csrc/spmm.cu) over column shards: all-reduce dataflow, through the reference API
+import scipy.sparse as sp                                          # noqa: E402
+from nmfgpu_b200.workloads import planted_inputs                   # noqa: E402
+m, n, k, iters = 3000, 2048, 24, 20
+rng = np.random.default_rng(5)
+D = ((rng.random((m, n)) < 0.01) * (0.1 + rng.random((m, n)))).astype(np.float32)
+_, W0, H0 = planted_inputs(m, n, k, seed=2)
+
+
+def csr_desc(block):
+    S = sp.csr_matrix(block)
+    keep = (S.data.astype(np.float32), S.indptr.astype(np.int32), S.indices.astype(np.int32))
+    return api.sparse_description(api.StorageFormat.CSR, block.shape[0], block.shape[1], *keep), keep
+
+
+os.environ["NMFGPU_SPARSE"] = "1"
+desc, keep = csr_desc(D)
+single = L.compute(None, k, W0=W0, H0=H0, iterations=iters, sparse=(desc, np.dtype(np.float32)))
+c0, c1 = shard_columns(n, world, rank)
+if rank == 0:
+    buf = (ctypes.c_ubyte * 128)()
+    assert L.lib.nmfgpu_b200_dist_unique_id(buf) == 0
+    uid = torch.tensor(list(buf), dtype=torch.uint8)
+u = uid.cuda()
+dist.broadcast(u, 0)
+assert L.lib.nmfgpu_b200_dist_init(rank, world, bytes(u.cpu().tolist())) == 0
+assert L.lib.nmfgpu_b200_dist_set_shard(n, c0) == 0
+desc, keep = csr_desc(np.ascontiguousarray(D[:, c0:c1]))
+shard = L.compute(None, k, W0=W0, H0=np.asfortranarray(H0[:, c0:c1]), iterations=iters, sparse=(desc, np.dtype(np.float32)))
+assert L.lib.nmfgpu_b200_dist_finalize() == 0
+assert single["rc"] == 0 and shard["rc"] == 0, (single["rc"], shard["rc"])
+eW = np.linalg.norm(shard["W"] - single["W"]) / np.linalg.norm(single["W"])
+eH = np.linalg.norm(shard["H"] - single["H"][:, c0:c1]) / np.linalg.norm(single["H"][:, c0:c1])
+ef = abs(shard["frobenius"] - single["frobenius"]) / single["frobenius"]
+ok = eW <= 2e-4 and eH <= 2e-4 and ef <= 2e-5
+failed |= not ok
+print("rank %d sparse %s W %.2e  H %.2e  residual %.9g vs %.9g (%.1e)  %s"
+      % (rank, (m, n, k), eW, eH, shard["frobenius"], single["frobenius"], ef, "ok" if ok else "MISMATCH"), flush=True)
 L.finalize()
 dist.destroy_process_group()
 sys.exit(1 if failed else 0)
