@@ -71,6 +71,7 @@ template <typename T>
 void Engine<T>::reportStamps() {
 	if (m_stamps.empty()) return;
 	cudaStreamSynchronize(m_stream);
+	const bool quiet = m_cfg.comm != nullptr && m_cfg.comm->rank() != 0;   // one report per job
 	std::vector<std::pair<const char*, double>> sums;
 	unsigned iterations = 0;
 	for (size_t i = 1; i < m_stamps.size(); ++i) {
@@ -89,8 +90,10 @@ void Engine<T>::reportStamps() {
 	const double count = iterations > 2 ? iterations - 2 : 1;
 	double total = 0.0;
 	for (auto& s : sums) total += s.second / count;
-	for (auto& s : sums) errorf("[iteration] %-28s %8.1f us\n", s.first, 1000.0 * s.second / count);
-	errorf("[iteration] %-28s %8.1f us over %u iterations\n", "total", 1000.0 * total, (unsigned)count);
+	if (!quiet) {
+		for (auto& s : sums) errorf("[iteration] %-28s %8.1f us\n", s.first, 1000.0 * s.second / count);
+		errorf("[iteration] %-28s %8.1f us over %u iterations\n", "total", 1000.0 * total, (unsigned)count);
+	}
 	for (auto& s : m_stamps) cudaEventDestroy(s.second);
 	m_stamps.clear();
 }
@@ -358,12 +361,16 @@ void Engine<T>::iterateMURowOwners(bool err) {
 	const unsigned n = m_cfg.n, k = m_cfg.k;
 	Communicator* comm = m_cfg.comm;
 	// ---- H <- H o (W^T V) / ((W^T W) H + eps) on the columns of this rank (MU.h:164-198); m_G is up to date
+	stamp("begin");
 	productWtV(m_W[m_wCur].get());
+	stamp("product W^T V (own columns)");
 	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_eps,
 	                 err ? m_partN.get() : nullptr, nullptr, nullptr, m_ldHt, m_stream, m_slotsN, m_corrN);
 	m_launches += 1;
 	m_hCur = 1 - m_hCur;
+	stamp("update H");
 	gatherH();
+	stamp("all-gather H, split, H H^T");
 	if (err) {
 		kern::traceKK<T>(k, m_B.get(), m_G.get(), m_partK.get(), m_stream);                 // tr(HH^T W^T W) MU.h:203-216
 		m_launches += 1;
@@ -372,6 +379,7 @@ void Engine<T>::iterateMURowOwners(bool err) {
 	// ---- W <- W o (V H^T) / (W (H H^T) + eps) on the rows of this rank (MU.h:200-248)
 	float* stat = m_stat.get();
 	tc::gemmVHt(m_tcR->plan, m_PpartR.get(), m_ldPr, m_stridePr, m_stream);
+	stamp("product V H^T (own rows)");
 	T* Wnext = m_W[1 - m_wCur].get();
 	kern::updateW<T>(m_mr, k, m_B.get(), m_W[m_wCur].get() + m_r0, Wnext + m_r0, m_ldW, reinterpret_cast<const T*>(m_PpartR.get()), m_ldPr, m_splitsPr,
 	                 m_stridePr, m_eps, m_colSqPartials.get(), m_stream, m_tcR->plan.vht.slotCount, reinterpret_cast<const T*>(m_tcR->plan.corrP));
@@ -379,11 +387,16 @@ void Engine<T>::iterateMURowOwners(bool err) {
 	kern::gemmTN<T>(m_mr, k, k, Wnext + m_r0, m_ldW, Wnext + m_r0, m_ldW, m_kkScratch.get(), k, m_splitsGWrows, (size_t)k * k, m_stream);
 	kern::sumSplits<T>(k, k, m_kkScratch.get(), k, m_splitsGWrows, (size_t)k * k, reinterpret_cast<T*>(stat), k, m_stream);
 	tc::columnSums(m_tc->plan, reinterpret_cast<const float*>(Wnext) + m_r0, m_mr, m_ldW, stat + (size_t)k * k, m_stream);
+	stamp("update W rows, statistics");
 	comm->allReduceSum(stat, (size_t)k * k + k, m_stream);
+	stamp("all-reduce statistics");
 	kern::finishStats(k, stat, m_tc->plan.center, reinterpret_cast<float*>(m_G.get()), m_tc->plan.corrN, m_stream);
 	kern::scalePackRows(m_mr, m_mrPad, k, reinterpret_cast<const float*>(Wnext) + m_r0, m_ldW, stat, m_Wblk.get(), m_stream);
+	stamp("norms, scale, pack");
 	comm->allGather(m_Wblk.get(), m_Wgath.get(), (size_t)m_mrPad * k, m_stream);
+	stamp("all-gather W");
 	kern::unpackSplit(m_cfg.m, k, m_mrPad, m_Wgath.get(), reinterpret_cast<float*>(Wnext), m_ldW, m_Whi.get(), m_Wlo.get(), m_stream);
+	stamp("unpack W, hi/lo");
 	m_launches += 10;
 	m_wCur = 1 - m_wCur;
 	if (err) resolveError(n);
