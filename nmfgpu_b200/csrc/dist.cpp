@@ -111,6 +111,15 @@ void Communicator::allGather(const float* send, float* recv, size_t countPerRank
 	++m_calls;
 }
 
+void Communicator::allGatherPair(const float* sendA, float* recvA, size_t countA, const float* sendB, float* recvB, size_t countB, cudaStream_t stream) {
+	if (m_world <= 1) return;
+	ncclCheck(api().groupStart(), "ncclGroupStart");
+	ncclCheck(api().allGather(sendA, recvA, countA, ncclFloat, static_cast<ncclComm_t>(m_comm), stream), "ncclAllGather");
+	ncclCheck(api().allGather(sendB, recvB, countB, ncclFloat, static_cast<ncclComm_t>(m_comm), stream), "ncclAllGather");
+	ncclCheck(api().groupEnd(), "ncclGroupEnd");
+	++m_calls;
+}
+
 void Communicator::exchange(const std::vector<Transfer>& sends, const std::vector<Transfer>& recvs, cudaStream_t stream) {
 	if (m_world <= 1) return;
 	ncclCheck(api().groupStart(), "ncclGroupStart");

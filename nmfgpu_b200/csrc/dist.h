@@ -33,6 +33,8 @@ public:
 	void allReduceSum(double* buffer, size_t count, cudaStream_t stream);
 	// recv[r * countPerRank ...] <- send of rank r (equal counts on every rank)
 	void allGather(const float* send, float* recv, size_t countPerRank, cudaStream_t stream);
+	// two all-gathers in one NCCL group (one launch): a matrix block and the small statistics that travel with it
+	void allGatherPair(const float* sendA, float* recvA, size_t countA, const float* sendB, float* recvB, size_t countB, cudaStream_t stream);
 	// one grouped point-to-point exchange: every send/recv pair of the group proceeds concurrently
 	struct Transfer {
 		float* buffer;

@@ -335,7 +335,11 @@ void Engine<T>::setupRowOwners() {
 	m_ldPr = roundUp(m_mr, 32);
 	m_stridePr = m_ldPr * k;
 	m_PpartR.allocate(m_stridePr * m_splitsPr);
-	m_stat.allocate((size_t)k * k + 128);
+	m_statLen = roundUp((size_t)k * k + k, 32);
+	m_stat.allocate(m_statLen);
+	m_statPart.allocate(m_statLen);
+	m_statGath.allocate(m_statLen * G);
+	m_statPart.zero(m_stream);
 	m_Wblk.allocate((size_t)mrPad * k);
 	m_Wgath.allocate((size_t)mrPad * k * G);
 	m_splitsGHfull = kern::effectiveSplits(N, pickGramSplits(ceilDiv(k, 64) * ceilDiv(k, 64), N));
@@ -343,17 +347,24 @@ void Engine<T>::setupRowOwners() {
 	m_kkScratch.allocate((size_t)k * k * std::max(std::max(m_splitsGW, m_splitsGH), std::max(m_splitsGHfull, m_splitsGWrows)));
 }
 
-// everything the W update derives from H: the full matrix, its transposed TF32 split, H H^T and the centring term
+// Everything the W update derives from H: the full matrix and its transposed TF32 split, H H^T and the centring term.
+// The k*k + k statistics of the local columns (H_g H_g^T and the row sums) travel with the all-gather of H in one NCCL
+// group and are added up in rank order on every rank: no separate all-reduce and no replicated work on all n columns.
 template <typename T>
-void Engine<T>::gatherH() {
-	const unsigned k = m_cfg.k, N = m_globalN;
-	m_cfg.comm->allGather(reinterpret_cast<const float*>(m_H[m_hCur].get()), m_Hfull.get(), m_ldH * m_cfg.n, m_stream);
+void Engine<T>::gatherH(bool haveRowSums) {
+	const unsigned k = m_cfg.k, n = m_cfg.n, N = m_globalN;
+	const unsigned G = (unsigned)m_cfg.comm->worldSize();
+	const T* Hloc = m_H[m_hCur].get();
+	float* part = m_statPart.get();
+	kern::gemmNT<T>(k, n, k, Hloc, m_ldH, Hloc, m_ldH, m_kkScratch.get(), k, m_splitsGH, (size_t)k * k, m_stream);
+	kern::sumSplits<T>(k, k, m_kkScratch.get(), k, m_splitsGH, (size_t)k * k, reinterpret_cast<T*>(part), k, m_stream);
+	if (haveRowSums) kern::finishPartialSums(k, ceilDiv(n, 64), reinterpret_cast<const float*>(m_rowSumPartials.get()), 1.f, part + (size_t)k * k, m_stream);
+	else tc::rowSums(m_tcR->plan, reinterpret_cast<const float*>(Hloc), n, m_ldH, part + (size_t)k * k, m_stream);
+	m_cfg.comm->allGatherPair(reinterpret_cast<const float*>(Hloc), m_Hfull.get(), m_ldH * n, part, m_statGath.get(), m_statLen, m_stream);
 	tc::splitTransposeH(k, N, m_Hfull.get(), m_ldH, m_HtHiFull.get(), m_HtLoFull.get(), m_ldHtFull, m_stream);
-	const T* H = reinterpret_cast<const T*>(m_Hfull.get());
-	kern::gemmNT<T>(k, N, k, H, m_ldH, H, m_ldH, m_kkScratch.get(), k, m_splitsGHfull, (size_t)k * k, m_stream);
-	kern::sumSplits<T>(k, k, m_kkScratch.get(), k, m_splitsGHfull, (size_t)k * k, m_B.get(), k, m_stream);
-	tc::refreshCorrectionH(m_tcR->plan, m_Hfull.get(), m_ldH, m_stream);
-	m_launches += 5;
+	kern::sumGathered((unsigned)((size_t)k * k + k), G, m_statLen, m_statGath.get(), m_stat.get(), m_stream);
+	kern::finishStatsH(k, m_stat.get(), m_tcR->plan.center, reinterpret_cast<float*>(m_B.get()), m_tcR->plan.corrP, m_stream);
+	m_launches += 7;
 }
 
 template <typename T>
@@ -365,12 +376,12 @@ void Engine<T>::iterateMURowOwners(bool err) {
 	productWtV(m_W[m_wCur].get());
 	stamp("product W^T V (own columns)");
 	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_eps,
-	                 err ? m_partN.get() : nullptr, nullptr, nullptr, m_ldHt, m_stream, m_slotsN, m_corrN);
+	                 err ? m_partN.get() : nullptr, nullptr, nullptr, m_ldHt, m_stream, m_slotsN, m_corrN, m_rowSumPartials.get());
 	m_launches += 1;
 	m_hCur = 1 - m_hCur;
 	stamp("update H");
-	gatherH();
-	stamp("all-gather H, split, H H^T");
+	gatherH(true);
+	stamp("H statistics, all-gather, split");
 	if (err) {
 		kern::traceKK<T>(k, m_B.get(), m_G.get(), m_partK.get(), m_stream);                 // tr(HH^T W^T W) MU.h:203-216
 		m_launches += 1;
@@ -383,20 +394,21 @@ void Engine<T>::iterateMURowOwners(bool err) {
 	T* Wnext = m_W[1 - m_wCur].get();
 	kern::updateW<T>(m_mr, k, m_B.get(), m_W[m_wCur].get() + m_r0, Wnext + m_r0, m_ldW, reinterpret_cast<const T*>(m_PpartR.get()), m_ldPr, m_splitsPr,
 	                 m_stridePr, m_eps, m_colSqPartials.get(), m_stream, m_tcR->plan.vht.slotCount, reinterpret_cast<const T*>(m_tcR->plan.corrP));
-	// statistics of the un-normalised block: Gram matrix (its diagonal = the column sums of squares) and column sums
+	// statistics of the un-normalised block: Gram matrix (its diagonal = the column sums of squares) and column sums.
+	// They travel with the all-gather of the (still un-normalised) blocks in one NCCL group; every rank adds them up in
+	// rank order and the unpack kernel divides by the norms.
+	float* part = m_statPart.get();
 	kern::gemmTN<T>(m_mr, k, k, Wnext + m_r0, m_ldW, Wnext + m_r0, m_ldW, m_kkScratch.get(), k, m_splitsGWrows, (size_t)k * k, m_stream);
-	kern::sumSplits<T>(k, k, m_kkScratch.get(), k, m_splitsGWrows, (size_t)k * k, reinterpret_cast<T*>(stat), k, m_stream);
-	tc::columnSums(m_tc->plan, reinterpret_cast<const float*>(Wnext) + m_r0, m_mr, m_ldW, stat + (size_t)k * k, m_stream);
-	stamp("update W rows, statistics");
-	comm->allReduceSum(stat, (size_t)k * k + k, m_stream);
-	stamp("all-reduce statistics");
+	kern::sumSplits<T>(k, k, m_kkScratch.get(), k, m_splitsGWrows, (size_t)k * k, reinterpret_cast<T*>(part), k, m_stream);
+	tc::columnSums(m_tc->plan, reinterpret_cast<const float*>(Wnext) + m_r0, m_mr, m_ldW, part + (size_t)k * k, m_stream);
+	kern::scalePackRows(m_mr, m_mrPad, k, reinterpret_cast<const float*>(Wnext) + m_r0, m_ldW, nullptr, m_Wblk.get(), m_stream);
+	stamp("update W rows, statistics, pack");
+	comm->allGatherPair(m_Wblk.get(), m_Wgath.get(), (size_t)m_mrPad * k, part, m_statGath.get(), m_statLen, m_stream);
+	stamp("all-gather W + statistics");
+	kern::sumGathered((unsigned)((size_t)k * k + k), (unsigned)comm->worldSize(), m_statLen, m_statGath.get(), stat, m_stream);
 	kern::finishStats(k, stat, m_tc->plan.center, reinterpret_cast<float*>(m_G.get()), m_tc->plan.corrN, m_stream);
-	kern::scalePackRows(m_mr, m_mrPad, k, reinterpret_cast<const float*>(Wnext) + m_r0, m_ldW, stat, m_Wblk.get(), m_stream);
-	stamp("norms, scale, pack");
-	comm->allGather(m_Wblk.get(), m_Wgath.get(), (size_t)m_mrPad * k, m_stream);
-	stamp("all-gather W");
-	kern::unpackSplit(m_cfg.m, k, m_mrPad, m_Wgath.get(), reinterpret_cast<float*>(Wnext), m_ldW, m_Whi.get(), m_Wlo.get(), m_stream);
-	stamp("unpack W, hi/lo");
+	kern::unpackSplit(m_cfg.m, k, m_mrPad, m_Wgath.get(), reinterpret_cast<float*>(Wnext), m_ldW, m_Whi.get(), m_Wlo.get(), m_stream, stat);
+	stamp("norms, unpack W, hi/lo");
 	m_launches += 10;
 	m_wCur = 1 - m_wCur;
 	if (err) resolveError(n);
@@ -518,7 +530,7 @@ void Engine<T>::finishInitialisation() {
 	operandChangedH(m_H[m_hCur].get());
 	if (m_rowOwners) {   // what the iteration keeps up to date itself: W^T W and everything derived from the full H
 		gramW(m_W[m_wCur].get(), m_G.get());
-		gatherH();
+		gatherH(false);
 	}
 }
 

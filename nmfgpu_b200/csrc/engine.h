@@ -98,7 +98,7 @@ private:
 	void iterateMU(bool err);
 	void iterateMURowOwners(bool err);
 	void setupRowOwners();                                     // dist.h: second dataflow for column shards (MU, tensor cores)
-	void gatherH();                                            // full H, its transposed split, H H^T and the centring term
+	void gatherH(bool haveRowSums);                            // full H, its transposed split, H H^T and the centring term
 	void iterateNsNMF(bool err);
 	void iterateLS(bool err);
 	void resolveError(unsigned secondLen);
@@ -162,8 +162,8 @@ private:
 	// only those rows of W; m_tcR plans V[I, :] H^T over all columns
 	bool m_rowOwners = false;
 	unsigned m_r0 = 0, m_mr = 0, m_mrPad = 0, m_globalN = 0, m_splitsGHfull = 1, m_splitsGWrows = 1, m_splitsPr = 1;
-	size_t m_ldVr = 0, m_ldHtFull = 0, m_ldPr = 0, m_stridePr = 0;
-	DeviceBuffer<float> m_Vr, m_Hfull, m_HtHiFull, m_HtLoFull, m_PpartR, m_stat, m_Wblk, m_Wgath;
+	size_t m_ldVr = 0, m_ldHtFull = 0, m_ldPr = 0, m_stridePr = 0, m_statLen = 0;
+	DeviceBuffer<float> m_Vr, m_Hfull, m_HtHiFull, m_HtLoFull, m_PpartR, m_stat, m_statPart, m_statGath, m_Wblk, m_Wgath;
 	std::unique_ptr<TcPlan> m_tcR;
 };
 

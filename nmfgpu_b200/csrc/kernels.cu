@@ -555,6 +555,23 @@ __global__ void finish_stats_kernel(unsigned k, const float* __restrict__ stat, 
 	if (j == 0 && corrN != nullptr) corrN[i] = center * (stat[(size_t)k * k + i] / ni);
 }
 
+// stat[x] = sum over the ranks of gathered[g * stride + x], g ascending (what an all-reduce would deliver, in a fixed order)
+__global__ void sum_gathered_kernel(unsigned count, unsigned ranks, size_t stride, const float* __restrict__ gathered, float* __restrict__ stat) {
+	const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+	if (x >= count) return;
+	float s = 0.f;
+	for (unsigned g = 0; g < ranks; ++g) s += gathered[(size_t)g * stride + x];
+	stat[x] = s;
+}
+
+// B = H H^T and the centring term of V H^T from the summed statistics [H_g H_g^T (k x k), row sums of H_g (k)]
+__global__ void finish_stats_h_kernel(unsigned k, const float* __restrict__ stat, float center, float* __restrict__ B, float* __restrict__ corrP) {
+	const unsigned i = threadIdx.x, j = blockIdx.x;
+	if (i >= k) return;
+	B[(size_t)j * k + i] = stat[(size_t)j * k + i];
+	if (j == 0) corrP[i] = center * stat[(size_t)k * k + i];
+}
+
 // block[c * ldb + r] = W[r, c] / n_c for the rows of this rank (zero beyond `rows`)
 __global__ void scale_pack_kernel(unsigned rows, unsigned rowsPadded, unsigned k, const float* __restrict__ W, size_t ldw, const float* __restrict__ stat,
                                   float* __restrict__ block) {
@@ -563,21 +580,27 @@ __global__ void scale_pack_kernel(unsigned rows, unsigned rowsPadded, unsigned k
 	if (r >= rowsPadded) return;
 	float v = 0.f;
 	if (r < rows) {
-		const float s = stat[(size_t)c * k + c];
 		v = W[(size_t)c * ldw + r];
-		if (s > 0.f) v = v / sqrtf(s);
+		if (stat != nullptr) {   // nullptr: pack only, the unpack kernel scales
+			const float s = stat[(size_t)c * k + c];
+			if (s > 0.f) v = v / sqrtf(s);
+		}
 	}
 	block[(size_t)c * rowsPadded + r] = v;
 }
 
 // W, hi, lo (m x k, ld ldw) <- gathered[(g * k + c) * rowsPadded + r], global row = g * rowsPadded + r
 __global__ void unpack_split_kernel(unsigned m, unsigned k, unsigned rowsPadded, const float* __restrict__ gathered, float* __restrict__ W, size_t ldw,
-                                    float* __restrict__ hi, float* __restrict__ lo) {
+                                    float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ stat) {
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned c = blockIdx.y;
 	if (i >= m) return;
 	const unsigned g = i / rowsPadded, r = i - g * rowsPadded;
-	const float v = gathered[((size_t)g * k + c) * rowsPadded + r];
+	float v = gathered[((size_t)g * k + c) * rowsPadded + r];
+	if (stat != nullptr) {   // un-normalised blocks were gathered: unit columns here (KernelNormalizeColumns.cu:52-58)
+		const float s = stat[(size_t)c * k + c];
+		if (s > 0.f) v = v / sqrtf(s);
+	}
 	W[(size_t)c * ldw + i] = v;
 	const float h = tf32_hi(v);
 	hi[(size_t)c * ldw + i] = h;
@@ -1091,9 +1114,20 @@ void scalePackRows(unsigned rows, unsigned rowsPadded, unsigned k, const float* 
 	launchCheck();
 }
 
-void unpackSplit(unsigned m, unsigned k, unsigned rowsPadded, const float* gathered, float* W, size_t ldw, float* hi, float* lo, cudaStream_t stream) {
+void sumGathered(unsigned count, unsigned ranks, size_t stride, const float* gathered, float* stat, cudaStream_t stream) {
+	sum_gathered_kernel<<<ceilDiv(count, 256), 256, 0, stream>>>(count, ranks, stride, gathered, stat);
+	launchCheck();
+}
+
+void finishStatsH(unsigned k, const float* stat, float center, float* B, float* corrP, cudaStream_t stream) {
+	finish_stats_h_kernel<<<k, roundUp(k, 32), 0, stream>>>(k, stat, center, B, corrP);
+	launchCheck();
+}
+
+void unpackSplit(unsigned m, unsigned k, unsigned rowsPadded, const float* gathered, float* W, size_t ldw, float* hi, float* lo, cudaStream_t stream,
+                 const float* stat) {
 	dim3 grid(ceilDiv(m, 256), k);
-	unpack_split_kernel<<<grid, 256, 0, stream>>>(m, k, rowsPadded, gathered, W, ldw, hi, lo);
+	unpack_split_kernel<<<grid, 256, 0, stream>>>(m, k, rowsPadded, gathered, W, ldw, hi, lo, stat);
 	launchCheck();
 }
 

@@ -821,6 +821,13 @@ void columnSums(Plan& plan, const float* W, unsigned rows, size_t ldW, float* ou
 	CUDA_CHECK(cudaGetLastError());
 }
 
+void rowSums(Plan& plan, const float* H, unsigned cols, size_t ldH, float* out, cudaStream_t stream) {
+	const unsigned chunk = ceilDiv(cols, ROW_SUM_SLICES);
+	row_sums_stage1<<<ROW_SUM_SLICES, 256, 0, stream>>>(plan.k, cols, H, ldH, chunk, plan.sumScratch);
+	sums_stage2<<<ceilDiv(plan.k, 8), 256, 0, stream>>>(plan.k, ROW_SUM_SLICES, plan.sumScratch, 1.f, out);
+	CUDA_CHECK(cudaGetLastError());
+}
+
 void refreshCorrectionH(Plan& plan, const float* H, size_t ldH, cudaStream_t stream) {
 	const unsigned chunk = ceilDiv(plan.n, ROW_SUM_SLICES);
 	row_sums_stage1<<<ROW_SUM_SLICES, 256, 0, stream>>>(plan.k, plan.n, H, ldH, chunk, plan.sumScratch);

@@ -77,6 +77,8 @@ void refreshCorrectionW(Plan& plan, const float* W, size_t ldW, cudaStream_t str
 void refreshCorrectionH(Plan& plan, const float* H, size_t ldH, cudaStream_t stream);
 // out[c] = sum of the first `rows` entries of column c of W (fp64 accumulation), c < plan.k
 void columnSums(Plan& plan, const float* W, unsigned rows, size_t ldW, float* out, cudaStream_t stream);
+// out[r] = sum of the first `cols` entries of row r of H (k x cols), r < plan.k
+void rowSums(Plan& plan, const float* H, unsigned cols, size_t ldH, float* out, cudaStream_t stream);
 
 // Npart + slot*slotStride (k x n, leading dimension ldn) receives the partial products of W^T V
 void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream);

@@ -3,8 +3,9 @@
 Each rank holds a column shard of V (and, for the row-owner dataflow, the row block it would receive from the
 grouped send/recv at setup) and exchanges exactly what the engine exchanges:
   all-reduce  : the m x k partial V H^T and the k x k partial H H^T;
-  row owners  : all-gather of H, all-reduce of the k*k + k statistics of the un-normalised row block
-                (Gram matrix -- its diagonal gives the column norms -- and column sums), all-gather of W.
+  row owners  : all-gather of H together with the statistics of the local columns (H_g H_g^T), all-gather of the
+                un-normalised row blocks of W together with their k*k + k statistics (Gram matrix -- its diagonal gives
+                the column norms -- and column sums); every rank adds the gathered statistics up in rank order.
 Both must reproduce the single-process MU restatement (tests/np_restatement.py).
 """
 import os
@@ -66,16 +67,16 @@ def _worker(rank, world, port, mode, ret):
                 G = W.T @ W
             else:
                 Hfull = np.concatenate(_all_gather(H, world), axis=1)
-                B = Hfull @ Hfull.T
+                B = sum(_all_gather(H @ H.T, world))         # statistics of the local columns, added up in rank order
                 Wb = W[r0:r1] * (Vr @ Hfull.T) / (W[r0:r1] @ B + EPS)
-                stat = _all_reduce(np.concatenate([(Wb.T @ Wb).ravel(), Wb.sum(axis=0)]))
+                stat = sum(_all_gather(np.concatenate([(Wb.T @ Wb).ravel(), Wb.sum(axis=0)]), world))
                 gram = stat[:K * K].reshape(K, K)
                 d = np.diag(gram)
                 norm = np.where(d > 0, np.sqrt(d), 1.0)
                 G = gram / np.outer(norm, norm)
                 padded = np.zeros((block, K))
-                padded[:r1 - r0] = Wb / norm
-                W = np.concatenate(_all_gather(padded, world), axis=0)[:M]
+                padded[:r1 - r0] = Wb                       # the blocks travel un-normalised, the receiver scales
+                W = np.concatenate(_all_gather(padded, world), axis=0)[:M] / norm
                 colsum = stat[K * K:] / norm                # centring term of the next W^T V: column sums of the unit-column W
                 assert np.allclose(colsum, W.sum(axis=0), rtol=1e-12)
         Hall = np.concatenate(_all_gather(H, world), axis=1)
