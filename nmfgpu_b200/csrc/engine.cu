@@ -207,7 +207,7 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	m_splitsGH = kern::effectiveSplits(n, pickGramSplits(ceilDiv(k, 64) * ceilDiv(k, 64), n));
 	m_strideN = m_ldH * n;
 	m_strideP = m_ldW * k;
-	m_Npart.allocate(m_strideN * m_splitsN);
+	m_Npart.allocate(m_strideN * (m_splitsN + 1));   // +1: landing zone of the pre-reduced product (many partials per tile)
 	m_Ppart.allocate(m_strideP * (m_splitsP + 1));  // +1: slot for the summed / all-reduced product
 	m_kkScratch.allocate((size_t)k * k * std::max(m_splitsGW, m_splitsGH));
 	m_colSqPartials.allocate((size_t)ceilDiv(m, 128) * k);
@@ -375,8 +375,13 @@ void Engine<T>::iterateMURowOwners(bool err) {
 	stamp("begin");
 	productWtV(m_W[m_wCur].get());
 	stamp("product W^T V (own columns)");
-	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_eps,
-	                 err ? m_partN.get() : nullptr, nullptr, nullptr, m_ldHt, m_stream, m_slotsN, m_corrN, m_rowSumPartials.get());
+	const T* N = m_Npart.get();
+	unsigned splits = m_splitsN;
+	const unsigned char* slots = m_slotsN;
+	const T* corr = m_corrN;
+	preReduceN(N, splits, slots, corr);
+	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, N, m_ldH, splits, m_strideN, m_eps,
+	                 err ? m_partN.get() : nullptr, nullptr, nullptr, m_ldHt, m_stream, slots, corr, m_rowSumPartials.get());
 	m_launches += 1;
 	m_hCur = 1 - m_hCur;
 	stamp("update H");
@@ -392,15 +397,16 @@ void Engine<T>::iterateMURowOwners(bool err) {
 	tc::gemmVHt(m_tcR->plan, m_PpartR.get(), m_ldPr, m_stridePr, m_stream);
 	stamp("product V H^T (own rows)");
 	T* Wnext = m_W[1 - m_wCur].get();
-	kern::updateW<T>(m_mr, k, m_B.get(), m_W[m_wCur].get() + m_r0, Wnext + m_r0, m_ldW, reinterpret_cast<const T*>(m_PpartR.get()), m_ldPr, m_splitsPr,
-	                 m_stridePr, m_eps, m_colSqPartials.get(), m_stream, m_tcR->plan.vht.slotCount, reinterpret_cast<const T*>(m_tcR->plan.corrP));
+	const unsigned wBlocks = kern::updateW<T>(m_mr, k, m_B.get(), m_W[m_wCur].get() + m_r0, Wnext + m_r0, m_ldW, reinterpret_cast<const T*>(m_PpartR.get()),
+	                                          m_ldPr, m_splitsPr, m_stridePr, m_eps, m_colSqPartials.get(), m_stream, m_tcR->plan.vht.slotCount,
+	                                          reinterpret_cast<const T*>(m_tcR->plan.corrP), m_colSumPartials.get());
 	// statistics of the un-normalised block: Gram matrix (its diagonal = the column sums of squares) and column sums.
 	// They travel with the all-gather of the (still un-normalised) blocks in one NCCL group; every rank adds them up in
 	// rank order and the unpack kernel divides by the norms.
 	float* part = m_statPart.get();
 	kern::gemmTN<T>(m_mr, k, k, Wnext + m_r0, m_ldW, Wnext + m_r0, m_ldW, m_kkScratch.get(), k, m_splitsGWrows, (size_t)k * k, m_stream);
 	kern::sumSplits<T>(k, k, m_kkScratch.get(), k, m_splitsGWrows, (size_t)k * k, reinterpret_cast<T*>(part), k, m_stream);
-	tc::columnSums(m_tc->plan, reinterpret_cast<const float*>(Wnext) + m_r0, m_mr, m_ldW, part + (size_t)k * k, m_stream);
+	kern::finishPartialSums(k, wBlocks, reinterpret_cast<const float*>(m_colSumPartials.get()), 1.f, part + (size_t)k * k, m_stream);
 	kern::scalePackRows(m_mr, m_mrPad, k, reinterpret_cast<const float*>(Wnext) + m_r0, m_ldW, nullptr, m_Wblk.get(), m_stream);
 	stamp("update W rows, statistics, pack");
 	comm->allGatherPair(m_Wblk.get(), m_Wgath.get(), (size_t)m_mrPad * k, part, m_statGath.get(), m_statLen, m_stream);
@@ -637,6 +643,21 @@ void Engine<T>::multiplicativeW(const T* B) {
 	normaliseW(blocks, true);
 }
 
+// A tile of W^T V may receive many partial products (4 reduction chunks x 5 CTAs on one GPU, 30 CTAs per tile on an
+// 8-GPU shard).  The update kernel has only n/64 blocks and would walk them one memory latency after the other (68 us
+// measured at 8 GPUs, 50 us at one); one thread per element adds them up first.
+template <typename T>
+void Engine<T>::preReduceN(const T*& N, unsigned& splits, const unsigned char*& slots, const T*& corr) {
+	if (m_splitsN <= 24) return;   // up to ~20 partials the update kernel walks them faster than a separate pass (50 vs 58 us at one GPU)
+	T* sum = m_Npart.get() + m_strideN * m_splitsN;
+	kern::sumSplits<T>(m_cfg.k, m_cfg.n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, sum, m_ldH, m_stream, m_slotsN, false, m_corrN);
+	m_launches += 1;
+	N = sum;
+	splits = 1;
+	slots = nullptr;
+	corr = nullptr;
+}
+
 // ---- MU -------------------------------------------------------------------------------------------------
 template <typename T>
 void Engine<T>::iterateMU(bool err) {
@@ -649,8 +670,13 @@ void Engine<T>::iterateMU(bool err) {
 	stamp("gram W^T W");
 	productWtV(m_W[m_wCur].get());                                                          // N = W^T V      MU.h:187
 	stamp("product W^T V");
-	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_eps,
-	                 err ? m_partN.get() : nullptr, htHi, htLo, m_ldHt, m_stream, m_slotsN, m_corrN,
+	const T* N = m_Npart.get();
+	unsigned splits = m_splitsN;
+	const unsigned char* slots = m_slotsN;
+	const T* corr = m_corrN;
+	preReduceN(N, splits, slots, corr);
+	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, N, m_ldH, splits, m_strideN, m_eps,
+	                 err ? m_partN.get() : nullptr, htHi, htLo, m_ldHt, m_stream, slots, corr,
 	                 m_useTC ? m_rowSumPartials.get() : nullptr);                           // H update  MU.h:181-197
 	m_launches += 1;
 	m_hCur = 1 - m_hCur;

@@ -108,6 +108,7 @@ private:
 	void productWtV(const T* W);                               // m_Npart / m_splitsN <- W^T V
 	void productVHt(const T* H, size_t ldh);                   // m_Ppart / m_splitsP <- V H^T (all-reduced)
 	void normaliseW(unsigned blocks, bool haveColumnSums = false);
+	void preReduceN(const T*& N, unsigned& splits, const unsigned char*& slots, const T*& corr);   // many partials of W^T V -> one
 	void operandChangedW(const T* W);                          // refresh what the tensor-core products derive from W resp. H
 	void operandChangedH(const T* H);
 	void multiplicativeW(const T* B);                          // W <- W o P / (W B + eps), normalise
