@@ -8,19 +8,21 @@
 // Two A tiles share every B tile: B comes out of L2, and its traffic and its latency -- not HBM -- bound
 // the one-tile version of this kernel (profiles/r01_notes.md).
 //
-// Kernel anatomy (one persistent CTA per SM, 384 threads, stream-K work split, see tc_gemm.h):
-//   warp 0      TMA producer of the V tiles (16 KB each, two per stage, EVICT_FIRST: V is streamed once per product)
+// Kernel anatomy (one persistent CTA per SM, 640 threads, stream-K work split in reduction chunks, see tc_gemm.h):
+//   warp 0      TMA producer of the V tiles (16 KB each, two per stage, one lane and one ring per A tile; EVICT_FIRST: V
+//               is streamed once per product)
 //   warp 2      TMEM allocation, then TMA producer of the B tiles (hi and lo, kp x 32 each, EVICT_LAST)
 //   warps 1, 3  MMA issuers, one per A tile: 4 k-steps x {A_hi B_hi, A_lo B_hi, A_hi B_lo}, tcgen05.mma kind::tf32 with
 //               A in TENSOR MEMORY and B in shared memory (128B swizzle); accumulators in TMEM
-//   warps 4-7, 8-11   two worker warpgroups, one per A tile: read the fp32 V tile from shared memory (each
-//               thread owns one A row = one TMEM lane), split every value into TF32 hi/lo in registers and
+//   warps 4-11  two splitter warpgroups, one per A tile: read the fp32 V tile from shared memory (each thread owns one
+//               A row = one TMEM lane), subtract the centre, split every value into TF32 hi/lo in registers and
 //               tcgen05.st both halves into an A slot of TMEM.  V is never written back anywhere.
-// The tensor core accumulates only `flushStages` stages at a time; each warpgroup then tcgen05.ld's its
-// tile's accumulator and adds it to fp32 running sums in registers with round-to-nearest (double-buffered
-// accumulators for kp <= 64, so the flush overlaps the next chunk's MMAs).  The tensor core truncates its
-// fp32 accumulator after every MMA (measured: bias of -2.4e-7 per accumulated stage), so a 100 000-term
-// reduction kept in TMEM would be off by 4e-4; chunked it stays at fp32 level.
+//   warps 12-19 two flusher warpgroups, one per A tile: own the fp32 running sums and write the partial products.
+// The tensor core accumulates only `flushStages` stages at a time; the flushers then tcgen05.ld the tile's accumulator
+// and add it to the running sums in registers with round-to-nearest (double-buffered accumulators for kp <= 64, so the
+// flush overlaps the next chunk's MMAs).  The tensor core truncates its fp32 accumulator after every MMA (measured: bias
+// of -2.4e-7 per accumulated stage), so a 100 000-term reduction kept in TMEM would be off by 4e-4; chunked and centred
+// it stays at fp32 level (tc_gemm.h).
 #include "tc_gemm.h"
 
 #include <cuda.h>
@@ -51,7 +53,6 @@ constexpr int SLOTS_SHIFT = 2;
 constexpr int SVH = 5;                // shared-memory ring of V tiles (16 KB each): SVH slots per A tile (= per splitter warpgroup)
 constexpr int SV = 2 * SVH;
 constexpr int A_BASE_COL = 256;       // TMEM columns [0, 256): accumulators, [256, 512): A slots
-constexpr int NUM_THREADS = 640;      // 4 helper warps + 16 warps of splitters and flushers
 constexpr uint64_t POLICY_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t POLICY_EVICT_LAST = 0x14F0000000000000ull;
 
