@@ -133,6 +133,18 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 		m_Pt.allocate(m_ldH * m);
 		m_Wt.zero(m_stream);
 		m_Pt.zero(m_stream);
+		// Blocked sweep of W^T V (spmm.h), a study knob: measured at configs[4] (W copy 512 MB, 13 blocks of 40 MB) it
+		// changes nothing, 13.1 vs 13.0 ms per iteration -- the gathers run at the L2-to-SM request rate whether the rows
+		// come from L2 or from HBM (profiles/r01_notes.md 15) -- so the default is the single sweep.
+		unsigned blocks = 1;
+		if (const char* e = getenv("NMFGPU_SPARSE_BLOCKS")) blocks = std::max(1, std::min(64, atoi(e)));
+		m_sparseBlocks = blocks;
+		if (blocks > 1) {
+			m_sparseBlockRows = (unsigned)roundUp(ceilDiv(m, blocks), 32);
+			m_sparseBlocks = ceilDiv(m, m_sparseBlockRows);
+			m_blockPtr.allocate((size_t)(m_sparseBlocks + 1) * n);
+			sparse::buildBlockPointers(n, m_sparseBlocks, m_sparseBlockRows, m_S.colPtr.get(), m_S.rowIdx.get(), m_blockPtr.get(), m_stream);
+		}
 	} else if (vOnDevice) {
 		if (V.format != StorageFormat::Dense) throw EngineError(ResultType::ErrorInvalidArgument, "device-resident V must be dense");
 		m_ldV = V.dense.leadingDimension;
@@ -197,7 +209,8 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 		m_slotsN = m_tc->plan.wtv.slotCount;
 		m_slotsP = m_tc->plan.vht.slotCount;
 	} else if (m_sparse) {
-		m_splitsN = m_splitsP = 1;   // a gather product is complete when it is written
+		m_splitsN = m_sparseBlocks;  // one partial product per row block of the sweep (1: complete when written)
+		m_splitsP = 1;
 	} else {
 		m_splitsN = kern::effectiveSplits(m, pickSplits(ceilDiv(k, 64) * ceilDiv(n, 64), m));
 		m_splitsP = kern::effectiveSplits(n, pickSplits(ceilDiv(m, 64) * ceilDiv(k, 64), n));
@@ -510,7 +523,7 @@ void Engine<T>::hFromWtV(bool absolute) {
 	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
 	if (m_sparse) {
 		productWtV(m_W[m_wCur].get());
-		kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, 1, m_strideN, m_H[m_hCur].get(), m_ldH, m_stream);
+		kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, m_H[m_hCur].get(), m_ldH, m_stream);
 		if (absolute) kern::absInPlace<T>(k, n, m_H[m_hCur].get(), m_ldH, m_stream);
 		else kern::clampNonNegative<T>(k, n, m_H[m_hCur].get(), m_ldH, m_stream);
 		return;
@@ -578,8 +591,14 @@ template <typename T>
 void Engine<T>::productWtV(const T* W) {
 	if (m_sparse) {   // N[:, j] = sum over the entries of column j of v * W[i, :]: gathers rows of the row-major copy of W
 		sparse::transpose<T>(m_cfg.m, m_cfg.k, W, m_ldW, m_Wt.get(), m_ldH, m_stream);
-		sparse::spmmGather<T>(m_cfg.n, m_cfg.k, m_S.colPtr.get(), m_S.rowIdx.get(), m_S.cscVal.get(), m_Wt.get(), m_ldH, m_Npart.get(), m_ldH, m_stream);
-		m_launches += 1;
+		if (m_sparseBlocks <= 1) {
+			sparse::spmmGather<T>(m_cfg.n, m_cfg.k, m_S.colPtr.get(), m_S.rowIdx.get(), m_S.cscVal.get(), m_Wt.get(), m_ldH, m_Npart.get(), m_ldH, m_stream);
+		} else {
+			for (unsigned b = 0; b < m_sparseBlocks; ++b)
+				sparse::spmmGather<T>(m_cfg.n, m_cfg.k, m_blockPtr.get() + (size_t)b * m_cfg.n, m_blockPtr.get() + (size_t)(b + 1) * m_cfg.n, m_S.rowIdx.get(),
+				                      m_S.cscVal.get(), m_Wt.get(), m_ldH, m_Npart.get() + m_strideN * b, m_ldH, m_stream);
+		}
+		m_launches += m_sparseBlocks;
 	} else if (m_useTC) {
 		static const bool poison = getenv("NMFGPU_TC_POISON") != nullptr;   // debugging: an unwritten slot shows up as NaN
 		if (poison) CUDA_CHECK(cudaMemsetAsync(m_Npart.get(), 0xFF, m_Npart.bytes(), m_stream));

@@ -157,6 +157,8 @@ private:
 	bool m_sparse = false;
 	sparse::DeviceSparse<T> m_S;
 	DeviceBuffer<T> m_Wt, m_Pt;   // row-major W (the gather operand of W^T V) and row-major V H^T, leading dimension m_ldH
+	DeviceBuffer<int> m_blockPtr; // blocked sweep of W^T V (spmm.h): (m_sparseBlocks + 1) x n entry positions
+	unsigned m_sparseBlocks = 1, m_sparseBlockRows = 0;
 	void decideSparse(const MatrixDescription<T>& V, bool vOnDevice);
 
 	// row-owner dataflow (dist.h): this rank also holds V[I, :] for its row block I = [m_r0, m_r0 + m_mr) and updates

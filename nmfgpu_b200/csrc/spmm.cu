@@ -88,13 +88,13 @@ void sortPositions(unsigned nnz, const unsigned* keys, unsigned keyCount, unsign
 // shuffle; lane l accumulates the output entries l, l + 32, ... (KQ of them), so every gather of an operand row is
 // KQ coalesced 128-byte requests.  Four entries are in flight per step to cover the L2 / HBM latency of the gathers.
 template <typename T, int KQ>
-__global__ void __launch_bounds__(256) spmm_gather_kernel(unsigned numMajor, unsigned k, const int* __restrict__ ptr, const int* __restrict__ idx,
-                                                          const T* __restrict__ val, const T* __restrict__ D, size_t ldd, T* __restrict__ out,
-                                                          size_t ldo) {
+__global__ void __launch_bounds__(256) spmm_gather_kernel(unsigned numMajor, unsigned k, const int* __restrict__ ptrBegin,
+                                                          const int* __restrict__ ptrEnd, const int* __restrict__ idx, const T* __restrict__ val,
+                                                          const T* __restrict__ D, size_t ldd, T* __restrict__ out, size_t ldo) {
 	const unsigned r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
 	const unsigned lane = threadIdx.x % 32;
 	if (r >= numMajor) return;
-	const int begin = ptr[r], end = ptr[r + 1];
+	const int begin = ptrBegin[r], end = ptrEnd[r];
 	T acc[KQ];
 #pragma unroll
 	for (int q = 0; q < KQ; ++q) acc[q] = T(0);
@@ -131,6 +131,27 @@ __global__ void __launch_bounds__(256) spmm_gather_kernel(unsigned numMajor, uns
 #pragma unroll
 	for (int q = 0; q < KQ; ++q)
 		if (lane + 32 * q < k) out[(size_t)r * ldo + lane + 32 * q] = acc[q];
+}
+
+// blockPtr[b * numMajor + j] = first entry of compressed column j whose (ascending) minor index is >= b * minorPerBlock;
+// row `blocks` holds the end of the column
+__global__ void block_pointers_kernel(unsigned numMajor, unsigned blocks, unsigned minorPerBlock, const int* __restrict__ ptr,
+                                      const int* __restrict__ idx, int* __restrict__ blockPtr) {
+	const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned b = blockIdx.y;
+	if (j >= numMajor) return;
+	int lo = ptr[j], hi = ptr[j + 1];
+	if (b >= blocks) {
+		blockPtr[(size_t)b * numMajor + j] = hi;
+		return;
+	}
+	const long long bound = (long long)b * minorPerBlock;
+	while (lo < hi) {
+		const int mid = lo + (hi - lo) / 2;
+		if ((long long)idx[mid] < bound) lo = mid + 1;
+		else hi = mid;
+	}
+	blockPtr[(size_t)b * numMajor + j] = lo;
 }
 
 template <typename T>
@@ -237,17 +258,30 @@ void ingest(const MatrixDescription<T>& src, DeviceSparse<T>& dst, cudaStream_t 
 }
 
 template <typename T>
-void spmmGather(unsigned numMajor, unsigned k, const int* ptr, const int* idx, const T* val, const T* D, size_t ldd, T* out, size_t ldo,
-                cudaStream_t stream) {
+void spmmGather(unsigned numMajor, unsigned k, const int* ptrBegin, const int* ptrEnd, const int* idx, const T* val, const T* D, size_t ldd, T* out,
+                size_t ldo, cudaStream_t stream) {
 	if (numMajor == 0) return;
 	if (k > 128) throw EngineError(ResultType::ErrorInvalidArgument, "sparse products support at most 128 features");
 	const unsigned grid = ceilDiv(numMajor, 8);
 	switch (ceilDiv(k, 32)) {
-	case 1: spmm_gather_kernel<T, 1><<<grid, 256, 0, stream>>>(numMajor, k, ptr, idx, val, D, ldd, out, ldo); break;
-	case 2: spmm_gather_kernel<T, 2><<<grid, 256, 0, stream>>>(numMajor, k, ptr, idx, val, D, ldd, out, ldo); break;
-	case 3: spmm_gather_kernel<T, 3><<<grid, 256, 0, stream>>>(numMajor, k, ptr, idx, val, D, ldd, out, ldo); break;
-	default: spmm_gather_kernel<T, 4><<<grid, 256, 0, stream>>>(numMajor, k, ptr, idx, val, D, ldd, out, ldo); break;
+	case 1: spmm_gather_kernel<T, 1><<<grid, 256, 0, stream>>>(numMajor, k, ptrBegin, ptrEnd, idx, val, D, ldd, out, ldo); break;
+	case 2: spmm_gather_kernel<T, 2><<<grid, 256, 0, stream>>>(numMajor, k, ptrBegin, ptrEnd, idx, val, D, ldd, out, ldo); break;
+	case 3: spmm_gather_kernel<T, 3><<<grid, 256, 0, stream>>>(numMajor, k, ptrBegin, ptrEnd, idx, val, D, ldd, out, ldo); break;
+	default: spmm_gather_kernel<T, 4><<<grid, 256, 0, stream>>>(numMajor, k, ptrBegin, ptrEnd, idx, val, D, ldd, out, ldo); break;
 	}
+	CUDA_CHECK(cudaGetLastError());
+}
+
+template <typename T>
+void spmmGather(unsigned numMajor, unsigned k, const int* ptr, const int* idx, const T* val, const T* D, size_t ldd, T* out, size_t ldo,
+                cudaStream_t stream) {
+	spmmGather<T>(numMajor, k, ptr, ptr + 1, idx, val, D, ldd, out, ldo, stream);
+}
+
+void buildBlockPointers(unsigned numMajor, unsigned blocks, unsigned minorPerBlock, const int* ptr, const int* idx, int* blockPtr, cudaStream_t stream) {
+	if (numMajor == 0) return;
+	const dim3 grid(ceilDiv(numMajor, 256), blocks + 1);
+	block_pointers_kernel<<<grid, 256, 0, stream>>>(numMajor, blocks, minorPerBlock, ptr, idx, blockPtr);
 	CUDA_CHECK(cudaGetLastError());
 }
 
@@ -269,6 +303,7 @@ void majorSquares(unsigned numMajor, const int* ptr, const T* val, T* out, cudaS
 #define NMF_INSTANTIATE(T)                                                                                                                    \
 	template void ingest<T>(const MatrixDescription<T>&, DeviceSparse<T>&, cudaStream_t);                                                     \
 	template void spmmGather<T>(unsigned, unsigned, const int*, const int*, const T*, const T*, size_t, T*, size_t, cudaStream_t);           \
+	template void spmmGather<T>(unsigned, unsigned, const int*, const int*, const int*, const T*, const T*, size_t, T*, size_t, cudaStream_t); \
 	template void transpose<T>(unsigned, unsigned, const T*, size_t, T*, size_t, cudaStream_t);                                               \
 	template void majorSquares<T>(unsigned, const int*, const T*, T*, cudaStream_t);
 NMF_INSTANTIATE(float)

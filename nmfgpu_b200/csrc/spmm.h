@@ -38,6 +38,17 @@ template <typename T>
 void spmmGather(unsigned numMajor, unsigned k, const int* ptr, const int* idx, const T* val, const T* D, size_t ldd, T* out, size_t ldo,
                 cudaStream_t stream);
 
+// the same over the entry ranges [ptrBegin[r], ptrEnd[r]): one block of a blocked sweep (buildBlockPointers)
+template <typename T>
+void spmmGather(unsigned numMajor, unsigned k, const int* ptrBegin, const int* ptrEnd, const int* idx, const T* val, const T* D, size_t ldd, T* out,
+                size_t ldo, cudaStream_t stream);
+
+// Blocked sweep (study knob NMFGPU_SPARSE_BLOCKS; measured: no gain, see engine.cu): W^T V block of rows by block of rows --
+// one launch per block over all columns, restricted to the entries whose row lies in the block (they are contiguous: rows
+// ascend inside a CSC column) -- so that the rows being gathered stay in L2; every block yields one partial product.  blockPtr is (blocks + 1) x numMajor: the first entry of column j at
+// or after row b * minorPerBlock, the last row holding the column ends.
+void buildBlockPointers(unsigned numMajor, unsigned blocks, unsigned minorPerBlock, const int* ptr, const int* idx, int* blockPtr, cudaStream_t stream);
+
 // B[r * ldb + c] = A[c * lda + r] for r < rows, c < cols  (column-major -> row-major, or the other way round with the roles swapped)
 template <typename T>
 void transpose(unsigned rows, unsigned cols, const T* A, size_t lda, T* B, size_t ldb, cudaStream_t stream);

@@ -323,6 +323,29 @@ def test_sparse_execution_matches_dense_and_oracle(L, monkeypatch, fmt, base, al
     assert rel(out["1"]["W"], out["0"]["W"]) <= tol and rel(out["1"]["H"], out["0"]["H"]) <= tol
 
 
+@pytest.mark.parametrize("fmt,algo,k", [("csr", "mu", 40), ("coo", "gdcls", 16)])
+def test_sparse_blocked_sweep(L, monkeypatch, fmt, algo, k):
+    """W^T V as a blocked sweep over row blocks of W (csrc/spmm.h: keeps the gathered rows in L2 on large problems; forced here
+    with NMFGPU_SPARSE_BLOCKS) against the single sweep and the oracle"""
+    rng = np.random.default_rng(9)
+    m, n = 900, 380
+    D = ((rng.random((m, n)) < 0.04) * (0.1 + rng.random((m, n)))).astype(np.float32)
+    _, W0, H0 = planted_inputs(m, n, k, seed=2)
+    desc, keep = _sparse_desc(D, fmt, 0)
+    monkeypatch.setenv("NMFGPU_SPARSE", "1")
+    out = {}
+    for blocks in ("1", "7"):
+        monkeypatch.setenv("NMFGPU_SPARSE_BLOCKS", blocks)
+        out[blocks] = L.compute(None, k, algorithm=algo, W0=W0, H0=H0, iterations=20, params=SPARSE_PARAMS[algo],
+                                sparse=(desc, np.dtype(np.float32)))
+        assert out[blocks]["rc"] == ResultType.Success
+    o = orc.run_nmf(algo, D, W0, H0, 20, params=SPARSE_PARAMS[algo])
+    for r in out.values():
+        assert abs(r["frobenius"] - o["frob"][-1]) / o["frob"][-1] <= 2e-5
+        assert rel(r["W"], o["W"]) <= 2e-4 and rel(r["H"], o["H"]) <= 2e-4
+    assert rel(out["7"]["W"], out["1"]["W"]) <= 2e-4
+
+
 def test_sparse_execution_double_and_auto_policy(L, monkeypatch):
     """fp64 entry point on the compressed path; without NMFGPU_SPARSE a 1 % dense input runs compressed, a 10 % one densified
     (both must agree with the oracle either way)"""

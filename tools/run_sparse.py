@@ -24,6 +24,7 @@ ap.add_argument("--n", type=int, default=100000)
 ap.add_argument("--density", type=float, default=1e-3)
 ap.add_argument("--k", type=int, default=100)
 ap.add_argument("--iters", type=int, default=30)
+ap.add_argument("--blocks", default="", help="comma separated NMFGPU_SPARSE_BLOCKS settings to compare (default: the library's choice)")
 ap.add_argument("--check", action="store_true", help="explicit ||V - W H||_F over the stored entries and the W H mass (host, slow)")
 a = ap.parse_args()
 
@@ -48,13 +49,17 @@ assert L.initialize() == 0
 desc = api.sparse_description(api.StorageFormat.CSR, a.m, a.n, vals, indptr, cols, 0)
 W0 = uniform_block(43, a.m, a.k)
 H0 = uniform_block(44, a.k, a.n)
-for iters in (10, a.iters):      # the first call also pays context and kernel loading
+runs = [(None, 10)] + [(b or None, a.iters) for b in (a.blocks.split(",") if a.blocks else [""])]   # the first call also pays context and kernel loading
+for blocks, iters in runs:
+    if blocks is not None:
+        os.environ["NMFGPU_SPARSE_BLOCKS"] = blocks
     t0 = time.time()
     r = L.compute(None, a.k, W0=W0, H0=H0, iterations=iters, sparse=(desc, np.dtype(np.float32)))
     wall = time.time() - t0
     assert r["rc"] == 0, r
-    print("%d iterations: library time %.3f s = %.2f iterations/s (%.3f ms each), wall %.2f s, frobenius %.6g"
-          % (iters, r["elapsed"], iters / max(r["elapsed"], 1e-3), 1000.0 * r["elapsed"] / iters, wall, r["frobenius"]), flush=True)
+    print("%d iterations%s: library time %.3f s = %.2f iterations/s (%.3f ms each), wall %.2f s, frobenius %.6g"
+          % (iters, " (row blocks %s)" % blocks if blocks else "", r["elapsed"], iters / max(r["elapsed"], 1e-3), 1000.0 * r["elapsed"] / iters, wall,
+             r["frobenius"]), flush=True)
 flops = 4.0 * nnz * a.k + 4.0 * a.k * a.k * (a.m + a.n)
 print("algorithmic work per iteration: %.3g FLOP, %.3g bytes" % (flops, 2 * (8.0 * nnz + 4.0 * (a.m + 1)) + 16.0 * a.k * (a.m + a.n)))
 if a.check:
