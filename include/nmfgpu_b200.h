@@ -69,6 +69,13 @@ int nmfgpu_b200_session_synchronize(nmfgpu_b200_session* s);
 int nmfgpu_b200_session_get_info(nmfgpu_b200_session* s, nmfgpu_b200_session_info* info);
 void nmfgpu_b200_session_destroy(nmfgpu_b200_session* s);
 
+/* ---- diagnostics: the stream-K work split of one tensor-core product (csrc/tc_gemm.h) for `sms` CTAs, computed on the host
+ * (no device needed).  A rows = rows_a, reduction length = reduce_len, kp = rank padded to 16.  Writes up to `capacity`
+ * segments {cta, 256-row tile, first stage, stages, slot} (5 words each) in execution order and returns their number;
+ * info5 = {tiles, stages per tile, chunks, stages per chunk, grid}; slots_per_tile[t] = partial products of 128-wide tile t. */
+unsigned nmfgpu_b200_plan_segments(unsigned rows_a, unsigned reduce_len, unsigned kp, unsigned sms, unsigned* segments,
+                                   unsigned capacity, unsigned* info5, unsigned char* slots_per_tile, unsigned tile_capacity);
+
 /* ---- device helpers for synthetic workloads (bench.py): no H2D of the 4 GB input */
 void* nmfgpu_b200_device_alloc(size_t bytes);
 void nmfgpu_b200_device_free(void* p);

@@ -148,7 +148,7 @@ EXT_SYMBOLS = ["nmfgpu_b200_set_precision", "nmfgpu_b200_dist_unique_id", "nmfgp
                "nmfgpu_b200_session_synchronize", "nmfgpu_b200_session_get_info", "nmfgpu_b200_session_destroy",
                "nmfgpu_b200_device_alloc", "nmfgpu_b200_device_free", "nmfgpu_b200_device_uniform_f32",
                "nmfgpu_b200_flush_l2", "nmfgpu_b200_device_download", "nmfgpu_b200_device_upload", "nmfgpu_b200_host_alloc",
-               "nmfgpu_b200_host_free"]
+               "nmfgpu_b200_host_free", "nmfgpu_b200_plan_segments"]
 
 
 class SummaryHandle:

@@ -8,6 +8,7 @@
 
 #include "host.h"
 #include "kernels.h"
+#include "tc_gemm.h"
 
 using namespace nmfgpu;
 using namespace nmfgpu::b200;
@@ -204,6 +205,17 @@ NMFGPU_EXPORT int nmfgpu_b200_session_time_iterations(nmfgpu_b200_session* s, un
 NMFGPU_EXPORT int nmfgpu_b200_session_products_f32(nmfgpu_b200_session* s, float* wtv, float* vht, float* ms_wtv, float* ms_vht) {
 	if (s == nullptr) return static_cast<int>(ResultType::ErrorInvalidArgument);
 	return guarded([&] { s->engine->debugProducts(wtv, vht, ms_wtv, ms_vht, s->start, s->stop); });
+}
+
+NMFGPU_EXPORT unsigned nmfgpu_b200_plan_segments(unsigned rows_a, unsigned reduce_len, unsigned kp, unsigned sms, unsigned* segments, unsigned capacity,
+                                                 unsigned* info5, unsigned char* slots_per_tile, unsigned tile_capacity) {
+	if (rows_a == 0 || reduce_len == 0 || kp == 0 || sms == 0 || info5 == nullptr || (capacity != 0 && segments == nullptr)) return 0;
+	try {
+		return tc::enumerateSegments(rows_a, reduce_len, kp, sms, segments, capacity, info5, slots_per_tile, slots_per_tile ? tile_capacity : 0);
+	} catch (const std::exception& e) {   // e.g. more than 255 partial products per tile under a forced chunk count
+		errorf("[ERROR] %s\n", e.what());
+		return 0;
+	}
 }
 
 NMFGPU_EXPORT int nmfgpu_b200_session_synchronize(nmfgpu_b200_session* s) {

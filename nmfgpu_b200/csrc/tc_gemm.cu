@@ -113,10 +113,12 @@ struct Segment {
 struct SegmentWalker {
 	unsigned long long u, uBegin, uEnd, units;
 	unsigned stagesPerTile, chunkStages, chunks, chunk, grid, cta;
-	__device__ SegmentWalker(const KParams& p, unsigned ctaIdx)
-	    : u(unitStart(ctaIdx, p.grid, p.units)), uBegin(u), uEnd(unitStart(ctaIdx + 1, p.grid, p.units)), units(p.units),
-	      stagesPerTile(p.stagesPerTile), chunkStages(p.chunkStages), chunks(p.chunks), chunk(0), grid(p.grid), cta(ctaIdx) {}
-	__device__ bool next(Segment& s) {
+	__host__ __device__ SegmentWalker(unsigned long long unitsPerChunk, unsigned gridSize, unsigned stagesPerTile_, unsigned chunkStages_, unsigned chunks_,
+	                                  unsigned ctaIdx)
+	    : u(unitStart(ctaIdx, gridSize, unitsPerChunk)), uBegin(u), uEnd(unitStart(ctaIdx + 1, gridSize, unitsPerChunk)), units(unitsPerChunk),
+	      stagesPerTile(stagesPerTile_), chunkStages(chunkStages_), chunks(chunks_), chunk(0), grid(gridSize), cta(ctaIdx) {}
+	__device__ SegmentWalker(const KParams& p, unsigned ctaIdx) : SegmentWalker(p.units, p.grid, p.stagesPerTile, p.chunkStages, p.chunks, ctaIdx) {}
+	__host__ __device__ bool next(Segment& s) {
 		if (u >= uEnd) {
 			if (++chunk >= chunks || uBegin >= uEnd) return false;
 			u = uBegin;
@@ -710,7 +712,8 @@ int smCount() {
 	return sms;
 }
 
-void planProduct(Product& prod, unsigned rowsA, unsigned kdim, unsigned kp) {
+// the shape-only part of a product's plan (no CUDA calls): tiles, chunks, grid and the partial products per 128-wide tile
+void planShape(Product& prod, unsigned rowsA, unsigned kdim, unsigned kp, unsigned sms, std::vector<unsigned char>& counts) {
 	prod.tiles = ceilDiv(rowsA, PAIR_ROWS);
 	prod.stagesPerTile = ceilDiv(kdim, STAGE_K);
 	// reduction chunks: the hi/lo copies of the small operand that one chunk reads should sit in L2 (~12 MB) while all CTAs
@@ -720,16 +723,16 @@ void planProduct(Product& prod, unsigned rowsA, unsigned kdim, unsigned kp) {
 	chunks = std::max(1u, std::min(chunks, prod.stagesPerTile / 64));
 	// every chunk multiplies the partial products a tile receives (one per CTA that shares the tile), and the consumers
 	// walk them one after the other: no more than ~24 per tile (8 GPUs: 5 tiles on 148 CTAs are 30 per chunk already)
-	const unsigned perTile = ceilDiv((unsigned)smCount(), prod.tiles) + 1;
+	const unsigned perTile = ceilDiv(sms, prod.tiles) + 1;
 	chunks = std::max(1u, std::min(chunks, 24u / perTile));
 	if (const char* e = getenv("NMFGPU_TC_CHUNKS")) chunks = std::max(1u, std::min((unsigned)atoi(e), prod.stagesPerTile));   // tuning knob
 	prod.chunkStages = ceilDiv(prod.stagesPerTile, chunks);
 	prod.chunks = ceilDiv(prod.stagesPerTile, prod.chunkStages);
 	const unsigned long long units = (unsigned long long)prod.tiles * prod.chunkStages;   // per chunk
-	prod.grid = (unsigned)std::min<unsigned long long>(units, (unsigned long long)smCount());
+	prod.grid = (unsigned)std::min<unsigned long long>(units, (unsigned long long)sms);
 	// consumers index the counts by 128-wide tile (kernels.h), the stream-K tiles are 256 wide
 	const unsigned tiles128 = ceilDiv(rowsA, TILE_ROWS);
-	std::vector<unsigned char> counts(tiles128);
+	counts.assign(tiles128, 0);
 	prod.maxSlots = 1;
 	for (unsigned t = 0; t < prod.tiles; ++t) {
 		const unsigned long long f = (unsigned long long)t * prod.chunkStages;
@@ -739,6 +742,12 @@ void planProduct(Product& prod, unsigned rowsA, unsigned kdim, unsigned kp) {
 			if (2 * t + h < tiles128) counts[2 * t + h] = (unsigned char)slots;
 		prod.maxSlots = std::max(prod.maxSlots, slots);
 	}
+}
+
+void planProduct(Product& prod, unsigned rowsA, unsigned kdim, unsigned kp) {
+	std::vector<unsigned char> counts;
+	planShape(prod, rowsA, kdim, kp, (unsigned)smCount(), counts);
+	const unsigned tiles128 = ceilDiv(rowsA, TILE_ROWS);
 	if (prod.slotCount) pooledDeviceFree(prod.slotCount, prod.slotCountBytes);
 	prod.slotCountBytes = roundUp(tiles128, 256);
 	prod.slotCount = static_cast<unsigned char*>(pooledDeviceAlloc(prod.slotCountBytes));
@@ -792,6 +801,33 @@ void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, s
 }
 
 }  // namespace
+
+unsigned enumerateSegments(unsigned rowsA, unsigned kdim, unsigned kp, unsigned sms, unsigned* segments, unsigned capacity, unsigned info[5],
+                           unsigned char* slotsPerTile, unsigned tileCapacity) {
+	Product prod;
+	std::vector<unsigned char> counts;
+	planShape(prod, rowsA, kdim, kp, sms, counts);
+	info[0] = prod.tiles;
+	info[1] = prod.stagesPerTile;
+	info[2] = prod.chunks;
+	info[3] = prod.chunkStages;
+	info[4] = prod.grid;
+	for (size_t t = 0; t < counts.size() && t < tileCapacity; ++t) slotsPerTile[t] = counts[t];
+	unsigned count = 0;
+	const unsigned long long units = (unsigned long long)prod.tiles * prod.chunkStages;
+	for (unsigned cta = 0; cta < prod.grid; ++cta) {
+		SegmentWalker walk(units, prod.grid, prod.stagesPerTile, prod.chunkStages, prod.chunks, cta);
+		Segment s;
+		while (walk.next(s)) {
+			if (count < capacity) {
+				unsigned* o = segments + 5 * (size_t)count;
+				o[0] = cta; o[1] = s.tile; o[2] = s.stage0; o[3] = s.len; o[4] = s.slot;
+			}
+			++count;
+		}
+	}
+	return count;
+}
 
 float meanOf(const float* V, unsigned m, unsigned n, size_t ldV, cudaStream_t stream) {
 	double* partial = nullptr;

@@ -62,6 +62,13 @@ struct Plan {
 	~Plan();
 };
 
+// The work split of one product for `sms` CTAs, on the host and without a device (what tests/test_stream_k_plan.py checks):
+// every segment {cta, 256-row tile, first stage, stages, slot} in execution order (5 words each, at most `capacity` are
+// written; the return value is their number), info = {tiles, stages per tile, chunks, stages per chunk, grid} and the
+// partial products per 128-wide tile that the consumers will add up.
+unsigned enumerateSegments(unsigned rowsA, unsigned kdim, unsigned kp, unsigned sms, unsigned* segments, unsigned capacity, unsigned info[5],
+                           unsigned char* slotsPerTile, unsigned tileCapacity);
+
 // fp32 problem shapes the tensor-core path covers (others run the SIMT kernels)
 bool shapeSupported(unsigned m, unsigned n, unsigned k, size_t ldV, size_t ldW);
 
