@@ -90,7 +90,7 @@ def dist_env():
     return rank, world, local
 
 
-def cpu_baseline(sample_cols=1000, iters=2):
+def cpu_baseline(sample_cols=2000, iters=8):
     """fp64 OpenMP oracle on the first `sample_cols` columns of the workload (bounded CPU time)."""
     from nmfgpu_b200.workloads import uniform_block
     from oracle import binding as orc
