@@ -84,6 +84,31 @@ def test_library_exports_every_declared_symbol(library_path):
         assert mangled in names, mangled
 
 
+REFERENCE_EXAMPLE = "/root/reference/example/main.cpp"
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE_EXAMPLE), reason="the reference tree is only mounted in the build container")
+def test_reference_example_builds_against_this_header_and_library(tmp_path, library_path):
+    """Source-level drop-in: the reference's own example caller (example/main.cpp, C++ API: nmfgpu::initialize / chooseGpu /
+    compute, ISummary through its vtable), compiled UNMODIFIED where it lies against include/nmfgpu.h and linked with this
+    libnmfgpu64.so.  Without a GPU the program must come back with the library's error, not crash."""
+    exe = str(tmp_path / "reference_example")
+    libdir = os.path.dirname(library_path)
+    subprocess.run(["g++", "-std=c++14", "-I", os.path.join(ROOT, "include"), REFERENCE_EXAMPLE, "-L", libdir, "-lnmfgpu64",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True, capture_output=True, text=True)
+    r = subprocess.run([exe], input="\n", capture_output=True, text=True, timeout=300)
+    assert r.returncode >= 0, "killed by signal %d" % -r.returncode      # ran to its own exit
+    if not _has_gpu():
+        assert "no CPU fallback" in (r.stdout + r.stderr)
+
+
+def _has_gpu():
+    try:
+        return subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).returncode == 0
+    except FileNotFoundError:
+        return False
+
+
 def test_product_sources_never_touch_the_oracle():
     """The product path may not include, link or call anything under oracle/ (no CPU fallback)."""
     pkg = os.path.join(ROOT, "nmfgpu_b200")
