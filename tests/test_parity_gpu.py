@@ -363,7 +363,7 @@ def test_sparse_execution_double_and_auto_policy(L, monkeypatch):
         assert rel(r["W"], o["W"]) <= 1e-9 and rel(r["H"], o["H"]) <= 1e-9
 
 
-def test_sparse_execution_rejects_dense_initialisations(L, monkeypatch):
+def test_dense_initialisations_densify_a_sparse_input(L, monkeypatch):
     monkeypatch.setenv("NMFGPU_SPARSE", "1")
     rng = np.random.default_rng(8)
     D = ((rng.random((300, 200)) < 0.02) * rng.random((300, 200))).astype(np.float32)
