@@ -5,10 +5,13 @@
 
 A step is one multiplicative-update iteration (H update, W update, column normalisation) over the whole
 synthetic matrix.  Rank 0 prints ONE JSON line:
-  value      iterations/s with V already resident in HBM (CUDA events on the engine's stream, max over ranks);
-             strong scaling: the same 100k x 10k problem is column-sharded over the N GPUs
-  e2e        the same metric through the reference-facing C ABI (nmfgpu_compute_single) with HOST buffers:
-             H2D of V, W0, H0 and D2H of W, H inside the timed region
+  value      iterations/s with V already resident in HBM (CUDA events on the engine's stream, max over ranks), issued the
+             way the reference's run loop issues them: the residual is evaluated on every 10th and on the last iteration
+             (SingleGpuDispatcher.cpp:173) and its host work is inside the events, as it is inside the reference's
+             elapsedTime; strong scaling: the same 100k x 10k problem is column-sharded over the N GPUs
+  e2e        the same metric through the reference-facing C ABI (nmfgpu_compute_single) with PAGEABLE host buffers (what
+             an R caller hands over): H2D of V, W0, H0 and D2H of W, H inside the timed region; e2e_pinned: the same
+             call from page-locked buffers.  The reference arm gets the same two kinds of buffers.
   roofline   the slower of the two V-streaming kernels against the measured HBM peak (MEASURED_PEAKS.json)
   cpu_baseline  the fp64 OpenMP oracle timed on a bounded column sample of the same workload
 `--impl reference` times the UNMODIFIED reference (oracle/_ref/libnmfgpu64_ref.so, compiled from
@@ -139,14 +142,30 @@ def run_reference(args, rank, world, local):
         r = REF.compute(V, K, W0=W0, H0=H0, iterations=args.steps)
         wall = time.perf_counter() - t0
         clocks = sampler.stop()
-        REF.finalize()
         assert r["rc"] == 0, r["rc"]
+        # the same call from page-locked memory (what our own e2e_pinned leg gets)
+        wall_pinned = None
+        try:
+            import torch
+            Vp = torch.empty((N, M), dtype=torch.float32, pin_memory=True)      # (N, M) C-order = (M, N) column-major
+            Vp.numpy()[:, :] = V.T
+            Vpin = Vp.numpy().T
+            REF.compute(Vpin, K, W0=W0, H0=H0, iterations=2)
+            t0 = time.perf_counter()
+            rp = REF.compute(Vpin, K, W0=W0, H0=H0, iterations=args.steps)
+            wall_pinned = time.perf_counter() - t0
+            assert rp["rc"] == 0
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("pinned leg of the reference arm skipped: %s\n" % e)
+        REF.finalize()
         inner = max(r["elapsed"], 1e-3)        # ExecutionRecord.elapsedTime: host clock, excludes setup (Dispatcher.cpp:166,181,218)
         value = args.steps / inner
         line.update(value=value, ms_per_step=1000.0 * inner / args.steps, clocks=clocks, gpu_launches=None,
                     cpu_baseline={"value": value, "unit": "iterations/s", "cores": 1, "kind": "reference",
                                   "sample": "unmodified reference (cuBLAS fp32 on the same B200), %d iterations, ExecutionRecord.elapsedTime" % args.steps},
-                    e2e={"value": args.steps / wall, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    e2e={"value": args.steps / wall, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                         "host_buffers": "pageable", "h2d_bytes_per_call": (M * N + M * K + K * N) * 4, "d2h_bytes_per_call": (M * K + K * N) * 4},
+                    e2e_pinned=None if wall_pinned is None else {"value": args.steps / wall_pinned, "unit": "iterations/s", "host_buffers": "page-locked"},
                     effective_tflops=flops_per_iteration(M, N, K) * value / 1e12, final_frobenius=r["frobenius"])
     else:
         cb = cpu_baseline()
@@ -201,11 +220,12 @@ def run_ours(args, rank, world, local):
     s = api.Session(L, "mu", M, nloc, K, device_ptr=dev, ld_v=ld)
     s.set_factors(W0, H0)
     sampler = ClockSampler(local) if rank == 0 else None      # started before the warm-up: nvidia-smi needs ~0.1 s to produce its first line
-    s.iterate(args.warmup)
+    s.iterate(args.warmup)                      # W >= 4 iterations also record the CUDA graph the timed batches replay
+    s.iterate_with_error()                      # ... and the residual path (pinned buffers, the host combine) is warm
     s.synchronize()
     info0 = s.info()
     barrier()
-    ms = s.time_iterations(args.steps)          # CUDA events on the engine's stream around exactly K iterations
+    ms, f_timed = s.time_run(args.steps)        # CUDA events on the engine's stream around exactly K iterations, residual cadence included
     barrier()
     clocks = sampler.stop() if sampler else None
     info1 = s.info()
@@ -217,19 +237,23 @@ def run_ours(args, rank, world, local):
     collectives = int(info1.collective_calls - info0.collective_calls)
     f_final, _ = s.iterate_with_error()
 
-    # ---- roofline of the two V-streaming kernels (each reads its shard of V exactly once per launch)
+    # ---- roofline of the two V-streaming kernels (each reads its block of V exactly once per launch).  Every rank
+    # launches them: with row blocks the W^T V kernel stores its tiles into the other ranks' memory.
     roof = None
+    reps, t_wtv, t_vht = 5, [], []
+    barrier()
+    for _ in range(reps):
+        _, _, a, b = s.products(want_wtv=False, want_vht=False)
+        t_wtv.append(a)
+        t_vht.append(b)
+    barrier()
     if rank == 0:
-        reps, t_wtv, t_vht = 5, [], []
-        for _ in range(reps):
-            _, _, a, b = s.products(want_wtv=False, want_vht=False)
-            t_wtv.append(a)
-            t_vht.append(b)
         a, b = float(np.mean(t_wtv)), float(np.mean(t_vht))
         peak, how = peaks()
         # algorithmic bytes per launch: V once + the small operand (hi and lo) + the partial outputs
-        bytes_wtv = 4.0 * M * nloc + 8.0 * M * K + 4.0 * K * nloc * info1.splits_wtv
-        bytes_vht = 4.0 * M * nloc + 8.0 * K * nloc + 4.0 * M * K * info1.splits_vht
+        # (N GPUs: a rank streams 1/N of V either way -- a column shard, or the row block it was regrouped into)
+        bytes_wtv = 4.0 * M * nloc + 8.0 * M * K / world + 4.0 * K * N * info1.splits_wtv / (world if info1.row_owners else 1)
+        bytes_vht = 4.0 * M * nloc + 8.0 * K * N + 4.0 * M * K * info1.splits_vht / world
         name, tms, by = ("gemm_vht (V H^T)", b, bytes_vht) if b >= a else ("gemm_wtv (W^T V)", a, bytes_wtv)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -242,28 +266,37 @@ def run_ours(args, rank, world, local):
     s.close()
     L.lib.nmfgpu_b200_device_free(dev)
 
-    # ---- end-to-end leg through the reference-facing C ABI with host buffers (rank-local shard)
+    # ---- end-to-end legs through the reference-facing C ABI with host buffers (rank-local shard): first from ordinary
+    # pageable memory -- what an nmfgpu4R caller hands over -- then from page-locked memory
     e2e_iters = args.steps
     nbytes = M * nloc * 4
+    tmp = L.lib.nmfgpu_b200_device_alloc(nbytes)
+    assert L.lib.nmfgpu_b200_device_uniform_f32(tmp, M, nloc, M, SEED_V, M, 0, c0) == 0
+
+    def timed_call(Vhost):
+        r = L.compute(Vhost, K, W0=W0, H0=H0, iterations=2)          # warm: module load, allocator
+        assert r["rc"] == 0, r["rc"]
+        barrier()
+        t0 = time.perf_counter()
+        r = L.compute(Vhost, K, W0=W0, H0=H0, iterations=e2e_iters)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        assert r["rc"] == 0, r["rc"]
+        tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        return float(tw.item()), r
+
+    Vpage = np.empty((nloc, M), dtype=np.float32)                    # (nloc, M) C-order = (M, nloc) column-major
+    assert L.lib.nmfgpu_b200_device_download(Vpage.ctypes.data, tmp, nbytes) == 0
+    wall, r = timed_call(Vpage.T)
+    del Vpage
     hp = L.lib.nmfgpu_b200_host_alloc(nbytes)
     assert hp, "pinned host allocation failed"
     Vh = np.ctypeslib.as_array(ctypes.cast(hp, ctypes.POINTER(ctypes.c_float)), shape=(nloc, M)).T   # (M, nloc) Fortran view
-    tmp = L.lib.nmfgpu_b200_device_alloc(nbytes)
-    assert L.lib.nmfgpu_b200_device_uniform_f32(tmp, M, nloc, M, SEED_V, M, 0, c0) == 0
     assert L.lib.nmfgpu_b200_device_download(hp, tmp, nbytes) == 0
     L.lib.nmfgpu_b200_device_free(tmp)
-    r = L.compute(Vh, K, W0=W0, H0=H0, iterations=2)          # warm: module load, allocator
-    assert r["rc"] == 0, r["rc"]
-    barrier()
-    t0 = time.perf_counter()
-    r = L.compute(Vh, K, W0=W0, H0=H0, iterations=e2e_iters)
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    assert r["rc"] == 0, r["rc"]
-    tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-    wall = float(tw.item())
+    wall_pinned, _ = timed_call(Vh)
     del Vh
     L.lib.nmfgpu_b200_host_free(hp)
     h2d = (M * nloc + M * K + K * nloc) * 4 * world
@@ -278,15 +311,19 @@ def run_ours(args, rank, world, local):
             "config": {"workload": "dense fp32 100000x10000, k=64, MU Frobenius, CopyExisting init (BASELINE configs[1])",
                        "arithmetic": "3xTF32 tcgen05 (fp32-equivalent)" if roof and roof["uses_tensor_cores"] else "fp32 SIMT",
                        "parallelism": ("single GPU" if world == 1 else
-                                       "column shards x%d + row blocks of V, NCCL all-gather of H and W, all-reduce of k*k+k statistics" % world
+                                       "column shards x%d regrouped into row blocks; per iteration k x n partials of W^T V, columns of H and k*k+k "
+                                       "statistics move as NVLink peer stores from inside the kernels (no NCCL call in the iteration)" % world
                                        if info1.row_owners else "column shards x%d, NCCL all-reduce of V H^T and H H^T" % world),
+                       "cadence": "residual on every 10th and the last iteration inside the timed region (reference run loop)",
                        "l2": "input (4 GB) larger than the 126 MB L2; no flush needed"},
             "effective_tflops": flops_per_iteration(M, N, K) * value / 1e12,
             "hbm_roofline_iterations_per_s": 1.0 / ((8.0 * M * N + 16.0 * K * (M + N)) / (peaks()[0] * 1e9)) * world,
             "e2e": {"value": e2e_iters / wall, "unit": "iterations/s", "h2d_bytes_per_step": h2d / e2e_iters, "d2h_bytes_per_step": d2h / e2e_iters,
-                    "call": "nmfgpu_compute_single(numIterations=%d) from pinned host buffers, wall clock incl. H2D of V" % e2e_iters},
+                    "host_buffers": "pageable",
+                    "call": "nmfgpu_compute_single(numIterations=%d) from pageable host buffers, wall clock incl. H2D of V" % e2e_iters},
+            "e2e_pinned": {"value": e2e_iters / wall_pinned, "unit": "iterations/s", "host_buffers": "page-locked"},
             "gpu_launches": launches, "collective_calls": collectives, "clocks": clocks, "roofline": roof,
-            "final_frobenius": f_final, "e2e_frobenius": r["frobenius"],
+            "timed_frobenius": f_timed, "final_frobenius": f_final, "e2e_frobenius": r["frobenius"],
         }
         try:
             line["cpu_baseline"] = cpu_baseline() if world == 1 else None

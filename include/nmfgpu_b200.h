@@ -30,7 +30,7 @@ typedef struct nmfgpu_b200_session_info {
 	unsigned long long kernel_launches;   /* kernels launched by this session so far */
 	unsigned long long collective_calls;  /* NCCL all-reduces issued so far */
 	size_t ld_v, ld_w, ld_h;
-	int row_owners;                   /* 1 when column shards run the row-owner dataflow (all-gather of H and W), 0 for all-reduce */
+	int row_owners;                   /* 1 when column shards were regrouped into row blocks (peer-store exchange, csrc/dist.h), 0 for all-reduce */
 } nmfgpu_b200_session_info;
 
 /* 0 = auto (tensor cores when the shape allows), 1 = exact SIMT fp32, 2 = force 3xTF32, 3 = 1xTF32 (diagnostic).
@@ -40,11 +40,16 @@ int nmfgpu_b200_set_precision(int mode);
 
 /* ---- multi-GPU: rank 0 creates the id, every rank passes it to dist_init after nmfgpu_initialize() and
  * nmfgpu_choose_gpu().  From then on inputMatrix / outputMatrixH of nmfgpu_compute_* describe this rank's
- * column shard (columnOffset .. columnOffset + inputMatrix.columns of globalColumns); W is replicated.
- * MU on the tensor-core path with equal shards runs the row-owner dataflow (every rank also keeps a row block of V,
- * built once from the shards; per iteration H and W are all-gathered), everything else all-reduces V H^T and H H^T;
- * NMFGPU_DIST_MODE=allreduce forces the latter. */
+ * column shard (columnOffset .. columnOffset + inputMatrix.columns of globalColumns); W is replicated on return.
+ * MU on the tensor-core path regroups the shards once into row blocks; per iteration the ranks then exchange only k x n
+ * partial products, columns of H and k*k + k statistics, as NVLink peer stores issued by the kernels themselves (no NCCL
+ * call in the iteration; csrc/dist.h, csrc/fused.h).  Everything else all-reduces V H^T and H H^T with NCCL;
+ * NMFGPU_DIST_MODE=allreduce forces that dataflow for MU as well.
+ * dist_unique_id: one process per GPU (NCCL + CUDA IPC).  dist_local_unique_id: the ranks are THREADS of the calling
+ * process (each with its own nmfgpu_initialize), on any devices -- also all on one, which is how the tests run the sharded
+ * dataflows on a single-GPU box. */
 int nmfgpu_b200_dist_unique_id(void* out128);
+int nmfgpu_b200_dist_local_unique_id(void* out128);
 int nmfgpu_b200_dist_init(int rank, int world_size, const void* unique_id128);
 int nmfgpu_b200_dist_set_shard(unsigned global_columns, unsigned column_offset);
 int nmfgpu_b200_dist_finalize(void);
@@ -61,6 +66,9 @@ int nmfgpu_b200_session_iterate(nmfgpu_b200_session* s, unsigned iterations);
 int nmfgpu_b200_session_iterate_with_error(nmfgpu_b200_session* s, double* frobenius, double* rmsd);
 /* `iterations` iterations bracketed by CUDA events on the session's stream; milliseconds for all of them */
 int nmfgpu_b200_session_time_iterations(nmfgpu_b200_session* s, unsigned iterations, float* milliseconds);
+/* `iterations` iterations issued the way the reference's run loop does (SingleGpuDispatcher.cpp:171-201): residual on every
+ * 10th and on the last iteration, its host work inside the events; *frobenius (may be NULL) = the last residual */
+int nmfgpu_b200_session_time_run(nmfgpu_b200_session* s, unsigned iterations, float* milliseconds, double* frobenius);
 /* the two V-sized products for the current factors, summed over their slices, copied to the host:
  * wtv is features x columns (ld = features), vht is rows x features (ld = rows).  Either may be NULL.
  * Also reports the device time of each product in milliseconds (NULL to skip). */

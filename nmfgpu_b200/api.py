@@ -140,7 +140,8 @@ C_SYMBOLS = ["nmfgpu_initialize", "nmfgpu_finalize", "nmfgpu_version", "nmfgpu_s
              "nmfgpu_compute_kmeans_double", "nmfgpu_choose_gpu", "nmfgpu_get_number_of_gpu",
              "nmfgpu_get_information_for_gpu_index"]
 
-EXT_SYMBOLS = ["nmfgpu_b200_set_precision", "nmfgpu_b200_dist_unique_id", "nmfgpu_b200_dist_init",
+EXT_SYMBOLS = ["nmfgpu_b200_set_precision", "nmfgpu_b200_dist_unique_id", "nmfgpu_b200_dist_local_unique_id", "nmfgpu_b200_dist_init",
+               "nmfgpu_b200_session_time_run",
                "nmfgpu_b200_dist_set_shard", "nmfgpu_b200_dist_finalize", "nmfgpu_b200_session_create_f32",
                "nmfgpu_b200_session_set_factors_f32", "nmfgpu_b200_session_get_factors_f32",
                "nmfgpu_b200_session_iterate", "nmfgpu_b200_session_iterate_with_error",
@@ -237,6 +238,8 @@ class Library:
             L.nmfgpu_b200_session_iterate.argtypes = [c_void_p, c_uint]
             L.nmfgpu_b200_session_iterate_with_error.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double)]
             L.nmfgpu_b200_session_time_iterations.argtypes = [c_void_p, c_uint, POINTER(c_float)]
+            L.nmfgpu_b200_session_time_run.argtypes = [c_void_p, c_uint, POINTER(c_float), POINTER(c_double)]
+            L.nmfgpu_b200_dist_local_unique_id.argtypes = [c_void_p]
             L.nmfgpu_b200_session_products_f32.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_float), POINTER(c_float)]
             L.nmfgpu_b200_session_synchronize.argtypes = [c_void_p]
             L.nmfgpu_b200_session_get_info.argtypes = [c_void_p, POINTER(SessionInfo)]
@@ -433,6 +436,14 @@ class Session:
         if rc != 0:
             raise RuntimeError("time_iterations -> %d" % rc)
         return ms.value
+
+    def time_run(self, iterations):
+        """Milliseconds of `iterations` iterations with the reference's residual cadence, and the last residual."""
+        ms, f = c_float(), c_double()
+        rc = self.L.lib.nmfgpu_b200_session_time_run(self.h, iterations, ctypes.byref(ms), ctypes.byref(f))
+        if rc != 0:
+            raise RuntimeError("time_run -> %d" % rc)
+        return ms.value, f.value
 
     def products(self, want_wtv=True, want_vht=True):
         wtv = np.zeros((self.k, self.n), dtype=np.float32, order="F") if want_wtv else None

@@ -21,7 +21,7 @@ if os.environ.get("NMFGPU_BUILD_OUT"):
     LIBRARY = os.path.abspath(os.environ["NMFGPU_BUILD_OUT"])
     OBJDIR = os.path.join(LIBDIR, "obj_" + os.path.basename(LIBRARY).replace(".", "_"))
 
-SOURCES = ["api.cpp", "host.cpp", "dist.cpp", "engine.cu", "kernels.cu", "tc_gemm.cu", "kmeans.cu", "sparse.cu", "spmm.cu",
+SOURCES = ["api.cpp", "host.cpp", "dist.cpp", "engine.cu", "kernels.cu", "fused.cu", "tc_gemm.cu", "kmeans.cu", "sparse.cu", "spmm.cu",
            "init_kernels.cu", "session.cu"]
 
 # NMFGPU_TC_TRACE_BUILD=1 compiles the timeline / ablation hooks of tc_gemm.cu in (diagnostic builds only)

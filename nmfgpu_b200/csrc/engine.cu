@@ -19,6 +19,7 @@
 #include <cstring>
 #include <limits>
 #include <numeric>
+#include <thread>
 
 #include "dist.h"
 #include "init_kernels.h"
@@ -43,6 +44,62 @@ unsigned pickGramSplits(unsigned tiles, unsigned reduceLen) {
 	unsigned s = ceilDiv(4 * 148, std::max(1u, tiles));
 	s = std::min(s, std::max(1u, reduceLen / 64));
 	return std::max(1u, s);
+}
+
+// H2D of a dense column-major host matrix.  Callers of the reference API (nmfgpu4R) hand over ordinary pageable memory;
+// cudaMemcpy from pageable memory goes through the driver's single-threaded staging at a fraction of the PCIe rate, and at
+// 20 iterations that copy IS the call (4 GB against 30 ms of iterations).  Here the matrix moves in column chunks through
+// two page-locked staging buffers (pooled between calls): a few host threads fill one buffer while the DMA engine drains
+// the other.  Page-locked / registered sources take the direct path.
+template <typename T>
+void uploadDense(T* dev, size_t ldDev, const T* host, size_t ldHost, unsigned rows, unsigned cols, unsigned ranksOnThisHost, cudaStream_t stream) {
+	const size_t columnBytes = (size_t)rows * sizeof(T);
+	cudaPointerAttributes attr;
+	bool pageable = true;
+	if (cudaPointerGetAttributes(&attr, host) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+	else cudaGetLastError();
+	if (const char* e = getenv("NMFGPU_STAGED_UPLOAD")) pageable = pageable && atoi(e) != 0;
+	if (!pageable || columnBytes * cols < (32u << 20)) {
+		CUDA_CHECK(cudaMemcpy2DAsync(dev, ldDev * sizeof(T), host, ldHost * sizeof(T), columnBytes, cols, cudaMemcpyHostToDevice, stream));
+		return;
+	}
+	const size_t chunkBytes = 64u << 20;
+	const unsigned chunkCols = (unsigned)std::max<size_t>(1, chunkBytes / columnBytes);
+	const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+	const unsigned threads = std::max(2u, std::min(8u, hw / std::max(1u, ranksOnThisHost)));
+	PinnedBuffer<T> staging[2];
+	cudaEvent_t drained[2] = {nullptr, nullptr};
+	for (int b = 0; b < 2; ++b) {
+		staging[b].allocate((size_t)chunkCols * rows);
+		CUDA_CHECK(cudaEventCreateWithFlags(&drained[b], cudaEventDisableTiming));
+	}
+	unsigned chunk = 0;
+	for (unsigned c0 = 0; c0 < cols; c0 += chunkCols, ++chunk) {
+		const unsigned nc = std::min(chunkCols, cols - c0);
+		const int b = (int)(chunk & 1);
+		if (chunk >= 2) CUDA_CHECK(cudaEventSynchronize(drained[b]));   // the DMA of two chunks ago has left this buffer
+		T* stage = staging[b].get();
+		auto fill = [&](unsigned t) {
+			// thread t copies an equal share of the chunk's bytes, column by column (the host matrix may have ld > rows)
+			const size_t total = (size_t)nc * columnBytes, begin = total * t / threads, end = total * (t + 1) / threads;
+			size_t at = begin;
+			while (at < end) {
+				const size_t col = at / columnBytes, off = at % columnBytes;
+				const size_t len = std::min(end - at, columnBytes - off);
+				memcpy(reinterpret_cast<char*>(stage) + col * columnBytes + off,
+				       reinterpret_cast<const char*>(host + (size_t)(c0 + col) * ldHost) + off, len);
+				at += len;
+			}
+		};
+		std::vector<std::thread> pool;
+		for (unsigned t = 1; t < threads; ++t) pool.emplace_back(fill, t);
+		fill(0);
+		for (std::thread& th : pool) th.join();
+		CUDA_CHECK(cudaMemcpy2DAsync(dev + (size_t)c0 * ldDev, ldDev * sizeof(T), stage, columnBytes, columnBytes, nc, cudaMemcpyHostToDevice, stream));
+		CUDA_CHECK(cudaEventRecord(drained[b], stream));
+	}
+	CUDA_CHECK(cudaStreamSynchronize(stream));   // the staging buffers go back to the pool
+	for (int b = 0; b < 2; ++b) cudaEventDestroy(drained[b]);
 }
 }  // namespace
 
@@ -78,7 +135,10 @@ void Engine<T>::reportStamps() {
 		if (strcmp(m_stamps[i - 1].first, "begin") == 0) ++iterations;
 		if (strcmp(m_stamps[i].first, "begin") == 0 || iterations <= 2) continue;
 		float ms = 0.f;
-		cudaEventElapsedTime(&ms, m_stamps[i - 1].second, m_stamps[i].second);
+		if (cudaEventElapsedTime(&ms, m_stamps[i - 1].second, m_stamps[i].second) != cudaSuccess) {
+			cudaGetLastError();
+			continue;
+		}
 		bool found = false;
 		for (auto& s : sums)
 			if (s.first == m_stamps[i].first) {
@@ -103,6 +163,7 @@ Engine<T>::~Engine() {
 	if (m_stream) {
 		reportStamps();
 		cudaStreamSynchronize(m_stream);
+		releaseFused();
 		for (auto& row : m_graphExec)
 			for (cudaGraphExec_t& g : row)
 				if (g) cudaGraphExecDestroy(g);
@@ -154,8 +215,7 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 		m_V.allocate(m_ldV * n);
 		if (V.format == StorageFormat::Dense) {
 			if (V.dense.leadingDimension < m) throw EngineError(ResultType::ErrorInvalidArgument, "leading dimension of V too small");
-			CUDA_CHECK(cudaMemcpy2DAsync(m_V.get(), m_ldV * sizeof(T), V.dense.values, (size_t)V.dense.leadingDimension * sizeof(T),
-			                             (size_t)m * sizeof(T), n, cudaMemcpyHostToDevice, m_stream));
+			uploadDense<T>(m_V.get(), m_ldV, V.dense.values, V.dense.leadingDimension, m, n, m_cfg.comm ? (unsigned)m_cfg.comm->worldSize() : 1u, m_stream);
 			if (m_ldV != m) sparse::zeroPadRows(m_V.get(), m, n, m_ldV, m_stream);
 		} else {
 			sparse::densify(V, m_V.get(), m_ldV, m_stream);
@@ -185,8 +245,11 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	}
 
 	timer.mark("  factor buffers");
+	m_fused = decideFused();
 	// split-K plans of the two V-sized products and of the Gram products
-	if (m_useTC) {
+	if (m_fused) {
+		// MU on the tensor cores: buffers, row blocks and plans in setupFused() below
+	} else if (m_useTC) {
 		m_tc.reset(new TcPlan());
 		m_ldHt = roundUp(n, 32);
 		m_Whi.allocate(m_ldW * k);
@@ -220,16 +283,20 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	m_splitsGH = kern::effectiveSplits(n, pickGramSplits(ceilDiv(k, 64) * ceilDiv(k, 64), n));
 	m_strideN = m_ldH * n;
 	m_strideP = m_ldW * k;
-	m_Npart.allocate(m_strideN * (m_splitsN + 1));   // +1: landing zone of the pre-reduced product (many partials per tile)
-	m_Ppart.allocate(m_strideP * (m_splitsP + 1));  // +1: slot for the summed / all-reduced product
+	if (!m_fused) {
+		m_Npart.allocate(m_strideN * (m_splitsN + 1));   // +1: landing zone of the pre-reduced product (many partials per tile)
+		m_Ppart.allocate(m_strideP * (m_splitsP + 1));  // +1: slot for the summed / all-reduced product
+	}
 	m_kkScratch.allocate((size_t)k * k * std::max(m_splitsGW, m_splitsGH));
 	m_colSqPartials.allocate((size_t)ceilDiv(m, 128) * k);
 	m_colSumPartials.allocate((size_t)ceilDiv(m, 128) * k);
 	m_rowSumPartials.allocate((size_t)ceilDiv(n, 64) * k);
 	m_colSq.allocate(k);
-	m_partN.allocate(std::max(n, k));
+	// residual terms: per column of the caller's shard at setup (tr V^T V), per updated column in the iterations
+	const unsigned globalColumns = m_cfg.comm != nullptr ? std::max(n, m_cfg.comm->globalColumns()) : n;
+	m_partN.allocate(std::max(globalColumns, k));
 	m_partK.allocate(k);
-	m_hostSecond.allocate(std::max(n, k));
+	m_hostSecond.allocate(std::max(globalColumns, k));
 	m_hostThird.allocate(k);
 	if (m_cfg.algorithm == NmfAlgorithm::nsNMF) {
 		m_smoothW.allocate(m_ldW * k);
@@ -248,7 +315,8 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	std::copy(m_hostSecond.get(), m_hostSecond.get() + n, m_vtvSorted.begin());
 	std::sort(m_vtvSorted.begin(), m_vtvSorted.end());
 	timer.mark("  tr(V^T V)");
-	setupRowOwners();
+	if (m_fused) setupFused();
+	timer.mark("  row blocks, exchange buffer, plans");
 }
 
 // Sparse inputs run compressed when densifying is wasteful or impossible (spmm.h); the reference always densifies.
@@ -266,46 +334,68 @@ void Engine<T>::decideSparse(const MatrixDescription<T>& V, bool vOnDevice) {
 	m_sparse = (double)V.csr.nnz <= 0.02 * cells || cells * sizeof(T) > 0.5 * (double)freeBytes;
 }
 
-// ---- row-owner dataflow for column shards (dist.h) ----------------------------------------------------------
-// The all-reduce dataflow repeats the whole W update on every rank and moves 2 x 4mk bytes per rank and iteration.
-// Here rank g also keeps the row block V[I_g, :] (one grouped send/recv of the column shards at setup; V is then
-// resident twice, 2 x 4mn/G bytes per GPU), so that
-//   H update : columns J_g from W^T V[:, J_g] as before, then all-gather of H (4kn bytes),
-//   W update : rows I_g from V[I_g, :] H^T -- no reduction --, all-reduce of k*k + k statistics of the un-normalised
-//              block (Gram matrix, whose diagonal holds the column norms, and column sums), all-gather of the unit-column
-//              blocks (4mk bytes).
-// Every W-side kernel works on m/G rows; W^T W falls out of the statistics.  Needs equal column shards.
+// ---- fused MU: one GPU, or row blocks over several (fused.h, dist.h) ------------------------------------------------
+// The caller hands in column shards (the north star's contract).  m >> n in the workloads this library serves, so the
+// shards are regrouped ONCE into row blocks V[I_g, :]; from then on
+//   W^T V    : rank g forms the partial W[I_g]^T V[I_g, :] (k x N) and its tcgen05 kernel stores every tile straight into
+//              the memory of the rank that owns those columns of H (NVLink peer stores),
+//   H update : the owners add the partials up, update their columns and store them (and their TF32 split) to every rank,
+//   V H^T    : V[I_g, :] H^T, the rank's own rows, no reduction,
+//   W update : rows I_g only; the unit-column scaling is applied when W is read, its k*k + k statistics travel as peer
+//              stores.  W is never gathered during the iterations.
+// Exchanged per iteration and rank: (G-1)/G of k x N partials out, k x N/G columns of H to G-1 ranks, 2 (k*k + k) statistics.
 template <typename T>
-void Engine<T>::setupRowOwners() {
+bool Engine<T>::decideFused() {
+	if (!std::is_same<T, float>::value || !m_useTC || m_cfg.algorithm != NmfAlgorithm::Multiplicative) return false;
+	if (const char* e = getenv("NMFGPU_FUSED"))
+		if (atoi(e) == 0) return false;
 	Communicator* comm = m_cfg.comm;
-	if (comm == nullptr || comm->worldSize() <= 1) return;
-	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
-	const unsigned G = (unsigned)comm->worldSize(), rank = (unsigned)comm->rank();
-	const unsigned N = comm->globalColumns();
-	const unsigned mrPad = (unsigned)roundUp(ceilDiv(m, G), 256);
+	if (comm == nullptr || comm->worldSize() <= 1) return true;
+	const unsigned G = (unsigned)comm->worldSize();
 	const char* mode = getenv("NMFGPU_DIST_MODE");
-	bool ok = std::is_same<T, float>::value && m_useTC && m_cfg.algorithm == NmfAlgorithm::Multiplicative && !m_cfg.constantW &&
-	          !(mode != nullptr && strcmp(mode, "allreduce") == 0) && (unsigned long long)n * G == N && comm->columnOffset() == rank * n &&
-	          (unsigned long long)(G - 1) * mrPad < m;
-	if (ok) {
-		const unsigned r0 = rank * mrPad, mr = std::min(mrPad, m - r0);
-		ok = tc::shapeSupported(mr, N, k, roundUp(mr, 32), m_ldW);
-	}
-	// every rank must take the same path: the collectives of the two dataflows do not match
-	if (comm->allReduceSumHost(ok ? 1.0 : 0.0) != (double)G) return;
+	const unsigned mrPad = (unsigned)roundUp(ceilDiv(m_cfg.m, G), 256);
+	bool ok = G <= fused::kMaxRanks && !(mode != nullptr && strcmp(mode, "allreduce") == 0) && (unsigned long long)(G - 1) * mrPad < m_cfg.m;
+	// every rank must take the same path: the two dataflows exchange different things
+	return comm->allReduceSumHost(ok ? 1.0 : 0.0) == (double)G;
+}
 
-	m_rowOwners = true;
+template <typename T>
+void Engine<T>::setupFused() {
+	Communicator* comm = (m_cfg.comm != nullptr && m_cfg.comm->worldSize() > 1) ? m_cfg.comm : nullptr;
+	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
+	const unsigned G = comm ? (unsigned)comm->worldSize() : 1u, rank = comm ? (unsigned)comm->rank() : 0u;
+	const unsigned N = comm ? comm->globalColumns() : n;
 	m_globalN = N;
-	m_mrPad = mrPad;
-	m_r0 = rank * mrPad;
-	m_mr = std::min(mrPad, m - m_r0);
-	m_ldVr = roundUp(m_mr, 32);
-	auto rowsOf = [&](unsigned g) { return std::min(mrPad, m - g * mrPad); };
+	m_peers.world = G;
+	m_peers.rank = rank;
+	fused::configure();
 
-	// ---- V[I_g, :] from the column shards: rank g sends V[I_h, J_g] to every h, packed with the receiver's leading dimension
-	m_Vr.allocate(m_ldVr * N);
-	m_Vr.zero(m_stream);
-	{
+	// ---- the row block of this rank
+	if (comm == nullptr) {
+		m_mrPad = m;
+		m_r0 = 0;
+		m_mr = m;
+		m_ldVr = m_ldV;
+		m_Vblock = reinterpret_cast<const float*>(m_V.get());
+	} else {
+		m_mrPad = (unsigned)roundUp(ceilDiv(m, G), 256);
+		m_r0 = rank * m_mrPad;
+		m_mr = std::min(m_mrPad, m - m_r0);
+		m_ldVr = roundUp(m_mr, 32);
+		auto rowsOf = [&](unsigned g) { return std::min(m_mrPad, m - g * m_mrPad); };
+		// who holds which columns (shards may be unequal)
+		struct Shard {
+			unsigned offset, columns;
+		};
+		const Shard mine = {comm->columnOffset(), n};
+		std::vector<Shard> shards(G);
+		comm->allGatherHost(&mine, sizeof(mine), shards.data());
+		unsigned long long covered = 0;
+		for (const Shard& sh : shards) covered += sh.columns;
+		if (covered != N) throw EngineError(ResultType::ErrorInvalidArgument, "the column shards of the ranks do not add up to the global column count");
+		// V[I_g, :] from the column shards: rank g sends V[I_h, J_g] to every h, packed with the receiver's leading dimension
+		m_Vr.allocate(m_ldVr * N);
+		m_Vr.zero(m_stream);
 		size_t total = 0;
 		for (unsigned h = 0; h < G; ++h)
 			if (h != rank) total += roundUp(rowsOf(h), 32) * n;
@@ -318,119 +408,249 @@ void Engine<T>::setupRowOwners() {
 		for (unsigned h = 0; h < G; ++h) {
 			const size_t ldh = roundUp(rowsOf(h), 32);
 			if (h == rank) {
-				CUDA_CHECK(cudaMemcpy2DAsync(m_Vr.get() + m_ldVr * ((size_t)rank * n), m_ldVr * sizeof(float), V + m_r0, m_ldV * sizeof(float),
+				CUDA_CHECK(cudaMemcpy2DAsync(m_Vr.get() + m_ldVr * (size_t)mine.offset, m_ldVr * sizeof(float), V + m_r0, m_ldV * sizeof(float),
 				                             (size_t)m_mr * sizeof(float), n, cudaMemcpyDeviceToDevice, m_stream));
 				continue;
 			}
-			CUDA_CHECK(cudaMemcpy2DAsync(pack.get() + at, ldh * sizeof(float), V + (size_t)h * mrPad, m_ldV * sizeof(float),
+			CUDA_CHECK(cudaMemcpy2DAsync(pack.get() + at, ldh * sizeof(float), V + (size_t)h * m_mrPad, m_ldV * sizeof(float),
 			                             (size_t)rowsOf(h) * sizeof(float), n, cudaMemcpyDeviceToDevice, m_stream));
 			sends.push_back({pack.get() + at, ldh * n, (int)h});
-			recvs.push_back({m_Vr.get() + m_ldVr * ((size_t)h * n), m_ldVr * n, (int)h});
+			if (shards[h].columns > 0) recvs.push_back({m_Vr.get() + m_ldVr * (size_t)shards[h].offset, m_ldVr * shards[h].columns, (int)h});
 			at += ldh * n;
 		}
+		if (n == 0) sends.clear();
 		comm->exchange(sends, recvs, m_stream);
 		synchronize();
+		m_Vblock = m_Vr.get();
 	}
 
-	// ---- operands and plan of V[I_g, :] H^T
+	// ---- the columns of H this rank updates (128-column granularity: a panel never straddles a stream-K tile)
+	m_colsPerRank = (unsigned)roundUp(ceilDiv(N, G), 128);
+	m_c0 = (unsigned)std::min<unsigned long long>(N, (unsigned long long)rank * m_colsPerRank);
+	m_nOwn = (unsigned)std::min<unsigned long long>(N, (unsigned long long)m_c0 + m_colsPerRank) - m_c0;
+
+	// ---- operands of the products and their plan.  The centre must be the same number on every rank (the rank-one terms
+	// it leaves out are added once, after the partials of all ranks have been summed).
+	m_Whi.allocate(m_ldW * k);
+	m_Wlo.allocate(m_ldW * k);
+	m_Whi.zero(m_stream);
+	m_Wlo.zero(m_stream);
 	m_ldHtFull = roundUp(N, 32);
-	m_Hfull.allocate(m_ldH * N);
-	m_HtHiFull.allocate(m_ldHtFull * k);
-	m_HtLoFull.allocate(m_ldHtFull * k);
-	m_Hfull.zero(m_stream);
-	m_HtHiFull.zero(m_stream);
-	m_HtLoFull.zero(m_stream);
-	m_tcR.reset(new TcPlan());
-	const float center = tc::meanOf(m_Vr.get(), m_mr, N, m_ldVr, m_stream);
-	tc::makePlan(m_tcR->plan, m_mr, N, k, m_Vr.get(), m_ldVr, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, m_ldW, m_HtHiFull.get(), m_HtLoFull.get(),
-	             m_ldHtFull, m_cfg.precision == Precision::Tf32x1, center);
-	m_splitsPr = m_tcR->plan.vht.maxSlots;
+	float center = tc::meanOf(m_Vblock, m_mr, N, m_ldVr, m_stream);
+	if (comm != nullptr) center = (float)(comm->allReduceSumHost((double)center * (double)m_mr * (double)N) / ((double)m * (double)N));
+	if (const char* e = getenv("NMFGPU_TC_CENTER")) center = (float)atof(e) * center;   // study knob: 0 switches centring off
+
+	// slots per rank follow from the shape-only work split: plan once with placeholder operands to learn it
+	unsigned info[5];
+	m_slotsPerRank = 1;
+	{
+		std::vector<unsigned char> perTile(ceilDiv(N, 128));
+		int sms = 0, dev = 0;
+		CUDA_CHECK(cudaGetDevice(&dev));
+		CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+		tc::enumerateSegments(N, comm ? m_mrPad : m, (unsigned)roundUp(k, 16), (unsigned)sms, nullptr, 0, info, perTile.data(), (unsigned)perTile.size());
+		for (unsigned char c : perTile) m_slotsPerRank = std::max<unsigned>(m_slotsPerRank, c);
+	}
+
+	// ---- exchange buffer: the same layout on every rank
+	auto align = [](size_t x) { return roundUp(x, 256); };
+	m_lay.statLen = (unsigned)roundUp((size_t)k * k + k + 1, 32);
+	size_t at = 0;
+	m_lay.flagsN = at; at = align(at + fused::kMaxRanks * sizeof(unsigned));
+	m_lay.flagsH = at; at = align(at + fused::kMaxRanks * sizeof(unsigned));
+	m_lay.statW = at; at = align(at + (size_t)G * m_lay.statLen * sizeof(float));
+	m_lay.statH = at; at = align(at + (size_t)G * m_lay.statLen * sizeof(float));
+	m_lay.H = at; at = align(at + m_ldH * (size_t)N * sizeof(float));
+	m_lay.HtHi = at; at = align(at + m_ldHtFull * (size_t)k * sizeof(float));
+	m_lay.HtLo = at; at = align(at + m_ldHtFull * (size_t)k * sizeof(float));
+	m_lay.slots = at; at = align(at + (size_t)G * m_slotsPerRank * m_ldH * m_colsPerRank * sizeof(float));
+	m_lay.bytes = at;
+	m_sym = static_cast<char*>(pooledDeviceAlloc(m_lay.bytes));
+	CUDA_CHECK(cudaMemsetAsync(m_sym, 0, m_lay.bytes, m_stream));
+	synchronize();   // zeroed before any other rank can store into it (openPeers is a collective)
+	if (comm != nullptr) {
+		m_peerPtrs = comm->openPeers(m_sym);
+		for (unsigned g = 0; g < G; ++g) m_peers.base[g] = static_cast<char*>(m_peerPtrs[g]);
+	} else {
+		m_peers.base[0] = m_sym;
+	}
+	m_route.world = G;
+	m_route.colsPerRank = m_colsPerRank;
+	m_route.slotBase = rank * m_slotsPerRank;
+	for (unsigned g = 0; g < G; ++g) m_route.base[g] = reinterpret_cast<float*>(m_peers.base[g] + m_lay.slots);
+
+	m_tc.reset(new TcPlan());
+	float* HtHi = reinterpret_cast<float*>(m_sym + m_lay.HtHi);
+	float* HtLo = reinterpret_cast<float*>(m_sym + m_lay.HtLo);
+	tc::makePlan(m_tc->plan, m_mr, N, k, m_Vblock, m_ldVr, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, m_ldW, HtHi, HtLo, m_ldHtFull,
+	             m_cfg.precision == Precision::Tf32x1, center, comm ? m_mrPad : 0);
+	if (m_tc->plan.wtv.maxSlots > m_slotsPerRank) throw EngineError(ResultType::ErrorExternalLibrary, "work split of W^T V changed between two plans of the same shape");
+	m_splitsN = m_slotsPerRank;
+	m_slotsN = m_tc->plan.wtv.slotCount;
+	m_slotsP = m_tc->plan.vht.slotCount;
+	m_corrN = reinterpret_cast<const T*>(m_tc->plan.corrN);
+	m_corrP = reinterpret_cast<const T*>(m_tc->plan.corrP);
+	m_strideN = m_ldH * m_colsPerRank;
+	m_splitsPr = m_splitsP = m_tc->plan.vht.maxSlots;
 	m_ldPr = roundUp(m_mr, 32);
 	m_stridePr = m_ldPr * k;
 	m_PpartR.allocate(m_stridePr * m_splitsPr);
-	m_statLen = roundUp((size_t)k * k + k, 32);
-	m_stat.allocate(m_statLen);
-	m_statPart.allocate(m_statLen);
-	m_statGath.allocate(m_statLen * G);
-	m_statPart.zero(m_stream);
-	m_Wblk.allocate((size_t)mrPad * k);
-	m_Wgath.allocate((size_t)mrPad * k * G);
-	m_splitsGHfull = kern::effectiveSplits(N, pickGramSplits(ceilDiv(k, 64) * ceilDiv(k, 64), N));
-	m_splitsGWrows = kern::effectiveSplits(m_mr, pickGramSplits(ceilDiv(k, 64) * ceilDiv(k, 64), m_mr));
-	m_kkScratch.allocate((size_t)k * k * std::max(std::max(m_splitsGW, m_splitsGH), std::max(m_splitsGHfull, m_splitsGWrows)));
+
+	m_statSum.allocate(m_lay.statLen);
+	m_inv.allocate(roundUp(k, 32));
+	m_statPartH.allocate((size_t)std::max(1u, ceilDiv(m_nOwn, 64)) * ((size_t)k * k + k));
+	m_statPartW.allocate((size_t)std::max(1u, ceilDiv(m_mr, 128)) * ((size_t)k * k + k));
+	m_ctlWords.allocate(32);
+	m_ctlWords.zero(m_stream);
+	m_ctl.epoch = m_ctlWords.get();
+	m_ctl.error = m_ctlWords.get() + 1;
+	m_hostFlags.allocate(2);
+	m_hostFlags.get()[0] = m_hostFlags.get()[1] = 0;
+	synchronize();
 }
 
-// Everything the W update derives from H: the full matrix and its transposed TF32 split, H H^T and the centring term.
-// The k*k + k statistics of the local columns (H_g H_g^T and the row sums) travel with the all-gather of H in one NCCL
-// group and are added up in rank order on every rank: no separate all-reduce and no replicated work on all n columns.
 template <typename T>
-void Engine<T>::gatherH(bool haveRowSums) {
+void Engine<T>::releaseFused() {
+	if (m_sym == nullptr) return;
+	cudaStreamSynchronize(m_stream);
+	Communicator* comm = (m_cfg.comm != nullptr && m_cfg.comm->worldSize() > 1) ? m_cfg.comm : nullptr;
+	if (comm != nullptr && !m_peerPtrs.empty()) {
+		try {
+			comm->barrier();   // nobody stores into a buffer that is about to be recycled
+			comm->closePeers(m_peerPtrs);
+			comm->barrier();
+		} catch (...) {
+		}
+	}
+	pooledDeviceFree(m_sym, m_lay.bytes);
+	m_sym = nullptr;
+}
+
+// Initial factors are in m_W (all rows on every rank) and m_H (the caller's columns): derive what the iteration keeps
+// up to date itself -- the TF32 split and the statistics of the own rows of W (flag 0: the reference uses the initial W
+// as it is and normalises only after an update, MU.h:247), the full H with its transposed split.
+template <typename T>
+void Engine<T>::finishInitialisationFused() {
+	Communicator* comm = (m_cfg.comm != nullptr && m_cfg.comm->worldSize() > 1) ? m_cfg.comm : nullptr;
 	const unsigned k = m_cfg.k, n = m_cfg.n, N = m_globalN;
-	const unsigned G = (unsigned)m_cfg.comm->worldSize();
-	const T* Hloc = m_H[m_hCur].get();
-	float* part = m_statPart.get();
-	kern::gemmNT<T>(k, n, k, Hloc, m_ldH, Hloc, m_ldH, m_kkScratch.get(), k, m_splitsGH, (size_t)k * k, m_stream);
-	kern::sumSplits<T>(k, k, m_kkScratch.get(), k, m_splitsGH, (size_t)k * k, reinterpret_cast<T*>(part), k, m_stream);
-	if (haveRowSums) kern::finishPartialSums(k, ceilDiv(n, 64), reinterpret_cast<const float*>(m_rowSumPartials.get()), 1.f, part + (size_t)k * k, m_stream);
-	else tc::rowSums(m_tcR->plan, reinterpret_cast<const float*>(Hloc), n, m_ldH, part + (size_t)k * k, m_stream);
-	m_cfg.comm->allGatherPair(reinterpret_cast<const float*>(Hloc), m_Hfull.get(), m_ldH * n, part, m_statGath.get(), m_statLen, m_stream);
-	tc::splitTransposeH(k, N, m_Hfull.get(), m_ldH, m_HtHiFull.get(), m_HtLoFull.get(), m_ldHtFull, m_stream);
-	kern::sumGathered((unsigned)((size_t)k * k + k), G, m_statLen, m_statGath.get(), m_stat.get(), m_stream);
-	kern::finishStatsH(k, m_stat.get(), m_tcR->plan.center, reinterpret_cast<float*>(m_B.get()), m_tcR->plan.corrP, m_stream);
-	m_launches += 7;
+	if (comm != nullptr) {   // no rank is still iterating on the buffers that are rewritten below
+		synchronize();
+		comm->barrier();
+	}
+	float* W = reinterpret_cast<float*>(m_W[m_wCur].get()) + m_r0;
+	kern::splitTf32(m_mr, k, W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, m_ldW, m_stream);
+	const unsigned blocks = fused::updateW(m_mr, k, nullptr, nullptr, W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, nullptr, 0, 0, nullptr, nullptr, 0.f,
+	                                       m_statPartW.get(), false, m_stream);
+	fused::reducePush(m_peers, m_lay.statW, m_lay.statLen, m_statPartW.get(), blocks, k * k + k, 0.f, m_stream);
+	float* Hfull = reinterpret_cast<float*>(m_sym + m_lay.H);
+	const float* Hmine = reinterpret_cast<const float*>(m_H[m_hCur].get());
+	if (comm == nullptr) {
+		CUDA_CHECK(cudaMemcpyAsync(Hfull, Hmine, m_ldH * (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, m_stream));
+	} else {
+		CUDA_CHECK(cudaMemsetAsync(Hfull, 0, m_ldH * (size_t)N * sizeof(float), m_stream));
+		CUDA_CHECK(cudaMemcpyAsync(Hfull + m_ldH * (size_t)comm->columnOffset(), Hmine, m_ldH * (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, m_stream));
+		comm->allReduceSum(Hfull, m_ldH * (size_t)N, m_stream);   // every column has exactly one non-zero contribution
+	}
+	tc::splitTransposeH(k, N, Hfull, m_ldH, reinterpret_cast<float*>(m_sym + m_lay.HtHi), reinterpret_cast<float*>(m_sym + m_lay.HtLo), m_ldHtFull, m_stream);
+	tc::refreshCorrectionH(m_tc->plan, Hfull, m_ldH, m_stream);   // centring term of V H^T for the initial H (debugProducts; the iteration recomputes it)
+	m_launches += 6;
+	if (comm != nullptr) {
+		synchronize();
+		comm->barrier();
+	}
 }
 
 template <typename T>
-void Engine<T>::iterateMURowOwners(bool err) {
-	const unsigned n = m_cfg.n, k = m_cfg.k;
-	Communicator* comm = m_cfg.comm;
-	// ---- H <- H o (W^T V) / ((W^T W) H + eps) on the columns of this rank (MU.h:164-198); m_G is up to date
+void Engine<T>::iterateMUFused(bool err) {
+	const unsigned k = m_cfg.k;
+	tc::Plan& plan = m_tc->plan;
+	float* G = reinterpret_cast<float*>(m_G.get());
+	float* B = reinterpret_cast<float*>(m_B.get());
 	stamp("begin");
-	productWtV(m_W[m_wCur].get());
-	stamp("product W^T V (own columns)");
-	const T* N = m_Npart.get();
-	unsigned splits = m_splitsN;
-	const unsigned char* slots = m_slotsN;
-	const T* corr = m_corrN;
-	preReduceN(N, splits, slots, corr);
-	kern::updateH<T>(k, n, m_G.get(), m_H[m_hCur].get(), m_H[1 - m_hCur].get(), m_ldH, N, m_ldH, splits, m_strideN, m_eps,
-	                 err ? m_partN.get() : nullptr, nullptr, nullptr, m_ldHt, m_stream, slots, corr, m_rowSumPartials.get());
-	m_launches += 1;
-	m_hCur = 1 - m_hCur;
+	// ---- H <- H o (W^T V) / ((W^T W) H + eps)   (MU.h:164-198)
+	tc::gemmWtV(plan, reinterpret_cast<float*>(m_sym + m_lay.slots) + (size_t)m_route.slotBase * m_strideN, m_ldH, m_strideN, m_stream, &m_route);
+	stamp("product W^T V");
+	fused::prepH(m_peers, m_lay, m_ctl, k, plan.center, m_statSum.get(), G, m_inv.get(), plan.corrN, true, m_stream);
+	stamp("exchange, W statistics");
+	const unsigned blocksH = fused::updateH(m_peers, m_lay, k, m_c0, m_nOwn, m_colsPerRank, m_ldH, m_ldHtFull, m_slotsPerRank, plan.wtv.slotCount, G, m_inv.get(),
+	                                        plan.corrN, (float)m_eps, err ? reinterpret_cast<float*>(m_partN.get()) : nullptr, m_statPartH.get(), m_stream);
 	stamp("update H");
-	gatherH(true);
-	stamp("H statistics, all-gather, split");
+	fused::reducePush(m_peers, m_lay.statH, m_lay.statLen, m_statPartH.get(), blocksH, k * k + k, -1.f, m_stream);
+	fused::finishH(m_peers, m_lay, m_ctl, k, plan.center, B, plan.corrP, m_stream);
+	stamp("exchange, H statistics");
+	m_launches += 5;
 	if (err) {
-		kern::traceKK<T>(k, m_B.get(), m_G.get(), m_partK.get(), m_stream);                 // tr(HH^T W^T W) MU.h:203-216
+		kern::traceKK<T>(k, m_B.get(), m_G.get(), m_partK.get(), m_stream);                     // tr(HH^T W^T W) MU.h:203-216
 		m_launches += 1;
 	}
+	// ---- W <- W o (V H^T) / (W (H H^T) + eps), unit columns (MU.h:200-248)
+	if (!m_cfg.constantW) {
+		tc::gemmVHt(plan, m_PpartR.get(), m_ldPr, m_stridePr, m_stream);
+		stamp("product V H^T");
+		float* W = reinterpret_cast<float*>(m_W[m_wCur].get()) + m_r0;
+		const unsigned blocksW = fused::updateW(m_mr, k, B, m_inv.get(), W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, m_PpartR.get(), m_ldPr, m_stridePr,
+		                                        plan.vht.slotCount, plan.corrP, (float)m_eps, m_statPartW.get(), true, m_stream);
+		stamp("update W");
+		fused::reducePush(m_peers, m_lay.statW, m_lay.statLen, m_statPartW.get(), blocksW, k * k + k, 1.f, m_stream);
+		stamp("W statistics");
+		m_launches += 3;
+	}
+	if (err) resolveError(m_nOwn);
+}
 
-	// ---- W <- W o (V H^T) / (W (H H^T) + eps) on the rows of this rank (MU.h:200-248)
-	float* stat = m_stat.get();
-	tc::gemmVHt(m_tcR->plan, m_PpartR.get(), m_ldPr, m_stridePr, m_stream);
-	stamp("product V H^T (own rows)");
-	T* Wnext = m_W[1 - m_wCur].get();
-	const unsigned wBlocks = kern::updateW<T>(m_mr, k, m_B.get(), m_W[m_wCur].get() + m_r0, Wnext + m_r0, m_ldW, reinterpret_cast<const T*>(m_PpartR.get()),
-	                                          m_ldPr, m_splitsPr, m_stridePr, m_eps, m_colSqPartials.get(), m_stream, m_tcR->plan.vht.slotCount,
-	                                          reinterpret_cast<const T*>(m_tcR->plan.corrP), m_colSumPartials.get());
-	// statistics of the un-normalised block: Gram matrix (its diagonal = the column sums of squares) and column sums.
-	// They travel with the all-gather of the (still un-normalised) blocks in one NCCL group; every rank adds them up in
-	// rank order and the unpack kernel divides by the norms.
-	float* part = m_statPart.get();
-	kern::gemmTN<T>(m_mr, k, k, Wnext + m_r0, m_ldW, Wnext + m_r0, m_ldW, m_kkScratch.get(), k, m_splitsGWrows, (size_t)k * k, m_stream);
-	kern::sumSplits<T>(k, k, m_kkScratch.get(), k, m_splitsGWrows, (size_t)k * k, reinterpret_cast<T*>(part), k, m_stream);
-	kern::finishPartialSums(k, wBlocks, reinterpret_cast<const float*>(m_colSumPartials.get()), 1.f, part + (size_t)k * k, m_stream);
-	kern::scalePackRows(m_mr, m_mrPad, k, reinterpret_cast<const float*>(Wnext) + m_r0, m_ldW, nullptr, m_Wblk.get(), m_stream);
-	stamp("update W rows, statistics, pack");
-	comm->allGatherPair(m_Wblk.get(), m_Wgath.get(), (size_t)m_mrPad * k, part, m_statGath.get(), m_statLen, m_stream);
-	stamp("all-gather W + statistics");
-	kern::sumGathered((unsigned)((size_t)k * k + k), (unsigned)comm->worldSize(), m_statLen, m_statGath.get(), stat, m_stream);
-	kern::finishStats(k, stat, m_tc->plan.center, reinterpret_cast<float*>(m_G.get()), m_tc->plan.corrN, m_stream);
-	kern::unpackSplit(m_cfg.m, k, m_mrPad, m_Wgath.get(), reinterpret_cast<float*>(Wnext), m_ldW, m_Whi.get(), m_Wlo.get(), m_stream, stat);
-	stamp("norms, unpack W, hi/lo");
-	m_launches += 10;
-	m_wCur = 1 - m_wCur;
-	if (err) resolveError(n);
+// The best run's factors for the caller (MU.h:251-254): W with unit columns -- materialised here, the iterations never
+// do it -- gathered over the row blocks; H: the caller's columns.
+template <typename T>
+void Engine<T>::storeFused(const MatrixDescription<T>& hostW, const MatrixDescription<T>& hostH) {
+	Communicator* comm = (m_cfg.comm != nullptr && m_cfg.comm->worldSize() > 1) ? m_cfg.comm : nullptr;
+	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
+	synchronize();
+	if (comm != nullptr) comm->barrier();   // the statistics of every rank's last W update have landed
+	fused::prepH(m_peers, m_lay, m_ctl, k, m_tc->plan.center, m_statSum.get(), reinterpret_cast<float*>(m_Gsaved.get()), m_inv.get(), m_tc->plan.corrN, false,
+	             m_stream);
+	float* spare = reinterpret_cast<float*>(m_W[1 - m_wCur].get());
+	const float* W = reinterpret_cast<const float*>(m_W[m_wCur].get()) + m_r0;
+	if (comm == nullptr) {
+		fused::scaleRows(m, (unsigned)m_ldW, k, W, m_ldW, m_inv.get(), spare, m_stream);
+	} else {
+		DeviceBuffer<float> block, gathered;
+		block.allocate((size_t)m_mrPad * k);
+		gathered.allocate((size_t)m_mrPad * k * comm->worldSize());
+		fused::scaleRows(m_mr, m_mrPad, k, W, m_ldW, m_inv.get(), block.get(), m_stream);
+		comm->allGather(block.get(), gathered.get(), (size_t)m_mrPad * k, m_stream);
+		fused::unpackRows(m, k, m_mrPad, gathered.get(), spare, m_ldW, m_stream);
+		synchronize();
+	}
+	if (hostW.dense.values != nullptr)
+		CUDA_CHECK(cudaMemcpy2DAsync(hostW.dense.values, (size_t)hostW.dense.leadingDimension * sizeof(T), spare, m_ldW * sizeof(T), (size_t)m * sizeof(T), k,
+		                             cudaMemcpyDeviceToHost, m_stream));
+	const float* Hfull = reinterpret_cast<const float*>(m_sym + m_lay.H) + m_ldH * (size_t)(comm ? comm->columnOffset() : 0);
+	if (hostH.dense.values != nullptr)
+		CUDA_CHECK(cudaMemcpy2DAsync(hostH.dense.values, (size_t)hostH.dense.leadingDimension * sizeof(T), Hfull, m_ldH * sizeof(T), (size_t)k * sizeof(T), n,
+		                             cudaMemcpyDeviceToHost, m_stream));
+	synchronize();
+	checkDeviceFlags();
+}
+
+// A wait inside a kernel that gave up (a tensor-core barrier, tc_gemm.cu, or another rank's signal, fused.cu) leaves
+// garbage behind; the counters are read at the host's synchronisation points and turned into an error code.
+template <typename T>
+void Engine<T>::checkDeviceFlags() {
+	if (!m_useTC) {
+		synchronize();
+		return;
+	}
+	unsigned* host = m_hostFlags.get();
+	if (host == nullptr) {
+		m_hostFlags.allocate(2);
+		host = m_hostFlags.get();
+	}
+	host[0] = host[1] = 0;
+	CUDA_CHECK(cudaMemcpyAsync(host, tc::timeoutCounter(), sizeof(unsigned), cudaMemcpyDeviceToHost, m_stream));
+	if (m_ctl.error != nullptr) CUDA_CHECK(cudaMemcpyAsync(host + 1, m_ctl.error, sizeof(unsigned), cudaMemcpyDeviceToHost, m_stream));
+	synchronize();
+	if (host[0] != 0) throw EngineError(ResultType::ErrorExternalLibrary, "a barrier wait inside the tensor-core product timed out: the factors are not valid (NMFGPU_TC_DEBUG=1 reports where)");
+	if (host[1] != 0) throw EngineError(ResultType::ErrorExternalLibrary, "another rank did not answer within 10 s: the factors are not valid");
 }
 
 // ---- initial factors --------------------------------------------------------------------------------
@@ -504,6 +724,9 @@ void Engine<T>::randomH(unsigned seed) {
 template <typename T>
 void Engine<T>::meanColumnsW(unsigned seed) {
 	if (m_sparse) throw EngineError(ResultType::ErrorInvalidArgument, "MeanColumns initialisation needs the dense matrix (NMFGPU_SPARSE=0)");
+	// W is replicated: every rank would average columns of its own shard and start from a different W
+	if (m_cfg.comm != nullptr && m_cfg.comm->worldSize() > 1)
+		throw EngineError(ResultType::ErrorInvalidArgument, "MeanColumns initialisation is not available with column shards");
 	init::meanColumns<T>(m_cfg.m, m_cfg.n, m_cfg.k, m_V.get(), m_ldV, m_W[m_wCur].get(), m_ldW, seed, m_stream);
 }
 
@@ -528,29 +751,31 @@ void Engine<T>::hFromWtV(bool absolute) {
 		else kern::clampNonNegative<T>(k, n, m_H[m_hCur].get(), m_ldH, m_stream);
 		return;
 	}
-	const unsigned splits = kern::effectiveSplits(m, std::min(m_splitsN, 16u));
-	// m_Npart has room for m_splitsN slices; reuse them
-	const unsigned use = std::min(splits, m_splitsN);
-	kern::gemmTN<T>(m, k, n, m_W[m_wCur].get(), m_ldW, m_V.get(), m_ldV, m_Npart.get(), m_ldH, use, m_strideN, m_stream);
-	const unsigned eff = kern::effectiveSplits(m, use);
-	kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, eff, m_strideN, m_H[m_hCur].get(), m_ldH, m_stream);
+	// exact fp32 SIMT product into scratch slices of its own (the iteration's slot buffers belong to the tensor-core plan)
+	const unsigned eff = kern::effectiveSplits(m, std::min(16u, pickSplits(ceilDiv(k, 64) * ceilDiv(n, 64), m)));
+	const size_t stride = m_ldH * (size_t)n;
+	DeviceBuffer<T> slices;
+	slices.allocate(stride * eff);
+	kern::gemmTN<T>(m, k, n, m_W[m_wCur].get(), m_ldW, m_V.get(), m_ldV, slices.get(), m_ldH, eff, stride, m_stream);
+	kern::sumSplits<T>(k, n, slices.get(), m_ldH, eff, stride, m_H[m_hCur].get(), m_ldH, m_stream);
 	if (absolute) kern::absInPlace<T>(k, n, m_H[m_hCur].get(), m_ldH, m_stream);
 	else kern::clampNonNegative<T>(k, n, m_H[m_hCur].get(), m_ldH, m_stream);
+	synchronize();
 }
 
 template <typename T>
 void Engine<T>::finishInitialisation() {
 	if (!m_useTC) return;
+	if (m_fused) {
+		finishInitialisationFused();
+		return;
+	}
 	float* W = reinterpret_cast<float*>(m_W[m_wCur].get());
 	float* H = reinterpret_cast<float*>(m_H[m_hCur].get());
 	kern::splitTf32(m_cfg.m, m_cfg.k, W, m_ldW, m_Whi.get(), m_Wlo.get(), m_ldW, m_stream);
 	tc::splitTransposeH(m_cfg.k, m_cfg.n, H, m_ldH, m_HtHi.get(), m_HtLo.get(), m_ldHt, m_stream);
 	operandChangedW(m_W[m_wCur].get());
 	operandChangedH(m_H[m_hCur].get());
-	if (m_rowOwners) {   // what the iteration keeps up to date itself: W^T W and everything derived from the full H
-		gramW(m_W[m_wCur].get(), m_G.get());
-		gatherH(false);
-	}
 }
 
 // the tensor-core products read hi/lo copies of W resp. H; their rank-one centring terms follow the same values
@@ -811,6 +1036,13 @@ void Engine<T>::iterateLS(bool err) {
 				m_launches += 1;
 			}
 			multiplicativeW(m_B.get());
+		} else if (err) {
+			// constant W: the reference reads a V H^T that only the skipped W update would have written (GDCLS.h:260-264, stale
+			// deviceMR: undefined); the term is formed from the actual product instead
+			productVHt(H, m_ldH);
+			kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, Psum, m_ldW, m_stream, m_slotsP, true, m_corrP);
+			if (multi) m_cfg.comm->allReduceSum(Psum, m_strideP, m_stream);
+			m_launches += 1;
 		}
 		if (err) {
 			kern::columnDots<T>(m, k, Psum, m_ldW, m_W[m_wCur].get(), m_ldW, m_partN.get(), m_stream);
@@ -853,7 +1085,7 @@ void Engine<T>::resolveError(unsigned secondLen) {
 	const bool multi = m_cfg.comm && m_cfg.comm->worldSize() > 1;
 	CUDA_CHECK(cudaMemcpyAsync(m_hostSecond.get(), m_partN.get(), secondLen * sizeof(T), cudaMemcpyDeviceToHost, m_stream));
 	CUDA_CHECK(cudaMemcpyAsync(m_hostThird.get(), m_partK.get(), k * sizeof(T), cudaMemcpyDeviceToHost, m_stream));
-	synchronize();
+	checkDeviceFlags();   // synchronises the stream
 	T* second = m_hostSecond.get();
 	T* third = m_hostThird.get();
 	std::sort(second, second + secondLen);
@@ -889,7 +1121,7 @@ void Engine<T>::resolveError(unsigned secondLen) {
 template <typename T>
 void Engine<T>::iterate(bool computeError) {
 	switch (m_cfg.algorithm) {
-	case NmfAlgorithm::Multiplicative: m_rowOwners ? iterateMURowOwners(computeError) : iterateMU(computeError); break;
+	case NmfAlgorithm::Multiplicative: m_fused ? iterateMUFused(computeError) : iterateMU(computeError); break;
 	case NmfAlgorithm::nsNMF: iterateNsNMF(computeError); break;
 	case NmfAlgorithm::GDCLS:
 	case NmfAlgorithm::ALS:
@@ -907,7 +1139,9 @@ void Engine<T>::iterateNoError(unsigned count) {
 		const char* e = getenv("NMFGPU_GRAPHS");
 		return e == nullptr || atoi(e) != 0;
 	}();
-	if (graphs && count >= 6 && getenv("NMFGPU_TC_DEBUG") == nullptr) {
+	// (the in-stream profiler records events, which a capture cannot hold)
+	const bool collectivesOk = m_fused || m_cfg.comm == nullptr || m_cfg.comm->capturable();   // the fused iteration calls no collective
+	if (graphs && collectivesOk && count >= 4 && !m_profile && getenv("NMFGPU_TC_DEBUG") == nullptr) {
 		cudaGraphExec_t& exec = m_graphExec[m_wCur][m_hCur];
 		if (exec == nullptr) {
 			iterate(false);   // an eager pair first: lazily set kernel attributes must not happen inside the capture
@@ -945,6 +1179,10 @@ void Engine<T>::store(const MatrixDescription<T>& hostW, const MatrixDescription
 	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
 	if (hostW.format != StorageFormat::Dense || hostH.format != StorageFormat::Dense)
 		throw EngineError(ResultType::ErrorInvalidArgument, "output matrices must be dense");
+	if (m_fused) {
+		storeFused(hostW, hostH);
+		return;
+	}
 	const T* W = m_W[m_wCur].get();
 	if (m_cfg.algorithm == NmfAlgorithm::nsNMF) {  // the returned basis is W S (nsNMF.h:221-225)
 		kern::smoothRight<T>(m, k, W, m_ldW, m_smoothW.get(), m_ldW, (T)m_cfg.params.theta, m_stream);
@@ -962,6 +1200,40 @@ void Engine<T>::store(const MatrixDescription<T>& hostW, const MatrixDescription
 template <typename T>
 void Engine<T>::debugProducts(T* wtv, T* vht, float* msWtV, float* msVHt, cudaEvent_t e0, cudaEvent_t e1) {
 	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
+	if (m_fused) {
+		tc::Plan& plan = m_tc->plan;
+		if (m_peers.world > 1 && (wtv != nullptr || vht != nullptr))
+			throw EngineError(ResultType::ErrorInvalidArgument, "with row blocks over several ranks the products can only be timed");
+		if (wtv != nullptr || msWtV != nullptr) {
+			CUDA_CHECK(cudaEventRecord(e0, m_stream));
+			tc::gemmWtV(plan, reinterpret_cast<float*>(m_sym + m_lay.slots) + (size_t)m_route.slotBase * m_strideN, m_ldH, m_strideN, m_stream, &m_route);
+			CUDA_CHECK(cudaEventRecord(e1, m_stream));
+			CUDA_CHECK(cudaEventSynchronize(e1));
+			if (msWtV) CUDA_CHECK(cudaEventElapsedTime(msWtV, e0, e1));
+			if (wtv) {
+				float* sum = reinterpret_cast<float*>(m_H[1 - m_hCur].get());   // spare H buffer as the landing zone
+				fused::prepH(m_peers, m_lay, m_ctl, k, plan.center, m_statSum.get(), reinterpret_cast<float*>(m_Gsaved.get()), m_inv.get(), plan.corrN, false, m_stream);
+				fused::collectN(m_peers, m_lay, k, m_c0, m_nOwn, m_colsPerRank, m_ldH, m_slotsPerRank, plan.wtv.slotCount, m_inv.get(), plan.corrN, sum, m_ldH, m_stream);
+				CUDA_CHECK(cudaMemcpy2DAsync(wtv, (size_t)k * sizeof(T), sum, m_ldH * sizeof(T), (size_t)k * sizeof(T), n, cudaMemcpyDeviceToHost, m_stream));
+				synchronize();
+			}
+		}
+		if (vht != nullptr || msVHt != nullptr) {
+			CUDA_CHECK(cudaEventRecord(e0, m_stream));
+			tc::gemmVHt(plan, m_PpartR.get(), m_ldPr, m_stridePr, m_stream);
+			CUDA_CHECK(cudaEventRecord(e1, m_stream));
+			CUDA_CHECK(cudaEventSynchronize(e1));
+			if (msVHt) CUDA_CHECK(cudaEventElapsedTime(msVHt, e0, e1));
+			if (vht) {
+				T* sum = m_W[1 - m_wCur].get();
+				kern::sumSplits<T>(m, k, reinterpret_cast<const T*>(m_PpartR.get()), m_ldPr, m_splitsPr, m_stridePr, sum, m_ldW, m_stream, plan.vht.slotCount, true,
+				                   reinterpret_cast<const T*>(plan.corrP));
+				CUDA_CHECK(cudaMemcpy2DAsync(vht, (size_t)m * sizeof(T), sum, m_ldW * sizeof(T), (size_t)m * sizeof(T), k, cudaMemcpyDeviceToHost, m_stream));
+				synchronize();
+			}
+		}
+		return;
+	}
 	if (wtv != nullptr || msWtV != nullptr) {
 		CUDA_CHECK(cudaEventRecord(e0, m_stream));
 		productWtV(m_W[m_wCur].get());

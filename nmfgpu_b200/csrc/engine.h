@@ -14,12 +14,14 @@
 #include <vector>
 
 #include "common.h"
+#include "fused.h"
 #include "spmm.h"
+#include "tc_gemm.h"
 
 namespace nmfgpu {
 namespace b200 {
 
-class Communicator;  // dist.h: NCCL all-reduce over the column shards (nullptr = single GPU)
+class Communicator;  // dist.h: the ranks of a column-sharded run (nullptr = single GPU)
 
 enum class Precision {
 	Auto,     // fp32: tensor cores (3xTF32) when the shape allows, else SIMT; fp64: SIMT
@@ -79,7 +81,8 @@ public:
 	cudaStream_t stream() const { return m_stream; }
 	const EngineConfig& config() const { return m_cfg; }
 	bool usesTensorCores() const { return m_useTC; }
-	bool rowOwners() const { return m_rowOwners; }
+	bool rowBlocks() const { return m_fused && m_peers.world > 1; }   // column shards regrouped into row blocks (dist.h)
+	bool fusedMU() const { return m_fused; }
 	bool sparseExecution() const { return m_sparse; }
 	unsigned long long kernelLaunches() const { return m_launches; }
 	unsigned splitsWtV() const { return m_splitsN; }
@@ -96,9 +99,14 @@ public:
 
 private:
 	void iterateMU(bool err);
-	void iterateMURowOwners(bool err);
-	void setupRowOwners();                                     // dist.h: second dataflow for column shards (MU, tensor cores)
-	void gatherH(bool haveRowSums);                            // full H, its transposed split, H H^T and the centring term
+	// MU on the tensor-core path, one GPU or row blocks over several (fused.h, dist.h): eight launches per iteration
+	bool decideFused();
+	void setupFused();
+	void finishInitialisationFused();
+	void iterateMUFused(bool err);
+	void storeFused(const MatrixDescription<T>& hostW, const MatrixDescription<T>& hostH);
+	void releaseFused();
+	void checkDeviceFlags();                                   // barrier / peer waits that timed out surface as ErrorExternalLibrary
 	void iterateNsNMF(bool err);
 	void iterateLS(bool err);
 	void resolveError(unsigned secondLen);
@@ -161,13 +169,23 @@ private:
 	unsigned m_sparseBlocks = 1, m_sparseBlockRows = 0;
 	void decideSparse(const MatrixDescription<T>& V, bool vOnDevice);
 
-	// row-owner dataflow (dist.h): this rank also holds V[I, :] for its row block I = [m_r0, m_r0 + m_mr) and updates
-	// only those rows of W; m_tcR plans V[I, :] H^T over all columns
-	bool m_rowOwners = false;
-	unsigned m_r0 = 0, m_mr = 0, m_mrPad = 0, m_globalN = 0, m_splitsGHfull = 1, m_splitsGWrows = 1, m_splitsPr = 1;
-	size_t m_ldVr = 0, m_ldHtFull = 0, m_ldPr = 0, m_stridePr = 0, m_statLen = 0;
-	DeviceBuffer<float> m_Vr, m_Hfull, m_HtHiFull, m_HtLoFull, m_PpartR, m_stat, m_statPart, m_statGath, m_Wblk, m_Wgath;
-	std::unique_ptr<TcPlan> m_tcR;
+	// fused MU (fused.h).  This rank holds the row block V[I, :], I = [m_r0, m_r0 + m_mr) (all of V on one GPU), updates
+	// those rows of W, and the columns [m_c0, m_c0 + m_nOwn) of H (all of them on one GPU).  H, its transposed TF32 split,
+	// the partial products of W^T V and the k*k + k statistics live in the exchange buffer m_sym, which every other rank
+	// stores into directly.  W stays UN-NORMALISED between iterations: m_inv holds 1 / column norm, applied where W is read.
+	bool m_fused = false;
+	fused::Peers m_peers;
+	fused::Layout m_lay;
+	fused::Control m_ctl;
+	tc::PeerRoute m_route;
+	char* m_sym = nullptr;
+	std::vector<void*> m_peerPtrs;
+	unsigned m_r0 = 0, m_mr = 0, m_mrPad = 0, m_globalN = 0, m_colsPerRank = 0, m_c0 = 0, m_nOwn = 0, m_slotsPerRank = 1, m_splitsPr = 1;
+	size_t m_ldVr = 0, m_ldHtFull = 0, m_ldPr = 0, m_stridePr = 0;
+	DeviceBuffer<float> m_Vr, m_PpartR, m_statSum, m_inv, m_statPartH, m_statPartW;
+	DeviceBuffer<unsigned> m_ctlWords;
+	PinnedBuffer<unsigned> m_hostFlags;
+	const float* m_Vblock = nullptr;   // V[I, :]: m_Vr, or V itself on one GPU
 };
 
 }  // namespace b200

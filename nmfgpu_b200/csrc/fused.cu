@@ -1,0 +1,640 @@
+// fused.cu -- see fused.h.  sm_100a; SIMT fp32 with fixed-order reductions (bit-reproducible from run to run).
+#include "fused.h"
+
+#include <algorithm>
+#include <cstdint>
+
+#include "common.h"
+
+namespace nmfgpu {
+namespace b200 {
+namespace fused {
+
+namespace {
+
+// ---- system-scope flag protocol between ranks ---------------------------------------------------------------------
+// A rank signals by storing its epoch into a flag word that lives in the RECEIVER's exchange buffer (so waiting spins on
+// local memory).  The data the flag announces was written by earlier kernels of the same stream (peer stores); the
+// kernel boundary plus the system fence order it before the flag.
+__device__ __forceinline__ void storeReleaseSystem(unsigned* p, unsigned v) {
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned loadAcquireSystem(const unsigned* p) {
+	unsigned v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ unsigned long long globalTimer() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+
+// one thread: tell every rank "epoch e of this rank is out", then wait until every rank has said the same.
+// A rank that never answers (it failed) must not hang the GPU: after 10 s the wait is abandoned and *error set; the
+// host turns that into ErrorExternalLibrary at its next synchronisation point.
+__device__ void signalAndWait(const Peers& peers, size_t flagOffset, unsigned epoch, unsigned* error) {
+	__threadfence_system();
+	for (unsigned g = 0; g < peers.world; ++g)
+		storeReleaseSystem(reinterpret_cast<unsigned*>(peers.base[g] + flagOffset) + peers.rank, epoch);
+	const unsigned* mine = reinterpret_cast<const unsigned*>(peers.base[peers.rank] + flagOffset);
+	const unsigned long long t0 = globalTimer();
+	for (unsigned g = 0; g < peers.world; ++g) {
+		unsigned spins = 0;
+		// epochs only grow; "reached" must survive a wrap of the 32-bit counter
+		while ((int)(loadAcquireSystem(mine + g) - epoch) < 0) {
+			if ((++spins & 0x3FF) == 0 && globalTimer() - t0 > 10000000000ull) {
+				atomicExch(error, 1u);
+				return;
+			}
+		}
+	}
+	__threadfence_system();
+}
+
+__device__ __forceinline__ float tf32Hi(float x) {
+	uint32_t u;
+	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+	return __uint_as_float(u);
+}
+
+// ---- step 2 ------------------------------------------------------------------------------------------------------------
+// statSum = sum over the ranks of [W_un^T W_un, column sums of W_un, flag].  Unit columns (KernelNormalizeColumns.cu:52-58:
+// divide by the norm where the sum of squares is positive) are applied lazily: inv[c] = 1 / ||w_c||, so
+//   W^T W of the unit-column matrix  = statSum[i, j] * inv[i] * inv[j]
+//   centring term of W^T V           = center * column sum * inv
+// flag == 0 (initial factors, constant W): W is used as it is (the reference normalises only after a W update, MU.h:247).
+__global__ void __launch_bounds__(1024) prep_h_kernel(Peers peers, size_t flagsN, size_t statW, unsigned statLen, Control ctl, unsigned k, float center,
+                                                      float* __restrict__ statSum, float* __restrict__ G, float* __restrict__ inv,
+                                                      float* __restrict__ corrN, int signal) {
+	__shared__ float invS[128];
+	if (signal && threadIdx.x == 0) {
+		const unsigned e = *ctl.epoch + 1u;
+		*ctl.epoch = e;
+		if (peers.world > 1) signalAndWait(peers, flagsN, e, ctl.error);
+	}
+	__syncthreads();
+	const unsigned count = k * k + k + 1;
+	const float* local = reinterpret_cast<const float*>(peers.base[peers.rank] + statW);
+	for (unsigned idx = threadIdx.x; idx < count; idx += blockDim.x) {
+		float s = 0.f;
+		for (unsigned g = 0; g < peers.world; ++g) s += __ldcg(local + (size_t)g * statLen + idx);
+		statSum[idx] = s;
+	}
+	__syncthreads();
+	const bool normalise = statSum[k * k + k] > 0.5f;
+	for (unsigned c = threadIdx.x; c < k; c += blockDim.x) {
+		const float d = statSum[(size_t)c * k + c];
+		const float v = (normalise && d > 0.f) ? 1.0f / sqrtf(d) : 1.0f;
+		invS[c] = v;
+		inv[c] = v;
+		corrN[c] = center * (statSum[(size_t)k * k + c] * v);
+	}
+	__syncthreads();
+	for (unsigned idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
+		const unsigned r = idx % k, t = idx / k;
+		G[idx] = statSum[idx] * invS[r] * invS[t];
+	}
+}
+
+// ---- step 5 ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) finish_h_kernel(Peers peers, size_t flagsH, size_t statH, unsigned statLen, Control ctl, unsigned k, float center,
+                                                        float* __restrict__ B, float* __restrict__ corrP) {
+	if (peers.world > 1 && threadIdx.x == 0) signalAndWait(peers, flagsH, *ctl.epoch, ctl.error);
+	__syncthreads();
+	const float* local = reinterpret_cast<const float*>(peers.base[peers.rank] + statH);
+	for (unsigned idx = threadIdx.x; idx < k * k + k; idx += blockDim.x) {
+		float s = 0.f;
+		for (unsigned g = 0; g < peers.world; ++g) s += __ldcg(local + (size_t)g * statLen + idx);   // rank order: identical on every rank
+		if (idx < k * k) B[idx] = s;
+		else corrP[idx - k * k] = center * s;
+	}
+}
+
+// ---- step 3 ------------------------------------------------------------------------------------------------------------
+// A 64-column panel of the own columns per block.  D = G H is a register-tiled product out of shared memory (thread =
+// KP/16 rows x 4 columns); the numerators are the partial products of all ranks and slots, fetched two partials at a
+// time so that their latencies overlap; the multiplicative update (KernelMultiplyDivide.cu:42: multiply, then divide),
+// the residual term and the stores to every rank are the epilogue; then the Gram matrix of the new panel.
+template <int KP>
+__global__ void __launch_bounds__(256) update_h_fused(Peers peers, size_t oH, size_t oHtHi, size_t oHtLo, size_t oSlots, unsigned k, unsigned c0,
+                                                     unsigned nOwn, size_t ldh, size_t ldht, unsigned slotsPerRank, size_t slotStride,
+                                                     const unsigned char* __restrict__ slotCount, const float* __restrict__ G,
+                                                     const float* __restrict__ inv, const float* __restrict__ corrN, float eps,
+                                                     float* __restrict__ tracePartials, float* __restrict__ statPart) {
+	constexpr int COLS = 64, RPT = KP / 16, LDJ = COLS + 4;
+	const unsigned jl0 = blockIdx.x * COLS;   // first column of the panel: local index, global index
+	const unsigned j0 = c0 + jl0;
+	const unsigned splits = slotCount[j0 >> 7];
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float* Gs = reinterpret_cast<float*>(smem_raw);  // [KP t][KP r]: Gs[t*KP + r] = G[r + t*k]
+	float* Hs = Gs + KP * KP;                         // [KP t][LDJ]:  Hs[t*LDJ + j] = H[t, j0 + j]
+	const unsigned tid = threadIdx.x;
+	const float* Hloc = reinterpret_cast<const float*>(peers.base[peers.rank] + oH);
+	const float* Nloc = reinterpret_cast<const float*>(peers.base[peers.rank] + oSlots);
+	for (unsigned idx = tid; idx < KP * KP; idx += 256) {
+		const unsigned r = idx % KP, t = idx / KP;
+		Gs[idx] = (r < k && t < k) ? G[(size_t)t * k + r] : 0.f;
+	}
+	for (unsigned idx = tid; idx < COLS * KP; idx += 256) {
+		const unsigned t = idx % KP, j = idx / KP;
+		Hs[t * LDJ + j] = (jl0 + j < nOwn && t < k) ? Hloc[(size_t)(j0 + j) * ldh + t] : 0.f;
+	}
+	const unsigned rx = tid % 16, jx = tid / 16;      // rows rx*RPT.., columns jx*4..
+	float numv[RPT][4];
+#pragma unroll
+	for (int q = 0; q < 4; ++q)
+#pragma unroll
+		for (int i = 0; i < RPT; ++i) numv[i][q] = 0.f;
+	{
+		const unsigned total = peers.world * splits;
+		const bool vec = RPT % 4 == 0 && rx * RPT + RPT <= k;
+		auto slotOf = [&](unsigned p) {
+			const unsigned g = p / splits, sl = p - g * splits;
+			return Nloc + ((size_t)g * slotsPerRank + sl) * slotStride;
+		};
+		auto fetch = [&](const float* slot, float (&x)[RPT][4]) {
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const unsigned jl = jl0 + jx * 4 + q;
+				if (jl < nOwn) {
+					const float* src = slot + (size_t)jl * ldh + rx * RPT;
+					if (vec) {
+#pragma unroll
+						for (int i = 0; i < RPT; i += 4) {
+							const float4 v = __ldcg(reinterpret_cast<const float4*>(src + i));
+							x[i][q] = v.x; x[i + 1][q] = v.y; x[i + 2][q] = v.z; x[i + 3][q] = v.w;
+						}
+					} else {
+#pragma unroll
+						for (int i = 0; i < RPT; ++i) x[i][q] = (rx * RPT + i < k) ? __ldcg(src + i) : 0.f;
+					}
+				} else {
+#pragma unroll
+					for (int i = 0; i < RPT; ++i) x[i][q] = 0.f;
+				}
+			}
+		};
+		unsigned p = 0;
+		for (; p + 2 <= total; p += 2) {
+			float x0[RPT][4], x1[RPT][4];
+			fetch(slotOf(p), x0);
+			fetch(slotOf(p + 1), x1);
+#pragma unroll
+			for (int q = 0; q < 4; ++q)
+#pragma unroll
+				for (int i = 0; i < RPT; ++i) numv[i][q] = (numv[i][q] + x0[i][q]) + x1[i][q];
+		}
+		if (p < total) {
+			float x0[RPT][4];
+			fetch(slotOf(p), x0);
+#pragma unroll
+			for (int q = 0; q < 4; ++q)
+#pragma unroll
+				for (int i = 0; i < RPT; ++i) numv[i][q] += x0[i][q];
+		}
+	}
+	// N = diag(inv) (sum of the partials) + centring term: what W^T V of the unit-column matrix would have been
+#pragma unroll
+	for (int i = 0; i < RPT; ++i) {
+		const unsigned r = rx * RPT + i;
+		const float s = r < k ? inv[r] : 0.f, c = r < k ? corrN[r] : 0.f;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) numv[i][q] = (jl0 + jx * 4 + q < nOwn) ? fmaf(s, numv[i][q], c) : 0.f;
+	}
+	__syncthreads();
+	float acc[RPT][4];
+#pragma unroll
+	for (int i = 0; i < RPT; ++i)
+#pragma unroll
+		for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+#pragma unroll 8
+	for (int t = 0; t < KP; ++t) {
+		float a[RPT];
+		if (RPT % 4 == 0) {
+#pragma unroll
+			for (int i = 0; i < RPT; i += 4) {
+				const float4 g = *reinterpret_cast<const float4*>(Gs + t * KP + rx * RPT + i);
+				a[i] = g.x; a[i + 1] = g.y; a[i + 2] = g.z; a[i + 3] = g.w;
+			}
+		} else {
+#pragma unroll
+			for (int i = 0; i < RPT; ++i) a[i] = Gs[t * KP + rx * RPT + i];
+		}
+		const float4 b = *reinterpret_cast<const float4*>(Hs + t * LDJ + jx * 4);
+#pragma unroll
+		for (int i = 0; i < RPT; ++i) {
+			acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+			acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+			acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+			acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+		}
+	}
+	// epilogue: the new values replace the old ones in the H tile (every thread overwrites exactly the entries it read)
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		const unsigned jl = jl0 + jx * 4 + q;
+		float tr = 0.f;
+#pragma unroll
+		for (int i = 0; i < RPT; ++i) {
+			const unsigned r = rx * RPT + i;
+			const float num = numv[i][q];
+			const float v = Hs[r * LDJ + jx * 4 + q] * num / (acc[i][q] + eps);   // padding entries: 0 * 0 / eps = 0
+			Hs[r * LDJ + jx * 4 + q] = v;
+			tr = fmaf(v, num, tr);
+		}
+		tr += __shfl_xor_sync(0xffffffffu, tr, 1);
+		tr += __shfl_xor_sync(0xffffffffu, tr, 2);
+		tr += __shfl_xor_sync(0xffffffffu, tr, 4);
+		tr += __shfl_xor_sync(0xffffffffu, tr, 8);
+		if (tracePartials != nullptr && rx == 0 && jl < nOwn) tracePartials[jl] = tr;   // MU.h:194-197
+	}
+	__syncthreads();
+	// the new columns and their transposed TF32 split go to every rank: the all-gather of H is this kernel's epilogue
+	for (unsigned g = 0; g < peers.world; ++g) {
+		float* Hout = reinterpret_cast<float*>(peers.base[g] + oH);
+		for (unsigned idx = tid; idx < COLS * KP; idx += 256) {
+			const unsigned t = idx % KP, j = idx / KP;
+			if (jl0 + j < nOwn && t < k) Hout[(size_t)(j0 + j) * ldh + t] = Hs[t * LDJ + j];
+		}
+		float* HtHi = reinterpret_cast<float*>(peers.base[g] + oHtHi);
+		float* HtLo = reinterpret_cast<float*>(peers.base[g] + oHtLo);
+		for (unsigned idx = tid; idx < COLS * KP; idx += 256) {
+			const unsigned j = idx % COLS, r = idx / COLS;
+			if (r < k && jl0 + j < nOwn) {
+				const float v = Hs[r * LDJ + j];
+				const float hi = tf32Hi(v);
+				HtHi[(size_t)r * ldht + j0 + j] = hi;
+				HtLo[(size_t)r * ldht + j0 + j] = v - hi;
+			}
+		}
+	}
+	// statistics of the new panel: Gram matrix (thread = rows a + 16 i x rows b + 16 q: conflict-free float4 reads) and row sums
+	float* stat = statPart + (size_t)blockIdx.x * ((size_t)k * k + k);
+	{
+		const unsigned a = tid % 16, b = tid / 16;
+		float gr[RPT][RPT];
+#pragma unroll
+		for (int i = 0; i < RPT; ++i)
+#pragma unroll
+			for (int q = 0; q < RPT; ++q) gr[i][q] = 0.f;
+		for (int j = 0; j < COLS; j += 4) {
+			float4 av[RPT], bv[RPT];
+#pragma unroll
+			for (int i = 0; i < RPT; ++i) av[i] = *reinterpret_cast<const float4*>(Hs + (a + 16 * i) * LDJ + j);
+#pragma unroll
+			for (int q = 0; q < RPT; ++q) bv[q] = *reinterpret_cast<const float4*>(Hs + (b + 16 * q) * LDJ + j);
+#pragma unroll
+			for (int i = 0; i < RPT; ++i)
+#pragma unroll
+				for (int q = 0; q < RPT; ++q)
+					gr[i][q] = fmaf(av[i].w, bv[q].w, fmaf(av[i].z, bv[q].z, fmaf(av[i].y, bv[q].y, fmaf(av[i].x, bv[q].x, gr[i][q]))));
+		}
+#pragma unroll
+		for (int q = 0; q < RPT; ++q)
+#pragma unroll
+			for (int i = 0; i < RPT; ++i) {
+				const unsigned r1 = a + 16 * i, r2 = b + 16 * q;
+				if (r1 < k && r2 < k) stat[(size_t)r2 * k + r1] = gr[i][q];
+			}
+	}
+	{
+		const unsigned lane = tid % 32;
+		for (unsigned r = tid / 32; r < k; r += 8) {
+			float sum = Hs[r * LDJ + lane] + Hs[r * LDJ + 32 + lane];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+			if (lane == 0) stat[(size_t)k * k + r] = sum;
+		}
+	}
+}
+
+// ---- steps 4 and 8 -------------------------------------------------------------------------------------------------------
+// 32 entries x 8 block groups per CTA; every thread keeps four loads in flight; fixed summation order
+__global__ void __launch_bounds__(256) reduce_push_kernel(Peers peers, size_t dstOffset, unsigned statLen, const float* __restrict__ partials,
+                                                          unsigned blocks, unsigned count, float flag) {
+	__shared__ float red[8][33];
+	const unsigned lane = threadIdx.x % 32, grp = threadIdx.x / 32;
+	const unsigned x = blockIdx.x * 32 + lane;
+	float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+	if (x < count) {
+		unsigned b = grp;
+		for (; b + 24 < blocks; b += 32) {
+			a0 += partials[(size_t)b * count + x];
+			a1 += partials[(size_t)(b + 8) * count + x];
+			a2 += partials[(size_t)(b + 16) * count + x];
+			a3 += partials[(size_t)(b + 24) * count + x];
+		}
+		for (; b < blocks; b += 8) a0 += partials[(size_t)b * count + x];
+	}
+	red[grp][lane] = (a0 + a1) + (a2 + a3);
+	__syncthreads();
+	if (grp == 0 && x < count) {
+		const float v = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) + ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
+		for (unsigned g = 0; g < peers.world; ++g) reinterpret_cast<float*>(peers.base[g] + dstOffset)[(size_t)peers.rank * statLen + x] = v;
+	}
+	if (flag >= 0.f && blockIdx.x == 0 && threadIdx.x == 0)
+		for (unsigned g = 0; g < peers.world; ++g) reinterpret_cast<float*>(peers.base[g] + dstOffset)[(size_t)peers.rank * statLen + count] = flag;
+}
+
+// ---- step 7 ------------------------------------------------------------------------------------------------------------
+// A 128-row panel per block.  The tile is read with the column scale applied (unit columns of the previous update,
+// KernelNormalizeColumns.cu:52-58, without a pass of their own), D = W (H H^T) is a register-tiled product out of
+// shared memory (thread = 4 rows x KP/8 columns), the multiplicative update writes the new un-normalised rows and their
+// TF32 split (what the next W^T V reads) and leaves them in the tile; then the Gram matrix and the column sums of the
+// new rows -- the statistics the next prepH turns into norms, W^T W and the centring term.
+template <int KP, bool UPDATE>
+__global__ void __launch_bounds__(256) update_w_fused(unsigned m, unsigned k, const float* __restrict__ B, const float* __restrict__ inv, float* __restrict__ W,
+                                                     size_t ldw, float* __restrict__ Whi, float* __restrict__ Wlo, const float* __restrict__ Ppart, size_t ldp,
+                                                     size_t slotStride, const unsigned char* __restrict__ slotCount, const float* __restrict__ corr,
+                                                     float eps, float* __restrict__ statPart) {
+	constexpr int ROWS = 128, CPT = KP / 8, LDW = ROWS + 4, RPT = KP / 16;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float* Ws = reinterpret_cast<float*>(smem_raw);  // [KP t][LDW]: Ws[t*LDW + r] = W[i0 + r, t] (scaled)
+	float* Bs = Ws + KP * LDW;                        // [KP t][KP c]: Bs[t*KP + c] = B[t + c*k]
+	const unsigned tid = threadIdx.x;
+	const unsigned i0 = blockIdx.x * ROWS;
+	for (unsigned idx = tid; idx < KP * ROWS; idx += 256) {
+		const unsigned r = idx % ROWS, t = idx / ROWS;
+		float v = 0.f;
+		if (i0 + r < m && t < k) {
+			v = W[(size_t)t * ldw + i0 + r];
+			if (UPDATE) v *= inv[t];
+		}
+		Ws[t * LDW + r] = v;
+	}
+	if (UPDATE) {
+		const unsigned splits = slotCount != nullptr ? slotCount[blockIdx.x] : 1u;
+		for (unsigned idx = tid; idx < KP * KP; idx += 256) {
+			const unsigned c = idx % KP, t = idx / KP;
+			Bs[idx] = (c < k && t < k) ? B[(size_t)c * k + t] : 0.f;
+		}
+		__syncthreads();
+		const unsigned tx = tid % 32, ty = tid / 32;      // rows tx*4.., columns ty*CPT..
+		float acc[4][CPT];
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+#pragma unroll
+			for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+		for (int t = 0; t < KP; ++t) {
+			const float4 a = *reinterpret_cast<const float4*>(Ws + t * LDW + tx * 4);
+			float b[CPT];
+			if (CPT % 4 == 0) {
+#pragma unroll
+				for (int j = 0; j < CPT; j += 4) {
+					const float4 x = *reinterpret_cast<const float4*>(Bs + t * KP + ty * CPT + j);
+					b[j] = x.x; b[j + 1] = x.y; b[j + 2] = x.z; b[j + 3] = x.w;
+				}
+			} else {
+#pragma unroll
+				for (int j = 0; j < CPT; ++j) b[j] = Bs[t * KP + ty * CPT + j];
+			}
+#pragma unroll
+			for (int j = 0; j < CPT; ++j) {
+				acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
+				acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
+				acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
+				acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+			}
+		}
+		__syncthreads();   // every thread is done reading the old tile: it can now be overwritten with the new values
+		const unsigned r0 = i0 + tx * 4;
+#pragma unroll
+		for (int j = 0; j < CPT; ++j) {
+			const unsigned c = ty * CPT + j;
+			if (c < k) {   // warp-uniform
+				const float base = corr != nullptr ? corr[c] : 0.f;
+				float p[4] = {base, base, base, base};
+				if (r0 + 3 < m) {
+					for (unsigned sl = 0; sl < splits; ++sl) {
+						const float4 x = __ldcg(reinterpret_cast<const float4*>(Ppart + sl * slotStride + (size_t)c * ldp + r0));
+						p[0] += x.x; p[1] += x.y; p[2] += x.z; p[3] += x.w;
+					}
+				} else {
+					for (unsigned sl = 0; sl < splits; ++sl)
+						for (int i = 0; i < 4; ++i)
+							if (r0 + i < m) p[i] += __ldcg(Ppart + sl * slotStride + (size_t)c * ldp + r0 + i);
+				}
+				const float4 w = *reinterpret_cast<const float4*>(Ws + c * LDW + tx * 4);
+				float wn[4];
+				wn[0] = w.x * p[0] / (acc[0][j] + eps);   // KernelMultiplyDivide.cu:42: multiply first, then divide
+				wn[1] = w.y * p[1] / (acc[1][j] + eps);
+				wn[2] = w.z * p[2] / (acc[2][j] + eps);
+				wn[3] = w.w * p[3] / (acc[3][j] + eps);
+				float hi[4];
+				if (r0 + 3 < m) {
+#pragma unroll
+					for (int i = 0; i < 4; ++i) hi[i] = tf32Hi(wn[i]);
+					*reinterpret_cast<float4*>(W + (size_t)c * ldw + r0) = make_float4(wn[0], wn[1], wn[2], wn[3]);
+					*reinterpret_cast<float4*>(Whi + (size_t)c * ldw + r0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+					*reinterpret_cast<float4*>(Wlo + (size_t)c * ldw + r0) = make_float4(wn[0] - hi[0], wn[1] - hi[1], wn[2] - hi[2], wn[3] - hi[3]);
+				} else {
+					for (int i = 0; i < 4; ++i) {
+						if (r0 + i < m) {
+							const float h = tf32Hi(wn[i]);
+							W[(size_t)c * ldw + r0 + i] = wn[i];
+							Whi[(size_t)c * ldw + r0 + i] = h;
+							Wlo[(size_t)c * ldw + r0 + i] = wn[i] - h;
+						} else {
+							wn[i] = 0.f;
+						}
+					}
+				}
+				*reinterpret_cast<float4*>(Ws + c * LDW + tx * 4) = make_float4(wn[0], wn[1], wn[2], wn[3]);
+			}
+		}
+	}
+	__syncthreads();
+	// statistics of the rows now in the tile: Gram matrix (thread = columns a + 16 i x columns b + 16 q) and column sums
+	float* stat = statPart + (size_t)blockIdx.x * ((size_t)k * k + k);
+	{
+		const unsigned a = tid % 16, b = tid / 16;
+		float gr[RPT][RPT];
+#pragma unroll
+		for (int i = 0; i < RPT; ++i)
+#pragma unroll
+			for (int q = 0; q < RPT; ++q) gr[i][q] = 0.f;
+#pragma unroll 2
+		for (int r = 0; r < ROWS; r += 4) {
+			float4 av[RPT], bv[RPT];
+#pragma unroll
+			for (int i = 0; i < RPT; ++i) av[i] = *reinterpret_cast<const float4*>(Ws + (a + 16 * i) * LDW + r);
+#pragma unroll
+			for (int q = 0; q < RPT; ++q) bv[q] = *reinterpret_cast<const float4*>(Ws + (b + 16 * q) * LDW + r);
+#pragma unroll
+			for (int i = 0; i < RPT; ++i)
+#pragma unroll
+				for (int q = 0; q < RPT; ++q)
+					gr[i][q] = fmaf(av[i].w, bv[q].w, fmaf(av[i].z, bv[q].z, fmaf(av[i].y, bv[q].y, fmaf(av[i].x, bv[q].x, gr[i][q]))));
+		}
+#pragma unroll
+		for (int q = 0; q < RPT; ++q)
+#pragma unroll
+			for (int i = 0; i < RPT; ++i) {
+				const unsigned c1 = a + 16 * i, c2 = b + 16 * q;
+				if (c1 < k && c2 < k) stat[(size_t)c2 * k + c1] = gr[i][q];
+			}
+	}
+	{
+		const unsigned lane = tid % 32;
+		for (unsigned c = tid / 32; c < k; c += 8) {
+			const float* col = Ws + c * LDW;
+			float sum = (col[lane] + col[lane + 32]) + (col[lane + 64] + col[lane + 96]);
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+			if (lane == 0) stat[(size_t)k * k + c] = sum;
+		}
+	}
+}
+
+__global__ void scale_rows_kernel(unsigned rows, unsigned rowsPadded, unsigned k, const float* __restrict__ W, size_t ldw, const float* __restrict__ inv,
+                                  float* __restrict__ block) {
+	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned c = blockIdx.y;
+	if (r >= rowsPadded) return;
+	block[(size_t)c * rowsPadded + r] = r < rows ? W[(size_t)c * ldw + r] * inv[c] : 0.f;
+}
+
+__global__ void unpack_rows_kernel(unsigned m, unsigned k, unsigned rowsPadded, const float* __restrict__ gathered, float* __restrict__ W, size_t ldw) {
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned c = blockIdx.y;
+	if (i >= m) return;
+	const unsigned g = i / rowsPadded, r = i - g * rowsPadded;
+	W[(size_t)c * ldw + i] = gathered[((size_t)g * k + c) * rowsPadded + r];
+}
+
+// out[r + j * ldo] = inv[r] * (sum of the partials of W^T V of all ranks and slots) + corrN[r] for the own columns: the
+// numerator of the H update as a matrix (tests, bench)
+__global__ void collect_n_kernel(Peers peers, size_t oSlots, unsigned k, unsigned c0, unsigned nOwn, size_t ldh, unsigned slotsPerRank, size_t slotStride,
+                                 const unsigned char* __restrict__ slotCount, const float* __restrict__ inv, const float* __restrict__ corrN,
+                                 float* __restrict__ out, size_t ldo) {
+	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= k) return;
+	const float* Nloc = reinterpret_cast<const float*>(peers.base[peers.rank] + oSlots);
+	for (unsigned jl = blockIdx.y; jl < nOwn; jl += gridDim.y) {
+		const unsigned splits = slotCount[(c0 + jl) >> 7];
+		float s = 0.f;
+		for (unsigned g = 0; g < peers.world; ++g)
+			for (unsigned sl = 0; sl < splits; ++sl) s += __ldcg(Nloc + ((size_t)g * slotsPerRank + sl) * slotStride + (size_t)jl * ldh + r);
+		out[(size_t)jl * ldo + r] = fmaf(inv[r], s, corrN[r]);
+	}
+}
+
+template <int KP>
+constexpr size_t smemUpdateH() {
+	return sizeof(float) * ((size_t)KP * KP + (size_t)KP * (64 + 4));
+}
+template <int KP>
+constexpr size_t smemUpdateW() {
+	return sizeof(float) * ((size_t)KP * (128 + 4) + (size_t)KP * KP);
+}
+
+template <int KP>
+void configureRank() {
+	CUDA_CHECK(cudaFuncSetAttribute(update_h_fused<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemUpdateH<KP>()));
+	CUDA_CHECK(cudaFuncSetAttribute(update_w_fused<KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemUpdateW<KP>()));
+	CUDA_CHECK(cudaFuncSetAttribute(update_w_fused<KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemUpdateW<KP>()));
+}
+
+inline void launchCheck() { CUDA_CHECK(cudaGetLastError()); }
+
+}  // namespace
+
+void configure() {
+	configureRank<16>();
+	configureRank<32>();
+	configureRank<64>();
+	configureRank<128>();
+}
+
+void prepH(const Peers& peers, const Layout& lay, const Control& ctl, unsigned k, float center, float* statSum, float* G, float* inv, float* corrN,
+           bool signal, cudaStream_t stream) {
+	prep_h_kernel<<<1, 1024, 0, stream>>>(peers, lay.flagsN, lay.statW, lay.statLen, ctl, k, center, statSum, G, inv, corrN, signal ? 1 : 0);
+	launchCheck();
+}
+
+template <int KP>
+static unsigned launchUpdateH(const Peers& peers, const Layout& lay, unsigned k, unsigned c0, unsigned nOwn, unsigned colsPerRank, size_t ldh, size_t ldht,
+                              unsigned slotsPerRank, const unsigned char* slotCount, const float* G, const float* inv, const float* corrN, float eps,
+                              float* tracePartials, float* statPart, cudaStream_t stream) {
+	const unsigned blocks = ceilDiv(nOwn, 64);
+	if (blocks == 0) return 0;
+	update_h_fused<KP><<<blocks, 256, smemUpdateH<KP>(), stream>>>(peers, lay.H, lay.HtHi, lay.HtLo, lay.slots, k, c0, nOwn, ldh, ldht, slotsPerRank,
+	                                                               ldh * (size_t)colsPerRank, slotCount, G, inv, corrN, eps, tracePartials, statPart);
+	launchCheck();
+	return blocks;
+}
+
+unsigned updateH(const Peers& peers, const Layout& lay, unsigned k, unsigned c0, unsigned nOwn, unsigned colsPerRank, size_t ldh, size_t ldht,
+                 unsigned slotsPerRank, const unsigned char* slotCount, const float* G, const float* inv, const float* corrN, float eps,
+                 float* tracePartials, float* statPart, cudaStream_t stream) {
+#define NMF_ARGS peers, lay, k, c0, nOwn, colsPerRank, ldh, ldht, slotsPerRank, slotCount, G, inv, corrN, eps, tracePartials, statPart, stream
+	if (k <= 16) return launchUpdateH<16>(NMF_ARGS);
+	if (k <= 32) return launchUpdateH<32>(NMF_ARGS);
+	if (k <= 64) return launchUpdateH<64>(NMF_ARGS);
+	if (k <= 128) return launchUpdateH<128>(NMF_ARGS);
+#undef NMF_ARGS
+	throw EngineError(ResultType::ErrorInvalidArgument, "the fused MU kernels cover ranks up to 128");
+}
+
+void reducePush(const Peers& peers, size_t dstOffset, unsigned statLen, const float* partials, unsigned blocks, unsigned count, float flag,
+                cudaStream_t stream) {
+	reduce_push_kernel<<<ceilDiv(count, 32), 256, 0, stream>>>(peers, dstOffset, statLen, partials, blocks, count, flag);
+	launchCheck();
+}
+
+void finishH(const Peers& peers, const Layout& lay, const Control& ctl, unsigned k, float center, float* B, float* corrP, cudaStream_t stream) {
+	finish_h_kernel<<<1, 1024, 0, stream>>>(peers, lay.flagsH, lay.statH, lay.statLen, ctl, k, center, B, corrP);
+	launchCheck();
+}
+
+template <int KP>
+static unsigned launchUpdateW(unsigned rows, unsigned k, const float* B, const float* inv, float* W, size_t ldw, float* Whi, float* Wlo, const float* Ppart,
+                              size_t ldp, size_t slotStride, const unsigned char* slotCount, const float* corrP, float eps, float* statPart, bool update,
+                              cudaStream_t stream) {
+	const unsigned blocks = ceilDiv(rows, 128);
+	if (blocks == 0) return 0;
+	if (update)
+		update_w_fused<KP, true><<<blocks, 256, smemUpdateW<KP>(), stream>>>(rows, k, B, inv, W, ldw, Whi, Wlo, Ppart, ldp, slotStride, slotCount, corrP, eps, statPart);
+	else
+		update_w_fused<KP, false><<<blocks, 256, smemUpdateW<KP>(), stream>>>(rows, k, B, inv, W, ldw, Whi, Wlo, Ppart, ldp, slotStride, slotCount, corrP, eps, statPart);
+	launchCheck();
+	return blocks;
+}
+
+unsigned updateW(unsigned rows, unsigned k, const float* B, const float* inv, float* W, size_t ldw, float* Whi, float* Wlo, const float* Ppart,
+                 size_t ldp, size_t slotStride, const unsigned char* slotCount, const float* corrP, float eps, float* statPart, bool update,
+                 cudaStream_t stream) {
+#define NMF_ARGS rows, k, B, inv, W, ldw, Whi, Wlo, Ppart, ldp, slotStride, slotCount, corrP, eps, statPart, update, stream
+	if (k <= 16) return launchUpdateW<16>(NMF_ARGS);
+	if (k <= 32) return launchUpdateW<32>(NMF_ARGS);
+	if (k <= 64) return launchUpdateW<64>(NMF_ARGS);
+	if (k <= 128) return launchUpdateW<128>(NMF_ARGS);
+#undef NMF_ARGS
+	throw EngineError(ResultType::ErrorInvalidArgument, "the fused MU kernels cover ranks up to 128");
+}
+
+void collectN(const Peers& peers, const Layout& lay, unsigned k, unsigned c0, unsigned nOwn, unsigned colsPerRank, size_t ldh, unsigned slotsPerRank,
+              const unsigned char* slotCount, const float* inv, const float* corrN, float* out, size_t ldo, cudaStream_t stream) {
+	if (nOwn == 0) return;
+	dim3 grid(ceilDiv(k, 64), std::min(nOwn, 65535u));
+	collect_n_kernel<<<grid, 64, 0, stream>>>(peers, lay.slots, k, c0, nOwn, ldh, slotsPerRank, ldh * (size_t)colsPerRank, slotCount, inv, corrN, out, ldo);
+	launchCheck();
+}
+
+void scaleRows(unsigned rows, unsigned rowsPadded, unsigned k, const float* W, size_t ldw, const float* inv, float* block, cudaStream_t stream) {
+	dim3 grid(ceilDiv(rowsPadded, 256), k);
+	scale_rows_kernel<<<grid, 256, 0, stream>>>(rows, rowsPadded, k, W, ldw, inv, block);
+	launchCheck();
+}
+
+void unpackRows(unsigned m, unsigned k, unsigned rowsPadded, const float* gathered, float* W, size_t ldw, cudaStream_t stream) {
+	dim3 grid(ceilDiv(m, 256), k);
+	unpack_rows_kernel<<<grid, 256, 0, stream>>>(m, k, rowsPadded, gathered, W, ldw);
+	launchCheck();
+}
+
+}  // namespace fused
+}  // namespace b200
+}  // namespace nmfgpu

@@ -9,6 +9,7 @@
 //     row/column in registers, so each factor is read once and written once per update.
 #include "kernels.h"
 
+#include <algorithm>
 #include <cstdint>
 
 #include "common.h"
@@ -98,13 +99,15 @@ __global__ void sum_splits_kernel(unsigned rows, unsigned cols, const T* __restr
                                   size_t splitStride, T* __restrict__ dst, size_t lddst, const unsigned char* __restrict__ tileSlots,
                                   bool tilesAlongRows, const T* __restrict__ corr) {
 	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
-	const unsigned c = blockIdx.y;
-	if (r >= rows || c >= cols) return;
-	if (tileSlots != nullptr) splits = tileSlots[(tilesAlongRows ? r : c) >> 7];
-	// corr: rank-one term of a mean-centred tensor-core product (tc_gemm.h), indexed along the short (rank) dimension
-	T s = corr != nullptr ? corr[tilesAlongRows ? c : r] : T(0);
-	for (unsigned sp = 0; sp < splits; ++sp) s += src[sp * splitStride + (size_t)c * ldsrc + r];
-	dst[(size_t)c * lddst + r] = s;
+	if (r >= rows) return;
+	// the columns stride over gridDim.y (at most 65535 blocks: k x n matrices have more columns than that)
+	for (unsigned c = blockIdx.y; c < cols; c += gridDim.y) {
+		const unsigned count = tileSlots != nullptr ? tileSlots[(tilesAlongRows ? r : c) >> 7] : splits;
+		// corr: rank-one term of a mean-centred tensor-core product (tc_gemm.h), indexed along the short (rank) dimension
+		T s = corr != nullptr ? corr[tilesAlongRows ? c : r] : T(0);
+		for (unsigned sp = 0; sp < count; ++sp) s += src[sp * splitStride + (size_t)c * ldsrc + r];
+		dst[(size_t)c * lddst + r] = s;
+	}
 }
 
 // many partials of a small matrix (the split-K Gram products): 32 elements x 8 partial groups per block
@@ -326,8 +329,8 @@ __global__ void __launch_bounds__(256) finish_partial_sums_kernel(unsigned count
 template <typename T>
 __global__ void clamp_kernel(unsigned rows, unsigned cols, T* A, size_t lda) {
 	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
-	const unsigned c = blockIdx.y;
-	if (r < rows && c < cols) {
+	if (r >= rows) return;
+	for (unsigned c = blockIdx.y; c < cols; c += gridDim.y) {
 		const T v = A[(size_t)c * lda + r];
 		A[(size_t)c * lda + r] = v > T(0) ? v : T(0);
 	}
@@ -336,8 +339,8 @@ __global__ void clamp_kernel(unsigned rows, unsigned cols, T* A, size_t lda) {
 template <typename T>
 __global__ void abs_kernel(unsigned rows, unsigned cols, T* A, size_t lda) {
 	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
-	const unsigned c = blockIdx.y;
-	if (r < rows && c < cols) {
+	if (r >= rows) return;
+	for (unsigned c = blockIdx.y; c < cols; c += gridDim.y) {
 		const T v = A[(size_t)c * lda + r];
 		A[(size_t)c * lda + r] = v < T(0) ? -v : v;
 	}
@@ -814,10 +817,14 @@ inline void launchCheck() { CUDA_CHECK(cudaGetLastError()); }
 template <typename K>
 void allowSmem(K kernel, size_t bytes) {
 	if (bytes <= 48 * 1024) return;
-	static size_t allowed = 0;   // one instance per kernel type K
-	if (bytes <= allowed) return;
+	// the attribute belongs to the (kernel, device) pair: one cached size per device ordinal and kernel type K
+	static size_t allowed[64] = {};
+	int dev = 0;
+	CUDA_CHECK(cudaGetDevice(&dev));
+	size_t& mine = allowed[dev & 63];
+	if (bytes <= mine) return;
 	CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-	allowed = bytes;
+	mine = bytes;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -971,7 +978,7 @@ void sumSplits(unsigned rows, unsigned cols, const T* src, size_t ldsrc, unsigne
 		launchCheck();
 		return;
 	}
-	dim3 grid(ceilDiv(rows, 128), cols);
+	dim3 grid(ceilDiv(rows, 128), std::min(cols, 65535u));
 	sum_splits_kernel<T><<<grid, 128, 0, stream>>>(rows, cols, src, ldsrc, splits, splitStride, dst, lddst, tileSlots, tilesAlongRows, corr);
 	launchCheck();
 }
@@ -1024,14 +1031,14 @@ void updateH<double>(unsigned k, unsigned n, const double* G, const double* Hin,
 
 template <typename T>
 void clampNonNegative(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream_t stream) {
-	dim3 grid(ceilDiv(rows, 128), cols);
+	dim3 grid(ceilDiv(rows, 128), std::min(cols, 65535u));
 	clamp_kernel<T><<<grid, 128, 0, stream>>>(rows, cols, A, lda);
 	launchCheck();
 }
 
 template <typename T>
 void absInPlace(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream_t stream) {
-	dim3 grid(ceilDiv(rows, 128), cols);
+	dim3 grid(ceilDiv(rows, 128), std::min(cols, 65535u));
 	abs_kernel<T><<<grid, 128, 0, stream>>>(rows, cols, A, lda);
 	launchCheck();
 }

@@ -2,6 +2,7 @@
 // HBM-resident sessions, synthetic-workload helpers).  See that header for the contract.
 #include "../../include/nmfgpu_b200.h"
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -72,6 +73,11 @@ NMFGPU_EXPORT int nmfgpu_b200_set_precision(int mode) {
 NMFGPU_EXPORT int nmfgpu_b200_dist_unique_id(void* out128) {
 	if (out128 == nullptr) return static_cast<int>(ResultType::ErrorInvalidArgument);
 	return guarded([&] { Communicator::makeUniqueId(out128); });
+}
+
+NMFGPU_EXPORT int nmfgpu_b200_dist_local_unique_id(void* out128) {
+	if (out128 == nullptr) return static_cast<int>(ResultType::ErrorInvalidArgument);
+	return guarded([&] { Communicator::makeLocalUniqueId(out128); });
 }
 
 NMFGPU_EXPORT int nmfgpu_b200_dist_init(int rank, int world_size, const void* unique_id128) {
@@ -202,6 +208,31 @@ NMFGPU_EXPORT int nmfgpu_b200_session_time_iterations(nmfgpu_b200_session* s, un
 	});
 }
 
+// `iterations` iterations the way the reference's run loop issues them (SingleGpuDispatcher.cpp:171-201): the residual is
+// evaluated on every 10th iteration and on the last one -- partial sums to the host, sort, combine -- and that cost is
+// inside the events, as it is inside the reference's elapsedTime
+NMFGPU_EXPORT int nmfgpu_b200_session_time_run(nmfgpu_b200_session* s, unsigned iterations, float* milliseconds, double* frobenius) {
+	if (s == nullptr || milliseconds == nullptr || iterations == 0) return static_cast<int>(ResultType::ErrorInvalidArgument);
+	return guarded([&] {
+		cudaStream_t st = s->engine->stream();
+		CUDA_CHECK(cudaEventRecord(s->start, st));
+		unsigned it = 1;
+		while (it <= iterations) {
+			const unsigned nextError = std::min(iterations, (it + 9) / 10 * 10);
+			if (nextError > it) {
+				s->engine->iterateNoError(nextError - it);
+				it = nextError;
+			}
+			s->engine->iterate(true);
+			++it;
+		}
+		CUDA_CHECK(cudaEventRecord(s->stop, st));
+		CUDA_CHECK(cudaEventSynchronize(s->stop));
+		CUDA_CHECK(cudaEventElapsedTime(milliseconds, s->start, s->stop));
+		if (frobenius) *frobenius = s->engine->frobenius();
+	});
+}
+
 NMFGPU_EXPORT int nmfgpu_b200_session_products_f32(nmfgpu_b200_session* s, float* wtv, float* vht, float* ms_wtv, float* ms_vht) {
 	if (s == nullptr) return static_cast<int>(ResultType::ErrorInvalidArgument);
 	return guarded([&] { s->engine->debugProducts(wtv, vht, ms_wtv, ms_vht, s->start, s->stop); });
@@ -234,7 +265,7 @@ NMFGPU_EXPORT int nmfgpu_b200_session_get_info(nmfgpu_b200_session* s, nmfgpu_b2
 	info->ld_v = s->engine->ldV();
 	info->ld_w = s->engine->ldW();
 	info->ld_h = s->engine->ldH();
-	info->row_owners = s->engine->rowOwners() ? 1 : 0;
+	info->row_owners = s->engine->rowBlocks() ? 1 : 0;
 	return 0;
 }
 

@@ -1,6 +1,8 @@
 // spmm.cu -- see spmm.h.
 #include "spmm.h"
 
+#include <algorithm>
+
 #include <cub/cub.cuh>
 
 namespace nmfgpu {
@@ -157,16 +159,20 @@ __global__ void block_pointers_kernel(unsigned numMajor, unsigned blocks, unsign
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_kernel(unsigned rows, unsigned cols, const T* __restrict__ A, size_t lda, T* __restrict__ B, size_t ldb) {
 	__shared__ T tile[32][33];
-	const unsigned r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+	const unsigned r0 = blockIdx.x * 32;
 	const unsigned tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-	for (unsigned cc = ty; cc < 32; cc += 8) {
-		const unsigned r = r0 + tx, c = c0 + cc;
-		tile[cc][tx] = (r < rows && c < cols) ? A[(size_t)c * lda + r] : T(0);
-	}
-	__syncthreads();
-	for (unsigned rr = ty; rr < 32; rr += 8) {
-		const unsigned r = r0 + rr, c = c0 + tx;
-		if (r < rows && c < cols) B[(size_t)r * ldb + c] = tile[tx][rr];
+	// the column tiles stride over gridDim.y (at most 65535 blocks; a transposed k x m matrix has m / 32 of them)
+	for (unsigned c0 = blockIdx.y * 32; c0 < cols; c0 += gridDim.y * 32) {
+		for (unsigned cc = ty; cc < 32; cc += 8) {
+			const unsigned r = r0 + tx, c = c0 + cc;
+			tile[cc][tx] = (r < rows && c < cols) ? A[(size_t)c * lda + r] : T(0);
+		}
+		__syncthreads();
+		for (unsigned rr = ty; rr < 32; rr += 8) {
+			const unsigned r = r0 + rr, c = c0 + tx;
+			if (r < rows && c < cols) B[(size_t)r * ldb + c] = tile[tx][rr];
+		}
+		__syncthreads();
 	}
 }
 
@@ -288,7 +294,7 @@ void buildBlockPointers(unsigned numMajor, unsigned blocks, unsigned minorPerBlo
 template <typename T>
 void transpose(unsigned rows, unsigned cols, const T* A, size_t lda, T* B, size_t ldb, cudaStream_t stream) {
 	if (rows == 0 || cols == 0) return;
-	const dim3 grid(ceilDiv(rows, 32), ceilDiv(cols, 32));
+	const dim3 grid(ceilDiv(rows, 32), std::min(ceilDiv(cols, 32), 65535u));
 	transpose_kernel<T><<<grid, 256, 0, stream>>>(rows, cols, A, lda, B, ldb);
 	CUDA_CHECK(cudaGetLastError());
 }

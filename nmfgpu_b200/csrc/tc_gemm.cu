@@ -86,6 +86,11 @@ struct KParams {
 	alignas(64) CUtensorMap mapBhi;
 	alignas(64) CUtensorMap mapBlo;
 	float* out;
+	// W^T V over row blocks (dist.h): column r of the product belongs to rank r / colsPerRank and its partial goes into THAT
+	// rank's memory (peerOut[owner], NVLink peer stores), slot slotBase + s of the owner's slot array, at the owner's local
+	// column r - owner * colsPerRank.  Single GPU and V H^T: peerOut[0] = out, colsPerRank = 0xFFFFFFFF, slotBase = 0.
+	float* peerOut[8];
+	unsigned colsPerRank, slotBase;
 	unsigned long long* trace;   // optional timeline of CTA 0 (NMFGPU_TC_TRACE), nullptr otherwise
 	unsigned long long ldOut, slotStride, units;
 	unsigned rowsA, k, kp, tiles, stagesPerTile, flushStages, passes, grid;
@@ -555,7 +560,10 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 				const unsigned r = s.tile * PAIR_ROWS + (fwg + i * FLUSH_WGS) * TILE_ROWS + row;
 				if (r < p.rowsA) {
 					if (V_COLS_ARE_ROWS) {
-						float4* dst = reinterpret_cast<float4*>(out + (size_t)r * p.ldOut);     // column r of N: kp contiguous values
+						// column r of N: kp contiguous values, stored into the memory of the rank that owns the column
+						const unsigned owner = r / p.colsPerRank;
+						float4* dst = reinterpret_cast<float4*>(p.peerOut[owner] + (size_t)(p.slotBase + s.slot) * p.slotStride +
+						                                        (size_t)(r - owner * p.colsPerRank) * p.ldOut);
 #pragma unroll
 						for (int c = 0; c < KPM / 4; ++c)
 							if (c * 4 < (int)kp) dst[c] = make_float4(sum[i][4 * c], sum[i][4 * c + 1], sum[i][4 * c + 2], sum[i][4 * c + 3]);
@@ -754,15 +762,32 @@ void planProduct(Product& prod, unsigned rowsA, unsigned kdim, unsigned kp) {
 	CUDA_CHECK(cudaMemcpy(prod.slotCount, counts.data(), tiles128, cudaMemcpyHostToDevice));
 }
 
+// the opt-in to > 48 KB of dynamic shared memory is per device: set when a plan is made on a device (never inside a
+// stream capture), not cached process-wide
 template <int KPM, bool VC>
-void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, size_t ldOut, size_t slotStride, cudaStream_t stream) {
-	static bool configured = false;
+void configureOne() {
+	CUDA_CHECK(cudaFuncSetAttribute(tc_stream_gemm<KPM, VC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes<KPM>()));
+}
+void configureKernels() {
+	configureOne<64, true>();
+	configureOne<64, false>();
+	configureOne<128, true>();
+	configureOne<128, false>();
+}
+
+template <int KPM, bool VC>
+void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, size_t ldOut, size_t slotStride, cudaStream_t stream,
+            const PeerRoute* route = nullptr) {
 	const size_t smem = smemBytes<KPM>();
-	if (!configured) {
-		CUDA_CHECK(cudaFuncSetAttribute(tc_stream_gemm<KPM, VC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		configured = true;
-	}
 	KParams p;
+	for (int g = 0; g < 8; ++g) p.peerOut[g] = out;
+	p.colsPerRank = 0xFFFFFFFFu;
+	p.slotBase = 0;
+	if (route != nullptr && route->world > 1) {
+		for (unsigned g = 0; g < route->world && g < 8; ++g) p.peerOut[g] = route->base[g];
+		p.colsPerRank = route->colsPerRank;
+		p.slotBase = route->slotBase;
+	}
 	memcpy(&p.mapV, prod.mapV, 128);
 	memcpy(&p.mapBhi, prod.mapBhi, 128);
 	memcpy(&p.mapBlo, prod.mapBlo, 128);
@@ -907,7 +932,8 @@ bool shapeSupported(unsigned m, unsigned n, unsigned k, size_t ldV, size_t ldW) 
 }
 
 void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, size_t ldV, const float* Whi, const float* Wlo, size_t ldW,
-              const float* HtHi, const float* HtLo, size_t ldHt, bool singlePass, float center) {
+              const float* HtHi, const float* HtLo, size_t ldHt, bool singlePass, float center, unsigned reduceLenWtV) {
+	configureKernels();
 	plan.m = m;
 	plan.n = n;
 	plan.k = k;
@@ -934,7 +960,9 @@ void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, si
 		CUDA_CHECK(cudaMemset(plan.trace, 0, TRACE_STAGES * TRACE_EVENTS * sizeof(unsigned long long)));
 	}
 	// W^T V: A rows = columns of V, reduction over m
-	planProduct(plan.wtv, n, m, plan.kp);
+	// (reduceLenWtV > m: the work split of a longer reduction -- every rank of a row-block run uses the split of the
+	// largest block so that the slot layout is the same everywhere; the rows beyond m are TMA out-of-bounds zeros)
+	planProduct(plan.wtv, n, std::max(m, reduceLenWtV), plan.kp);
 	makeMap(plan.wtv.mapV, V, m, n, ldV, STAGE_K, TILE_ROWS, true);
 	makeMap(plan.wtv.mapBhi, Whi, m, k, ldW, STAGE_K, plan.kp, true);
 	makeMap(plan.wtv.mapBlo, Wlo, m, k, ldW, STAGE_K, plan.kp, true);
@@ -945,9 +973,15 @@ void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, si
 	makeMap(plan.vht.mapBlo, HtLo, n, k, ldHt, STAGE_K, plan.kp, true);
 }
 
-void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream) {
-	if (plan.kp <= 64) launch<64, true>(plan, plan.wtv, plan.n, Npart, ldn, slotStride, stream);
-	else launch<128, true>(plan, plan.wtv, plan.n, Npart, ldn, slotStride, stream);
+void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream, const PeerRoute* route) {
+	if (plan.kp <= 64) launch<64, true>(plan, plan.wtv, plan.n, Npart, ldn, slotStride, stream, route);
+	else launch<128, true>(plan, plan.wtv, plan.n, Npart, ldn, slotStride, stream, route);
+}
+
+const unsigned* timeoutCounter() {
+	void* p = nullptr;
+	CUDA_CHECK(cudaGetSymbolAddress(&p, g_waitTimeout));
+	return static_cast<const unsigned*>(p);
 }
 
 void gemmVHt(const Plan& plan, float* Ppart, size_t ldp, size_t slotStride, cudaStream_t stream) {

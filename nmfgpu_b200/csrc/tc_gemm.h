@@ -72,8 +72,9 @@ unsigned enumerateSegments(unsigned rowsA, unsigned kdim, unsigned kp, unsigned 
 // fp32 problem shapes the tensor-core path covers (others run the SIMT kernels)
 bool shapeSupported(unsigned m, unsigned n, unsigned k, size_t ldV, size_t ldW);
 
+// reduceLenWtV: plan the work split of W^T V for a reduction of that many rows (>= m; the surplus reads TMA zeros)
 void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, size_t ldV, const float* Whi, const float* Wlo, size_t ldW,
-              const float* HtHi, const float* HtLo, size_t ldHt, bool singlePass, float center);
+              const float* HtHi, const float* HtLo, size_t ldHt, bool singlePass, float center, unsigned reduceLenWtV = 0);
 
 // mean of all elements of V (fp64 accumulation; synchronises the stream)
 float meanOf(const float* V, unsigned m, unsigned n, size_t ldV, cudaStream_t stream);
@@ -87,8 +88,22 @@ void columnSums(Plan& plan, const float* W, unsigned rows, size_t ldW, float* ou
 // out[r] = sum of the first `cols` entries of row r of H (k x cols), r < plan.k
 void rowSums(Plan& plan, const float* H, unsigned cols, size_t ldH, float* out, cudaStream_t stream);
 
+// Where the partial products of W^T V go when the rows of V are spread over several ranks (dist.h): column r belongs to
+// rank r / colsPerRank; its partial is stored into base[owner] (that rank's slot array, mapped into this process) at slot
+// slotBase + s and local column r - owner * colsPerRank -- a reduce-scatter whose transfers leave the kernel tile by tile.
+struct PeerRoute {
+	unsigned world = 1;
+	unsigned colsPerRank = 0xFFFFFFFFu;
+	unsigned slotBase = 0;         // rank * (slots per rank)
+	float* base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
 // Npart + slot*slotStride (k x n, leading dimension ldn) receives the partial products of W^T V
-void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream);
+void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream, const PeerRoute* route = nullptr);
+
+// device address of the counter of tensor-core barrier waits that timed out (0 = healthy); the engine reads it with the
+// residual terms and turns a non-zero value into ErrorExternalLibrary instead of returning garbage with Success
+const unsigned* timeoutCounter();
 // Ppart + slot*slotStride (m x k, leading dimension ldp)
 void gemmVHt(const Plan& plan, float* Ppart, size_t ldp, size_t slotStride, cudaStream_t stream);
 

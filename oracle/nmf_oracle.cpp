@@ -517,6 +517,10 @@ static int run_impl(const OracleConfig& cfg, const T* V, long ldV, double* W, lo
 						}
 					}
 					normalize_columns(m, k, W, ldW);
+				} else if (check) {
+					// The reference reads a stale V H^T here when W is constant (GDCLS.h:260-264 uses deviceMR, which only the
+					// skipped W update writes): undefined.  The defined value of the same term is used instead.
+					gemm_v_ht(m, n, k, V, ldV, H, ldH, P.data(), m);
 				}
 				if (check) {
 					second.assign(k, 0.0);
