@@ -4,7 +4,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tools/dist_check.py
 
 Every rank first factorises the whole matrix on its own GPU (no communicator), then its column shard with
-NMFGPU_DIST_MODE = allreduce and with the default (row owners, dist.h).  W, the gathered H and the residual of both
+NMFGPU_DIST_MODE = allreduce and with the default (row blocks with peer-store exchange, dist.h), one process per GPU
+(NCCL + CUDA IPC transport; tests/test_sharded_gpu.py runs the same dataflows with the ranks as threads).  W, the gathered H and the residual of both
 sharded runs must agree with the single-GPU run within the tolerance of tests/test_parity_gpu.py.
 """
 import ctypes
@@ -42,7 +43,7 @@ for (m, n, k, iters) in shapes:
 
     c0, c1 = shard_columns(n, world, rank)
     uid = torch.zeros(128, dtype=torch.uint8)
-    for mode in ("allreduce", "rowowners"):
+    for mode in ("allreduce", "rowblocks"):
         os.environ["NMFGPU_DIST_MODE"] = mode
         if rank == 0:
             buf = (ctypes.c_ubyte * 128)()
@@ -64,7 +65,7 @@ for (m, n, k, iters) in shapes:
         eW = np.linalg.norm(W2 - W1) / np.linalg.norm(W1)
         eH = np.linalg.norm(H2 - H1[:, c0:c1]) / np.linalg.norm(H1[:, c0:c1])
         ef = abs(f2 - f1) / f1
-        ok = eW <= 2e-4 and eH <= 2e-4 and ef <= 2e-5
+        ok = eW <= 5e-5 and eH <= 5e-5 and ef <= 5e-6
         failed |= not ok
         print("rank %d %s %-9s W %.2e  H %.2e  residual %.9g vs %.9g (%.1e)  collectives %d  %s"
               % (rank, (m, n, k), mode, eW, eH, f2, f1, ef, calls, "ok" if ok else "MISMATCH"), flush=True)
