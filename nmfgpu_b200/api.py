@@ -348,7 +348,7 @@ class Library:
         if rc == ResultType.Success and summary.record_count() > 0:
             r = summary.record(summary.best_run())
             out.update(frobenius=r.frobenius, rmsd=r.rmsd, iterations=r.numIterations, elapsed=r.elapsedTime,
-                       best_run=summary.best_run())
+                       sparsity_w=r.sparsityW, sparsity_h=r.sparsityH, best_run=summary.best_run())
         summary.destroy()
         return out
 

@@ -136,7 +136,10 @@ ResultType computeKMeansImpl(KMeansDescription<T>& desc, KMeansSummary* /*summar
 	Context* ctx = t_context;
 	if (ctx == nullptr) return ResultType::ErrorNotInitialized;
 	// Interface.cpp:365-389
-	if (desc.numClusters == 0 || desc.numClusters >= desc.inputMatrix.columns) {
+	// column shards (include/nmfgpu_b200.h): the samples of this rank are a slice of the global sample set
+	Communicator* comm = (ctx->comm && ctx->comm->worldSize() > 1) ? ctx->comm.get() : nullptr;
+	const unsigned globalSamples = comm != nullptr ? comm->globalColumns() : desc.inputMatrix.columns;
+	if (desc.numClusters == 0 || desc.numClusters >= globalSamples) {
 		errorf(" [ERROR] Number of clusters must be smaller than number of samples in dataset!\n");
 		return ResultType::ErrorInvalidArgument;
 	}
@@ -175,7 +178,7 @@ ResultType computeKMeansImpl(KMeansDescription<T>& desc, KMeansSummary* /*summar
 		} else {
 			sparse::densify(desc.inputMatrix, data.get(), ld, stream);
 		}
-		kmeans::run<T>(m, n, k, data.get(), ld, centroids.get(), ld, membership.get(), desc.seed, desc.numIterations, desc.thresholdValue, stream, nullptr);
+		kmeans::run<T>(m, n, k, data.get(), ld, centroids.get(), ld, membership.get(), desc.seed, desc.numIterations, desc.thresholdValue, stream, comm);
 		CUDA_CHECK(cudaMemcpy2DAsync(desc.outputMatrixClusters.dense.values, (size_t)desc.outputMatrixClusters.dense.leadingDimension * sizeof(T), centroids.get(),
 		                             ld * sizeof(T), (size_t)m * sizeof(T), k, cudaMemcpyDeviceToHost, stream));
 		if (desc.outputMemberships != nullptr)

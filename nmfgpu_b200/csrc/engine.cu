@@ -234,6 +234,7 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	m_B.allocate((size_t)k * k);
 	m_qr.allocate((size_t)k * k + k);
 	m_inverse.allocate((size_t)k * k);
+	if (std::is_same<T, float>::value) m_qrWork.allocate(3 * (size_t)k * k + k);
 
 	// tensor-core eligibility: fp32, rank that fits one UMMA N, TMA-compatible strides
 	m_useTC = false;
@@ -463,7 +464,9 @@ void Engine<T>::setupFused() {
 	m_lay.H = at; at = align(at + m_ldH * (size_t)N * sizeof(float));
 	m_lay.HtHi = at; at = align(at + m_ldHtFull * (size_t)k * sizeof(float));
 	m_lay.HtLo = at; at = align(at + m_ldHtFull * (size_t)k * sizeof(float));
-	m_lay.slots = at; at = align(at + (size_t)G * m_slotsPerRank * m_ldH * m_colsPerRank * sizeof(float));
+	// partial products of W^T V: one GPU -- the stream-K slots of the tensor-core kernel; several -- one partial per rank
+	// for the own columns (the slots of the own row block stay in m_Nlocal, fused::pushN sends their sum to the owners)
+	m_lay.slots = at; at = align(at + (size_t)(comm ? G : m_slotsPerRank) * m_ldH * m_colsPerRank * sizeof(float));
 	m_lay.bytes = at;
 	m_sym = static_cast<char*>(pooledDeviceAlloc(m_lay.bytes));
 	CUDA_CHECK(cudaMemsetAsync(m_sym, 0, m_lay.bytes, m_stream));
@@ -474,10 +477,7 @@ void Engine<T>::setupFused() {
 	} else {
 		m_peers.base[0] = m_sym;
 	}
-	m_route.world = G;
-	m_route.colsPerRank = m_colsPerRank;
-	m_route.slotBase = rank * m_slotsPerRank;
-	for (unsigned g = 0; g < G; ++g) m_route.base[g] = reinterpret_cast<float*>(m_peers.base[g] + m_lay.slots);
+	if (comm != nullptr) m_Nlocal.allocate((size_t)m_slotsPerRank * m_ldH * N);
 
 	m_tc.reset(new TcPlan());
 	float* HtHi = reinterpret_cast<float*>(m_sym + m_lay.HtHi);
@@ -490,7 +490,7 @@ void Engine<T>::setupFused() {
 	m_slotsP = m_tc->plan.vht.slotCount;
 	m_corrN = reinterpret_cast<const T*>(m_tc->plan.corrN);
 	m_corrP = reinterpret_cast<const T*>(m_tc->plan.corrP);
-	m_strideN = m_ldH * m_colsPerRank;
+	m_strideN = m_ldH * (size_t)(comm ? N : m_colsPerRank);   // between the stream-K slots of W^T V
 	m_splitsPr = m_splitsP = m_tc->plan.vht.maxSlots;
 	m_ldPr = roundUp(m_mr, 32);
 	m_stridePr = m_ldPr * k;
@@ -498,7 +498,7 @@ void Engine<T>::setupFused() {
 
 	m_statSum.allocate(m_lay.statLen);
 	m_inv.allocate(roundUp(k, 32));
-	m_statPartH.allocate((size_t)std::max(1u, ceilDiv(m_nOwn, 64)) * ((size_t)k * k + k));
+	m_statPartH.allocate((size_t)std::max(1u, ceilDiv(m_nOwn, fused::panelColumnsH(m_nOwn))) * ((size_t)k * k + k));
 	m_statPartW.allocate((size_t)std::max(1u, ceilDiv(m_mr, 128)) * ((size_t)k * k + k));
 	m_ctlWords.allocate(32);
 	m_ctlWords.zero(m_stream);
@@ -560,6 +560,14 @@ void Engine<T>::finishInitialisationFused() {
 	}
 }
 
+// the stream-K slots of W^T V of the own row block: into the exchange buffer on one GPU (the H update reads them there),
+// into m_Nlocal over several ranks (pushN sums them on their way to the owners)
+template <typename T>
+void Engine<T>::productWtVFused() {
+	float* slots = m_peers.world > 1 ? m_Nlocal.get() : reinterpret_cast<float*>(m_sym + m_lay.slots);
+	tc::gemmWtV(m_tc->plan, slots, m_ldH, m_strideN, m_stream);
+}
+
 template <typename T>
 void Engine<T>::iterateMUFused(bool err) {
 	const unsigned k = m_cfg.k;
@@ -568,12 +576,19 @@ void Engine<T>::iterateMUFused(bool err) {
 	float* B = reinterpret_cast<float*>(m_B.get());
 	stamp("begin");
 	// ---- H <- H o (W^T V) / ((W^T W) H + eps)   (MU.h:164-198)
-	tc::gemmWtV(plan, reinterpret_cast<float*>(m_sym + m_lay.slots) + (size_t)m_route.slotBase * m_strideN, m_ldH, m_strideN, m_stream, &m_route);
+	const bool several = m_peers.world > 1;
+	productWtVFused();
 	stamp("product W^T V");
+	if (several) {
+		fused::pushN(m_peers, m_lay, plan.kp, m_globalN, m_colsPerRank, m_ldH, m_Nlocal.get(), m_strideN, plan.wtv.slotCount, m_stream);
+		stamp("partials to the owners");
+		m_launches += 1;
+	}
 	fused::prepH(m_peers, m_lay, m_ctl, k, plan.center, m_statSum.get(), G, m_inv.get(), plan.corrN, true, m_stream);
 	stamp("exchange, W statistics");
-	const unsigned blocksH = fused::updateH(m_peers, m_lay, k, m_c0, m_nOwn, m_colsPerRank, m_ldH, m_ldHtFull, m_slotsPerRank, plan.wtv.slotCount, G, m_inv.get(),
-	                                        plan.corrN, (float)m_eps, err ? reinterpret_cast<float*>(m_partN.get()) : nullptr, m_statPartH.get(), m_stream);
+	const unsigned blocksH = fused::updateH(m_peers, m_lay, k, m_c0, m_nOwn, m_colsPerRank, m_ldH, m_ldHtFull, several ? 1u : m_slotsPerRank,
+	                                        several ? nullptr : plan.wtv.slotCount, G, m_inv.get(), plan.corrN, (float)m_eps,
+	                                        err ? reinterpret_cast<float*>(m_partN.get()) : nullptr, m_statPartH.get(), m_stream);
 	stamp("update H");
 	fused::reducePush(m_peers, m_lay.statH, m_lay.statLen, m_statPartH.get(), blocksH, k * k + k, -1.f, m_stream);
 	fused::finishH(m_peers, m_lay, m_ctl, k, plan.center, B, plan.corrP, m_stream);
@@ -628,7 +643,9 @@ void Engine<T>::storeFused(const MatrixDescription<T>& hostW, const MatrixDescri
 	if (hostH.dense.values != nullptr)
 		CUDA_CHECK(cudaMemcpy2DAsync(hostH.dense.values, (size_t)hostH.dense.leadingDimension * sizeof(T), Hfull, m_ldH * sizeof(T), (size_t)k * sizeof(T), n,
 		                             cudaMemcpyDeviceToHost, m_stream));
+	measureSparsity(reinterpret_cast<const T*>(spare), m_ldW, reinterpret_cast<const T*>(Hfull), m_ldH);
 	synchronize();
+	finishSparsity();
 	checkDeviceFlags();
 }
 
@@ -1008,11 +1025,11 @@ void Engine<T>::iterateLS(bool err) {
 	if (algo == NmfAlgorithm::GDCLS) kern::addConstraint<T>(k, m_G.get(), T(0), (T)p.lambda, m_stream);
 	else if (algo == NmfAlgorithm::ACLS) kern::addConstraint<T>(k, m_G.get(), T(0), (T)p.lambdaH, m_stream);
 	else if (algo == NmfAlgorithm::AHCLS) kern::addConstraint<T>(k, m_G.get(), -(T)p.lambdaH, (T)p.lambdaH * betaH - (T)p.lambdaH, m_stream);
-	kern::qrFactor<T>(k, m_G.get(), m_qr.get(), m_stream);
+	kern::qrFactor<T>(k, m_G.get(), m_qr.get(), m_stream, n >= 4 * k ? m_inverse.get() : nullptr, m_qrWork.get());
 	productWtV(m_W[m_wCur].get());
 	T* H = m_H[m_hCur].get();
 	kern::sumSplits<T>(k, n, m_Npart.get(), m_ldH, m_splitsN, m_strideN, H, m_ldH, m_stream, m_slotsN, false, m_corrN);
-	kern::qrSolveClamp<T>(k, m_qr.get(), H, m_ldH, n, false, m_stream, m_inverse.get());
+	kern::qrSolveClamp<T>(k, m_qr.get(), H, m_ldH, n, false, m_stream, n >= 4 * k ? m_inverse.get() : nullptr);
 	m_launches += 4;
 	if (m_useTC) {
 		tc::splitTransposeH(k, n, reinterpret_cast<float*>(H), m_ldH, m_HtHi.get(), m_HtLo.get(), m_ldHt, m_stream);
@@ -1053,7 +1070,7 @@ void Engine<T>::iterateLS(bool err) {
 		if (!m_cfg.constantW) {
 			if (algo == NmfAlgorithm::ACLS) kern::addConstraint<T>(k, m_B.get(), T(0), (T)p.lambdaW, m_stream);
 			else if (algo == NmfAlgorithm::AHCLS) kern::addConstraint<T>(k, m_B.get(), -(T)p.lambdaW, (T)p.lambdaW * betaW - (T)p.lambdaW, m_stream);
-			kern::qrFactor<T>(k, m_B.get(), m_qr.get(), m_stream);
+			kern::qrFactor<T>(k, m_B.get(), m_qr.get(), m_stream, m >= 4 * k ? m_inverse.get() : nullptr, m_qrWork.get());
 			productVHt(H, m_ldH);
 			T* Wnext = m_W[1 - m_wCur].get();
 			kern::sumSplits<T>(m, k, m_Ppart.get(), m_ldW, m_splitsP, m_strideP, Wnext, m_ldW, m_stream, m_slotsP, true, m_corrP);
@@ -1063,7 +1080,7 @@ void Engine<T>::iterateLS(bool err) {
 				kern::columnDots<T>(m, k, m_W[m_wCur].get(), m_ldW, Wnext, m_ldW, m_partN.get(), m_stream);
 				m_launches += 1;
 			}
-			kern::qrSolveClamp<T>(k, m_qr.get(), Wnext, m_ldW, m, true, m_stream, m_inverse.get());
+			kern::qrSolveClamp<T>(k, m_qr.get(), Wnext, m_ldW, m, true, m_stream, m >= 4 * k ? m_inverse.get() : nullptr);
 			m_wCur = 1 - m_wCur;
 			const unsigned blocks = kern::columnSquares<T>(m, k, m_W[m_wCur].get(), m_ldW, m_colSqPartials.get(), m_stream);
 			m_launches += 2;
@@ -1194,7 +1211,49 @@ void Engine<T>::store(const MatrixDescription<T>& hostW, const MatrixDescription
 	if (hostH.dense.values != nullptr)
 		CUDA_CHECK(cudaMemcpy2DAsync(hostH.dense.values, (size_t)hostH.dense.leadingDimension * sizeof(T), m_H[m_hCur].get(), m_ldH * sizeof(T),
 		                             (size_t)k * sizeof(T), n, cudaMemcpyDeviceToHost, m_stream));
+	measureSparsity(W, m_ldW, m_H[m_hCur].get(), m_ldH);
 	synchronize();
+	finishSparsity();
+}
+
+// Sparseness of the factors that store() hands out (engine.h).  W is whole on every rank; H is this rank's columns, its two
+// norms are summed over the ranks.
+constexpr unsigned kSparsityBlocks = 128;
+template <typename T>
+void Engine<T>::measureSparsity(const T* W, size_t ldw, const T* H, size_t ldh) {
+	if (m_sparsityPartials.get() == nullptr) {
+		m_sparsityPartials.allocate(4 * kSparsityBlocks);
+		m_hostSparsity.allocate(4 * kSparsityBlocks);
+	}
+	kern::absSquareSums<T>(m_cfg.m, m_cfg.k, W, ldw, m_sparsityPartials.get(), kSparsityBlocks, m_stream);
+	kern::absSquareSums<T>(m_cfg.k, m_cfg.n, H, ldh, m_sparsityPartials.get() + 2 * kSparsityBlocks, kSparsityBlocks, m_stream);
+	CUDA_CHECK(cudaMemcpyAsync(m_hostSparsity.get(), m_sparsityPartials.get(), 4 * kSparsityBlocks * sizeof(double), cudaMemcpyDeviceToHost, m_stream));
+	m_launches += 2;
+}
+
+template <typename T>
+void Engine<T>::finishSparsity() {
+	const double* p = m_hostSparsity.get();
+	double sums[4] = {0.0, 0.0, 0.0, 0.0};   // |W|_1, |W|_2^2, |H|_1, |H|_2^2
+	for (unsigned f = 0; f < 2; ++f)
+		for (unsigned b = 0; b < kSparsityBlocks; ++b) {
+			sums[2 * f] += p[2 * (f * kSparsityBlocks + b)];
+			sums[2 * f + 1] += p[2 * (f * kSparsityBlocks + b) + 1];
+		}
+	double columns = (double)m_cfg.n;
+	if (m_cfg.comm != nullptr && m_cfg.comm->worldSize() > 1) {
+		sums[2] = m_cfg.comm->allReduceSumHost(sums[2]);
+		sums[3] = m_cfg.comm->allReduceSumHost(sums[3]);
+		columns = (double)m_cfg.comm->globalColumns();
+	}
+	auto hoyer = [](double l1, double l2sq, double count) {
+		if (count <= 1.0) return 0.0;
+		if (l2sq <= 0.0) return 1.0;   // nothing but zeros
+		const double root = std::sqrt(count);
+		return (root - l1 / std::sqrt(l2sq)) / (root - 1.0);
+	};
+	m_sparsityW = hoyer(sums[0], sums[1], (double)m_cfg.m * (double)m_cfg.k);
+	m_sparsityH = hoyer(sums[2], sums[3], (double)m_cfg.k * columns);
 }
 
 template <typename T>
@@ -1206,7 +1265,7 @@ void Engine<T>::debugProducts(T* wtv, T* vht, float* msWtV, float* msVHt, cudaEv
 			throw EngineError(ResultType::ErrorInvalidArgument, "with row blocks over several ranks the products can only be timed");
 		if (wtv != nullptr || msWtV != nullptr) {
 			CUDA_CHECK(cudaEventRecord(e0, m_stream));
-			tc::gemmWtV(plan, reinterpret_cast<float*>(m_sym + m_lay.slots) + (size_t)m_route.slotBase * m_strideN, m_ldH, m_strideN, m_stream, &m_route);
+			productWtVFused();
 			CUDA_CHECK(cudaEventRecord(e1, m_stream));
 			CUDA_CHECK(cudaEventSynchronize(e1));
 			if (msWtV) CUDA_CHECK(cudaEventElapsedTime(msWtV, e0, e1));

@@ -72,6 +72,11 @@ public:
 	void iterate(bool computeError);
 	double frobenius() const { return m_frobenius; }
 	double rmsd() const { return m_rmsd; }
+	// Hoyer sparseness (sqrt(N) - |x|_1 / |x|_2) / (sqrt(N) - 1) of the factors last handed out by store(), N = entries of
+	// the whole factor (all shards): 0 = all entries equal, 1 = a single non-zero.  The reference declares the two fields
+	// of ExecutionRecord and never writes them (SingleGpuDispatcher.cpp:217-222).
+	double sparsityW() const { return m_sparsityW; }
+	double sparsityH() const { return m_sparsityH; }
 
 	// enqueue `count` iterations without any error computation (bench / session API)
 	void iterateNoError(unsigned count);
@@ -104,12 +109,15 @@ private:
 	void setupFused();
 	void finishInitialisationFused();
 	void iterateMUFused(bool err);
+	void productWtVFused();
 	void storeFused(const MatrixDescription<T>& hostW, const MatrixDescription<T>& hostH);
 	void releaseFused();
 	void checkDeviceFlags();                                   // barrier / peer waits that timed out surface as ErrorExternalLibrary
 	void iterateNsNMF(bool err);
 	void iterateLS(bool err);
 	void resolveError(unsigned secondLen);
+	void measureSparsity(const T* W, size_t ldw, const T* H, size_t ldh);   // enqueues the reductions; finishSparsity() after the next synchronize()
+	void finishSparsity();
 
 	void gramW(const T* W, T* G);                              // G = W^T W
 	void gramH(const T* H, size_t ldh, T* B);                  // B = H H^T (all-reduced over shards)
@@ -140,6 +148,7 @@ private:
 	DeviceBuffer<T> m_V, m_W[2], m_H[2];
 	int m_wCur = 0, m_hCur = 0;
 	DeviceBuffer<T> m_G, m_Gsaved, m_B, m_kkScratch, m_qr, m_inverse;
+	DeviceBuffer<double> m_qrWork;   // fp32: the k x k inverse is formed in fp64 (kernels.h qrFactor)
 	DeviceBuffer<T> m_Npart, m_Ppart, m_smoothW, m_smoothH;
 	unsigned m_splitsN = 1, m_splitsP = 1, m_splitsGW = 1, m_splitsGH = 1;
 	size_t m_strideN = 0, m_strideP = 0;
@@ -153,6 +162,9 @@ private:
 	std::vector<T> m_vtvSorted;
 	double m_vtvSum = 0.0;
 	double m_frobenius = 0.0, m_rmsd = 0.0;
+	double m_sparsityW = 0.0, m_sparsityH = 0.0;
+	DeviceBuffer<double> m_sparsityPartials;
+	PinnedBuffer<double> m_hostSparsity;
 
 	// tensor-core operands (fp32 only): TF32 hi/lo splits of W (m x k) and of H^T (n x k, n contiguous)
 	DeviceBuffer<float> m_Whi, m_Wlo, m_HtHi, m_HtLo;
@@ -177,12 +189,11 @@ private:
 	fused::Peers m_peers;
 	fused::Layout m_lay;
 	fused::Control m_ctl;
-	tc::PeerRoute m_route;
 	char* m_sym = nullptr;
 	std::vector<void*> m_peerPtrs;
 	unsigned m_r0 = 0, m_mr = 0, m_mrPad = 0, m_globalN = 0, m_colsPerRank = 0, m_c0 = 0, m_nOwn = 0, m_slotsPerRank = 1, m_splitsPr = 1;
 	size_t m_ldVr = 0, m_ldHtFull = 0, m_ldPr = 0, m_stridePr = 0;
-	DeviceBuffer<float> m_Vr, m_PpartR, m_statSum, m_inv, m_statPartH, m_statPartW;
+	DeviceBuffer<float> m_Vr, m_Nlocal, m_PpartR, m_statSum, m_inv, m_statPartH, m_statPartW;
 	DeviceBuffer<unsigned> m_ctlWords;
 	PinnedBuffer<unsigned> m_hostFlags;
 	const float* m_Vblock = nullptr;   // V[I, :]: m_Vr, or V itself on one GPU

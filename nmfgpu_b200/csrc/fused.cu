@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -111,32 +112,64 @@ __global__ void __launch_bounds__(1024) finish_h_kernel(Peers peers, size_t flag
 	}
 }
 
+// ---- step 1b (several ranks) ---------------------------------------------------------------------------------------------
+// The partial product of the own row block, summed over its stream-K slots, goes to the rank that owns the columns: one
+// float4 per thread, a column (kp contiguous values) per group of threads, so the peer stores leave as whole 256-byte
+// rows.  (Stored straight from the tensor-core kernel -- one 16-byte piece per thread at a 256-byte stride -- the same
+// bytes cost 50 us over NVLink at 8 GPUs: W^T V 144 us against 93 us for the same launch without peers.)
+__global__ void __launch_bounds__(256) push_n_kernel(Peers peers, size_t oSlots, unsigned kp, unsigned N, unsigned colsPerRank, size_t ldh,
+                                                     const float* __restrict__ local, size_t localStride, const unsigned char* __restrict__ slotCount) {
+	const unsigned perCol = kp / 4;
+	const unsigned long long idx = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+	const unsigned j = (unsigned)(idx / perCol), q = (unsigned)(idx % perCol);
+	if (j >= N) return;
+	const unsigned splits = slotCount[j >> 7];
+	const float* src = local + (size_t)j * ldh + 4 * q;
+	float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+	unsigned sl = 0;
+	for (; sl + 2 <= splits; sl += 2) {
+		const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sl * localStride));
+		const float4 y = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sl + 1) * localStride));
+		a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+		b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
+	}
+	if (sl < splits) {
+		const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sl * localStride));
+		a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+	}
+	const unsigned owner = j / colsPerRank;
+	float* dst = reinterpret_cast<float*>(peers.base[owner] + oSlots) + ((size_t)peers.rank * colsPerRank + (j - owner * colsPerRank)) * ldh + 4 * q;
+	*reinterpret_cast<float4*>(dst) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
 // ---- step 3 ------------------------------------------------------------------------------------------------------------
-// A 64-column panel of the own columns per block.  D = G H is a register-tiled product out of shared memory (thread =
-// KP/16 rows x 4 columns); the numerators are the partial products of all ranks and slots, fetched two partials at a
-// time so that their latencies overlap; the multiplicative update (KernelMultiplyDivide.cu:42: multiply, then divide),
-// the residual term and the stores to every rank are the epilogue; then the Gram matrix of the new panel.
-template <int KP>
-__global__ void __launch_bounds__(256) update_h_fused(Peers peers, size_t oH, size_t oHtHi, size_t oHtLo, size_t oSlots, unsigned k, unsigned c0,
-                                                     unsigned nOwn, size_t ldh, size_t ldht, unsigned slotsPerRank, size_t slotStride,
-                                                     const unsigned char* __restrict__ slotCount, const float* __restrict__ G,
-                                                     const float* __restrict__ inv, const float* __restrict__ corrN, float eps,
-                                                     float* __restrict__ tracePartials, float* __restrict__ statPart) {
-	constexpr int COLS = 64, RPT = KP / 16, LDJ = COLS + 4;
+// A COLS-column panel of the own columns per block of 4 COLS threads (64 columns; 32 or 16 when the rank owns so few
+// columns that 64-wide panels would leave most SMs idle).  D = G H is a register-tiled product out of shared memory
+// (thread = KP/16 rows x 4 columns); the numerators are the partial products of all ranks and slots, fetched several
+// partials at a time so that their latencies overlap; the multiplicative update (KernelMultiplyDivide.cu:42: multiply,
+// then divide), the residual term and the stores to every rank are the epilogue; then the Gram matrix of the new panel.
+// slotCount == nullptr: one partial per rank (several ranks: fused::pushN has summed the slots).
+template <int KP, int COLS>
+__global__ void __launch_bounds__(COLS * 4) update_h_fused(Peers peers, size_t oH, size_t oHtHi, size_t oHtLo, size_t oSlots, unsigned k, unsigned c0,
+                                                          unsigned nOwn, size_t ldh, size_t ldht, unsigned slotsPerRank, size_t slotStride,
+                                                          const unsigned char* __restrict__ slotCount, const float* __restrict__ G,
+                                                          const float* __restrict__ inv, const float* __restrict__ corrN, float eps,
+                                                          float* __restrict__ tracePartials, float* __restrict__ statPart) {
+	constexpr int NT = COLS * 4, RPT = KP / 16, LDJ = COLS + 4;
 	const unsigned jl0 = blockIdx.x * COLS;   // first column of the panel: local index, global index
 	const unsigned j0 = c0 + jl0;
-	const unsigned splits = slotCount[j0 >> 7];
+	const unsigned splits = slotCount != nullptr ? slotCount[j0 >> 7] : 1u;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	float* Gs = reinterpret_cast<float*>(smem_raw);  // [KP t][KP r]: Gs[t*KP + r] = G[r + t*k]
 	float* Hs = Gs + KP * KP;                         // [KP t][LDJ]:  Hs[t*LDJ + j] = H[t, j0 + j]
 	const unsigned tid = threadIdx.x;
 	const float* Hloc = reinterpret_cast<const float*>(peers.base[peers.rank] + oH);
 	const float* Nloc = reinterpret_cast<const float*>(peers.base[peers.rank] + oSlots);
-	for (unsigned idx = tid; idx < KP * KP; idx += 256) {
+	for (unsigned idx = tid; idx < KP * KP; idx += NT) {
 		const unsigned r = idx % KP, t = idx / KP;
 		Gs[idx] = (r < k && t < k) ? G[(size_t)t * k + r] : 0.f;
 	}
-	for (unsigned idx = tid; idx < COLS * KP; idx += 256) {
+	for (unsigned idx = tid; idx < COLS * KP; idx += NT) {
 		const unsigned t = idx % KP, j = idx / KP;
 		Hs[t * LDJ + j] = (jl0 + j < nOwn && t < k) ? Hloc[(size_t)(j0 + j) * ldh + t] : 0.f;
 	}
@@ -175,17 +208,20 @@ __global__ void __launch_bounds__(256) update_h_fused(Peers peers, size_t oH, si
 				}
 			}
 		};
+		constexpr int BATCH = RPT <= 4 ? 4 : 2;   // partials in flight per thread
 		unsigned p = 0;
-		for (; p + 2 <= total; p += 2) {
-			float x0[RPT][4], x1[RPT][4];
-			fetch(slotOf(p), x0);
-			fetch(slotOf(p + 1), x1);
+		for (; p + BATCH <= total; p += BATCH) {
+			float x[BATCH][RPT][4];
 #pragma unroll
-			for (int q = 0; q < 4; ++q)
+			for (int b = 0; b < BATCH; ++b) fetch(slotOf(p + b), x[b]);
 #pragma unroll
-				for (int i = 0; i < RPT; ++i) numv[i][q] = (numv[i][q] + x0[i][q]) + x1[i][q];
+			for (int b = 0; b < BATCH; ++b)
+#pragma unroll
+				for (int q = 0; q < 4; ++q)
+#pragma unroll
+					for (int i = 0; i < RPT; ++i) numv[i][q] += x[b][i][q];
 		}
-		if (p < total) {
+		for (; p < total; ++p) {
 			float x0[RPT][4];
 			fetch(slotOf(p), x0);
 #pragma unroll
@@ -253,13 +289,13 @@ __global__ void __launch_bounds__(256) update_h_fused(Peers peers, size_t oH, si
 	// the new columns and their transposed TF32 split go to every rank: the all-gather of H is this kernel's epilogue
 	for (unsigned g = 0; g < peers.world; ++g) {
 		float* Hout = reinterpret_cast<float*>(peers.base[g] + oH);
-		for (unsigned idx = tid; idx < COLS * KP; idx += 256) {
+		for (unsigned idx = tid; idx < COLS * KP; idx += NT) {
 			const unsigned t = idx % KP, j = idx / KP;
 			if (jl0 + j < nOwn && t < k) Hout[(size_t)(j0 + j) * ldh + t] = Hs[t * LDJ + j];
 		}
 		float* HtHi = reinterpret_cast<float*>(peers.base[g] + oHtHi);
 		float* HtLo = reinterpret_cast<float*>(peers.base[g] + oHtLo);
-		for (unsigned idx = tid; idx < COLS * KP; idx += 256) {
+		for (unsigned idx = tid; idx < COLS * KP; idx += NT) {
 			const unsigned j = idx % COLS, r = idx / COLS;
 			if (r < k && jl0 + j < nOwn) {
 				const float v = Hs[r * LDJ + j];
@@ -269,39 +305,42 @@ __global__ void __launch_bounds__(256) update_h_fused(Peers peers, size_t oH, si
 			}
 		}
 	}
-	// statistics of the new panel: Gram matrix (thread = rows a + 16 i x rows b + 16 q: conflict-free float4 reads) and row sums
+	// statistics of the new panel: Gram matrix (thread = rows a + 16 i x rows b + BG q: conflict-free float4 reads) and row sums
 	float* stat = statPart + (size_t)blockIdx.x * ((size_t)k * k + k);
 	{
+		constexpr int BG = NT / 16, QN = KP / BG, QB = QN > 8 ? 8 : QN;
 		const unsigned a = tid % 16, b = tid / 16;
-		float gr[RPT][RPT];
-#pragma unroll
-		for (int i = 0; i < RPT; ++i)
-#pragma unroll
-			for (int q = 0; q < RPT; ++q) gr[i][q] = 0.f;
-		for (int j = 0; j < COLS; j += 4) {
-			float4 av[RPT], bv[RPT];
-#pragma unroll
-			for (int i = 0; i < RPT; ++i) av[i] = *reinterpret_cast<const float4*>(Hs + (a + 16 * i) * LDJ + j);
-#pragma unroll
-			for (int q = 0; q < RPT; ++q) bv[q] = *reinterpret_cast<const float4*>(Hs + (b + 16 * q) * LDJ + j);
+		for (int q0 = 0; q0 < QN; q0 += QB) {
+			float gr[RPT][QB];
 #pragma unroll
 			for (int i = 0; i < RPT; ++i)
 #pragma unroll
-				for (int q = 0; q < RPT; ++q)
-					gr[i][q] = fmaf(av[i].w, bv[q].w, fmaf(av[i].z, bv[q].z, fmaf(av[i].y, bv[q].y, fmaf(av[i].x, bv[q].x, gr[i][q]))));
-		}
+				for (int q = 0; q < QB; ++q) gr[i][q] = 0.f;
+			for (int j = 0; j < COLS; j += 4) {
+				float4 av[RPT];
 #pragma unroll
-		for (int q = 0; q < RPT; ++q)
+				for (int i = 0; i < RPT; ++i) av[i] = *reinterpret_cast<const float4*>(Hs + (a + 16 * i) * LDJ + j);
 #pragma unroll
-			for (int i = 0; i < RPT; ++i) {
-				const unsigned r1 = a + 16 * i, r2 = b + 16 * q;
-				if (r1 < k && r2 < k) stat[(size_t)r2 * k + r1] = gr[i][q];
+				for (int q = 0; q < QB; ++q) {
+					const float4 bv = *reinterpret_cast<const float4*>(Hs + (b + BG * (q0 + q)) * LDJ + j);
+#pragma unroll
+					for (int i = 0; i < RPT; ++i) gr[i][q] = fmaf(av[i].w, bv.w, fmaf(av[i].z, bv.z, fmaf(av[i].y, bv.y, fmaf(av[i].x, bv.x, gr[i][q]))));
+				}
 			}
+#pragma unroll
+			for (int q = 0; q < QB; ++q)
+#pragma unroll
+				for (int i = 0; i < RPT; ++i) {
+					const unsigned r1 = a + 16 * i, r2 = b + BG * (q0 + q);
+					if (r1 < k && r2 < k) stat[(size_t)r2 * k + r1] = gr[i][q];
+				}
+		}
 	}
 	{
 		const unsigned lane = tid % 32;
-		for (unsigned r = tid / 32; r < k; r += 8) {
-			float sum = Hs[r * LDJ + lane] + Hs[r * LDJ + 32 + lane];
+		for (unsigned r = tid / 32; r < k; r += NT / 32) {
+			float sum = 0.f;
+			for (unsigned j = lane; j < COLS; j += 32) sum += Hs[r * LDJ + j];
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
 			if (lane == 0) stat[(size_t)k * k + r] = sum;
@@ -513,7 +552,7 @@ __global__ void collect_n_kernel(Peers peers, size_t oSlots, unsigned k, unsigne
 	if (r >= k) return;
 	const float* Nloc = reinterpret_cast<const float*>(peers.base[peers.rank] + oSlots);
 	for (unsigned jl = blockIdx.y; jl < nOwn; jl += gridDim.y) {
-		const unsigned splits = slotCount[(c0 + jl) >> 7];
+		const unsigned splits = slotCount != nullptr ? slotCount[(c0 + jl) >> 7] : 1u;
 		float s = 0.f;
 		for (unsigned g = 0; g < peers.world; ++g)
 			for (unsigned sl = 0; sl < splits; ++sl) s += __ldcg(Nloc + ((size_t)g * slotsPerRank + sl) * slotStride + (size_t)jl * ldh + r);
@@ -521,9 +560,9 @@ __global__ void collect_n_kernel(Peers peers, size_t oSlots, unsigned k, unsigne
 	}
 }
 
-template <int KP>
+template <int KP, int COLS>
 constexpr size_t smemUpdateH() {
-	return sizeof(float) * ((size_t)KP * KP + (size_t)KP * (64 + 4));
+	return sizeof(float) * ((size_t)KP * KP + (size_t)KP * (COLS + 4));
 }
 template <int KP>
 constexpr size_t smemUpdateW() {
@@ -532,12 +571,14 @@ constexpr size_t smemUpdateW() {
 
 template <int KP>
 void configureRank() {
-	CUDA_CHECK(cudaFuncSetAttribute(update_h_fused<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemUpdateH<KP>()));
+	CUDA_CHECK(cudaFuncSetAttribute(update_h_fused<KP, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemUpdateH<KP, 64>()));
+	CUDA_CHECK(cudaFuncSetAttribute(update_h_fused<KP, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemUpdateH<KP, 32>()));
+	CUDA_CHECK(cudaFuncSetAttribute(update_h_fused<KP, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemUpdateH<KP, 16>()));
 	CUDA_CHECK(cudaFuncSetAttribute(update_w_fused<KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemUpdateW<KP>()));
 	CUDA_CHECK(cudaFuncSetAttribute(update_w_fused<KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemUpdateW<KP>()));
 }
 
-inline void launchCheck() { CUDA_CHECK(cudaGetLastError()); }
+#define launchCheck() CUDA_CHECK(cudaGetLastError())   // a macro: the message names the launch site
 
 }  // namespace
 
@@ -554,16 +595,41 @@ void prepH(const Peers& peers, const Layout& lay, const Control& ctl, unsigned k
 	launchCheck();
 }
 
+template <int KP, int COLS>
+static unsigned launchUpdateHCols(const Peers& peers, const Layout& lay, unsigned k, unsigned c0, unsigned nOwn, unsigned colsPerRank, size_t ldh, size_t ldht,
+                                  unsigned slotsPerRank, const unsigned char* slotCount, const float* G, const float* inv, const float* corrN, float eps,
+                                  float* tracePartials, float* statPart, cudaStream_t stream) {
+	const unsigned blocks = ceilDiv(nOwn, COLS);
+	update_h_fused<KP, COLS><<<blocks, COLS * 4, smemUpdateH<KP, COLS>(), stream>>>(peers, lay.H, lay.HtHi, lay.HtLo, lay.slots, k, c0, nOwn, ldh, ldht,
+	                                                                                 slotsPerRank, ldh * (size_t)colsPerRank, slotCount, G, inv, corrN, eps,
+	                                                                                 tracePartials, statPart);
+	launchCheck();
+	return blocks;
+}
+
+// panel width: 64 columns unless that leaves more than half of the SMs without a block (a rank of an 8-GPU run owns
+// 1 280 of 10 000 columns: 20 panels of 64 took 56 us, latency-bound)
+unsigned panelColumnsH(unsigned nOwn) {
+	static const unsigned forced = [] {
+		const char* e = getenv("NMFGPU_UPDATE_H_COLS");   // study knob
+		return e != nullptr ? (unsigned)atoi(e) : 0u;
+	}();
+	if (forced == 16 || forced == 32 || forced == 64) return forced;
+	return ceilDiv(nOwn, 64) >= 74 ? 64 : 32;   // measured on 1 280 own columns: 64 -> 29 us, 32 -> 24.6 us, 16 -> 30 us
+}
+
 template <int KP>
 static unsigned launchUpdateH(const Peers& peers, const Layout& lay, unsigned k, unsigned c0, unsigned nOwn, unsigned colsPerRank, size_t ldh, size_t ldht,
                               unsigned slotsPerRank, const unsigned char* slotCount, const float* G, const float* inv, const float* corrN, float eps,
                               float* tracePartials, float* statPart, cudaStream_t stream) {
-	const unsigned blocks = ceilDiv(nOwn, 64);
-	if (blocks == 0) return 0;
-	update_h_fused<KP><<<blocks, 256, smemUpdateH<KP>(), stream>>>(peers, lay.H, lay.HtHi, lay.HtLo, lay.slots, k, c0, nOwn, ldh, ldht, slotsPerRank,
-	                                                               ldh * (size_t)colsPerRank, slotCount, G, inv, corrN, eps, tracePartials, statPart);
-	launchCheck();
-	return blocks;
+	if (nOwn == 0) return 0;
+#define NMF_ARGS peers, lay, k, c0, nOwn, colsPerRank, ldh, ldht, slotsPerRank, slotCount, G, inv, corrN, eps, tracePartials, statPart, stream
+	switch (panelColumnsH(nOwn)) {
+	case 64: return launchUpdateHCols<KP, 64>(NMF_ARGS);
+	case 32: return launchUpdateHCols<KP, 32>(NMF_ARGS);
+	default: return launchUpdateHCols<KP, 16>(NMF_ARGS);
+	}
+#undef NMF_ARGS
 }
 
 unsigned updateH(const Peers& peers, const Layout& lay, unsigned k, unsigned c0, unsigned nOwn, unsigned colsPerRank, size_t ldh, size_t ldht,
@@ -576,6 +642,14 @@ unsigned updateH(const Peers& peers, const Layout& lay, unsigned k, unsigned c0,
 	if (k <= 128) return launchUpdateH<128>(NMF_ARGS);
 #undef NMF_ARGS
 	throw EngineError(ResultType::ErrorInvalidArgument, "the fused MU kernels cover ranks up to 128");
+}
+
+void pushN(const Peers& peers, const Layout& lay, unsigned kp, unsigned N, unsigned colsPerRank, size_t ldh, const float* localSlots, size_t localStride,
+           const unsigned char* slotCount, cudaStream_t stream) {
+	const unsigned long long threads = (unsigned long long)N * (kp / 4);
+	if (threads == 0) return;
+	push_n_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(peers, lay.slots, kp, N, colsPerRank, ldh, localSlots, localStride, slotCount);
+	launchCheck();
 }
 
 void reducePush(const Peers& peers, size_t dstOffset, unsigned statLen, const float* partials, unsigned blocks, unsigned count, float flag,

@@ -1,8 +1,9 @@
 // fused.h -- the non-GEMM kernels of the MU iteration on the tensor-core path, one GPU or row blocks over several
 // (dist.h).  Together with the two tcgen05 products (tc_gemm.h) one iteration is eight launches:
 //
-//   1  tc::gemmWtV        partial W_g^T V_g per stream-K slot, stored straight into the memory of the rank that owns the
-//                         columns (peer stores; a reduce-scatter that leaves the kernel tile by tile)
+//   1  tc::gemmWtV        partial W_g^T V_g per stream-K slot
+//   1b pushN              (several ranks only) the slots summed, each column stored into the memory of the rank that owns it
+//                         (NVLink peer stores in whole 256-byte rows: the reduce-scatter)
 //   2  prepH              signal "my partials and statistics are out", wait for every rank's signal; then the statistics
 //                         of the UN-NORMALISED W (Gram matrix + column sums, summed over ranks) become the column scales
 //                         1/||w_c||, W^T W of the unit-column matrix and the centring term of W^T V
@@ -42,7 +43,8 @@ struct Layout {
 	size_t flagsN = 0, flagsH = 0;   // kMaxRanks unsigned each: epoch of the last signal of every rank
 	size_t statW = 0, statH = 0;     // [world][statLen] floats: k*k Gram + k sums (+ 1 flag for W: 1 = columns get normalised)
 	size_t H = 0, HtHi = 0, HtLo = 0;
-	size_t slots = 0;                // [world][slotsPerRank][ldh * colsPerRank] partial products of W^T V for the own columns
+	size_t slots = 0;                // partial products of W^T V.  One rank: [slots][ldh * n], written by the tensor-core kernel;
+	                                 // several: [world][ldh * colsPerRank], one partial per rank for the own columns (pushN)
 	size_t bytes = 0;
 	unsigned statLen = 0;
 };
@@ -61,8 +63,15 @@ void configure();
 void prepH(const Peers& peers, const Layout& lay, const Control& ctl, unsigned k, float center, float* statSum, float* G, float* inv, float* corrN,
            bool signal, cudaStream_t stream);
 
+// step 1b.  localSlots: [slots][ldh * N] partial products of this rank's row block (slotCount per 128-column tile)
+void pushN(const Peers& peers, const Layout& lay, unsigned kp, unsigned N, unsigned colsPerRank, size_t ldh, const float* localSlots, size_t localStride,
+           const unsigned char* slotCount, cudaStream_t stream);
+
+// columns per block of updateH for a rank that owns nOwn columns (statPart needs ceil(nOwn / that) * (k*k + k) floats)
+unsigned panelColumnsH(unsigned nOwn);
+
 // step 3.  Columns [c0, c0 + nOwn) of the k x N matrix H are this rank's.  slotCount[t]: partial products per rank of
-// the 128-column tile t (global column index).  tracePartials (nOwn, or nullptr), statPart ([blocks][k*k + k]).
+// the 128-column tile t (global column index), nullptr = one per rank.  tracePartials (nOwn, or nullptr), statPart ([blocks][k*k + k]).
 // Returns the number of blocks (= partials in statPart).
 unsigned updateH(const Peers& peers, const Layout& lay, unsigned k, unsigned c0, unsigned nOwn, unsigned colsPerRank, size_t ldh, size_t ldht,
                  unsigned slotsPerRank, const unsigned char* slotCount, const float* G, const float* inv, const float* corrN, float eps,

@@ -282,15 +282,19 @@ bool runFactorisation(NmfDescription<T>& desc, Engine<T>& engine, Summary* summa
 		if (!interrupted) {
 			const bool stored = engine.frobenius() < bestError;  // always Frobenius, also when thresholding on RMSD (:214)
 			if (stored) {
+				ExecutionRecord rec = ExecutionRecord();
 				if (summary != nullptr) {
-					ExecutionRecord rec = ExecutionRecord();
 					rec.elapsedTime = elapsedMs / 1000.0;
 					rec.frobenius = engine.frobenius();
 					rec.rmsd = engine.rmsd();
 					rec.numIterations = iteration;
-					summary->insert(rec);
 				}
 				engine.store(desc.outputMatrixW, desc.outputMatrixH);
+				if (summary != nullptr) {
+					rec.sparsityW = engine.sparsityW();   // Hoyer sparseness of the stored factors (the reference leaves both at 0)
+					rec.sparsityH = engine.sparsityH();
+					summary->insert(rec);
+				}
 				timer.mark("  store W, H");
 				bestError = engine.frobenius();
 			}

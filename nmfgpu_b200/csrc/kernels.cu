@@ -11,6 +11,11 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.h"
 
@@ -811,17 +816,21 @@ __global__ void __launch_bounds__(64) qr_solve_clamp_kernel(unsigned k, const T*
 	}
 }
 
-inline void launchCheck() { CUDA_CHECK(cudaGetLastError()); }
+#define launchCheck() CUDA_CHECK(cudaGetLastError())   // a macro: the message names the launch site
 
-// opt-in to more than 48 KB of dynamic shared memory, once per kernel and size (never inside a stream capture)
+// opt-in to more than 48 KB of dynamic shared memory (never inside a stream capture).  The attribute belongs to the
+// (kernel, device) pair, so the cache is keyed by the kernel's ADDRESS and the device ordinal -- keyed by the pointer TYPE,
+// instantiations with the same signature (apply_left_clamp<128> / apply_right_clamp<128>) shared one entry and the second
+// one was launched without its opt-in ("invalid argument").
 template <typename K>
 void allowSmem(K kernel, size_t bytes) {
 	if (bytes <= 48 * 1024) return;
-	// the attribute belongs to the (kernel, device) pair: one cached size per device ordinal and kernel type K
-	static size_t allowed[64] = {};
+	static std::mutex lock;
+	static std::map<std::pair<const void*, int>, size_t> allowed;
 	int dev = 0;
 	CUDA_CHECK(cudaGetDevice(&dev));
-	size_t& mine = allowed[dev & 63];
+	std::lock_guard<std::mutex> guard(lock);
+	size_t& mine = allowed[{reinterpret_cast<const void*>(kernel), dev}];
 	if (bytes <= mine) return;
 	CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 	mine = bytes;
@@ -1043,6 +1052,42 @@ void absInPlace(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream_t str
 	launchCheck();
 }
 
+// partial[2 b] = sum |x|, partial[2 b + 1] = sum x^2 over the share of block b (fp64, fixed order): the two norms behind
+// the Hoyer sparseness of a factor (ExecutionRecord::sparsityW / sparsityH)
+template <typename T>
+__global__ void __launch_bounds__(256) abs_square_sums_kernel(unsigned rows, unsigned cols, const T* __restrict__ X, size_t ld, double* __restrict__ partial) {
+	__shared__ double redA[8], redQ[8];
+	double a = 0.0, q = 0.0;
+	const unsigned long long total = (unsigned long long)rows * cols;
+	for (unsigned long long idx = (unsigned long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (unsigned long long)gridDim.x * 256) {
+		const unsigned r = (unsigned)(idx % rows);
+		const size_t c = (size_t)(idx / rows);
+		const double v = (double)X[c * ld + r];
+		a += fabs(v);
+		q += v * v;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		a += __shfl_xor_sync(0xffffffffu, a, o);
+		q += __shfl_xor_sync(0xffffffffu, q, o);
+	}
+	if (threadIdx.x % 32 == 0) {
+		redA[threadIdx.x / 32] = a;
+		redQ[threadIdx.x / 32] = q;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		partial[2 * blockIdx.x] = ((redA[0] + redA[1]) + (redA[2] + redA[3])) + ((redA[4] + redA[5]) + (redA[6] + redA[7]));
+		partial[2 * blockIdx.x + 1] = ((redQ[0] + redQ[1]) + (redQ[2] + redQ[3])) + ((redQ[4] + redQ[5]) + (redQ[6] + redQ[7]));
+	}
+}
+
+template <typename T>
+void absSquareSums(unsigned rows, unsigned cols, const T* X, size_t ld, double* partial, unsigned blocks, cudaStream_t stream) {
+	abs_square_sums_kernel<T><<<blocks, 256, 0, stream>>>(rows, cols, X, ld, partial);
+	launchCheck();
+}
+
 template <int KP>
 static unsigned updateWReg(unsigned m, unsigned k, const float* B, const float* Win, float* Wout, size_t ldw, const float* Ppart,
                            size_t ldp, unsigned splits, size_t splitStride, float eps, float* colSqPartials, cudaStream_t stream,
@@ -1170,11 +1215,20 @@ void smoothLeft(unsigned k, unsigned n, const T* H, size_t ldh, T* Y, size_t ldy
 }
 
 template <typename T>
-void qrFactor(unsigned k, const T* G, T* factor, cudaStream_t stream) {
+static void qrFactorPlain(unsigned k, const T* G, T* factor, cudaStream_t stream) {
 	const size_t smem = sizeof(T) * ((size_t)k * k + k);
 	allowSmem(qr_factor_kernel<T>, smem);
 	qr_factor_kernel<T><<<1, 256, smem, stream>>>(k, G, factor);
 	launchCheck();
+}
+
+// dst[i] = (To)src[i]; identity != 0: dst = the k x k identity instead (count = k * k)
+template <typename From, typename To>
+__global__ void __launch_bounds__(256) convert_kernel(unsigned count, const From* __restrict__ src, To* __restrict__ dst, unsigned identityK) {
+	const unsigned i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= count) return;
+	if (identityK != 0) dst[i] = (i % identityK == i / identityK) ? To(1) : To(0);
+	else dst[i] = (To)src[i];
 }
 
 template <typename T>
@@ -1199,21 +1253,62 @@ static void applyInverse(unsigned k, const float* M, float* R, size_t ldr, unsig
 	launchCheck();
 }
 
+enum class LsSolve { InverseFp64, InverseFp32, Qr };
+// NMFGPU_LS_SOLVE (study knob behind tools/ls_stability.py): "qr" applies Q^T and back-substitutes per right-hand side
+// (what the reference's ormqr + trsm do, Matrix.h:587-618); "inverse32" forms M = R^-1 Q^T in fp32; default: M formed in fp64
+static LsSolve lsSolveMode() {
+	static const LsSolve mode = [] {
+		const char* e = getenv("NMFGPU_LS_SOLVE");
+		if (e != nullptr && strcmp(e, "qr") == 0) return LsSolve::Qr;
+		if (e != nullptr && strcmp(e, "inverse32") == 0) return LsSolve::InverseFp32;
+		return LsSolve::InverseFp64;
+	}();
+	return mode;
+}
+
 template <>
-void qrSolveClamp<float>(unsigned k, const float* factor, float* R, size_t ldr, unsigned nrhs, bool transposed, cudaStream_t stream, float* inverseScratch) {
-	if (inverseScratch == nullptr || k > 128 || nrhs < 4 * k) {
+void qrFactor<double>(unsigned k, const double* G, double* factor, cudaStream_t stream, double*, double*) {
+	qrFactorPlain<double>(k, G, factor, stream);
+}
+
+// fp32: the factorisation the per-right-hand-side solve walks, and -- when `inverse` is given -- the explicit inverse
+// M = R^-1 Q^T for the tiled products of qrSolveClamp.  M is FORMED in fp64 (G converted, factorised and applied to the
+// identity in double; k x k work, one block) and rounded once: formed in fp32 its error, cond(G) * eps * |M|, put ACLS 6-9x
+// and ALS 2-4x further from the fp64 oracle than the reference's QR solve (profiles/r02_ls_stability.txt).
+template <>
+void qrFactor<float>(unsigned k, const float* G, float* factor, cudaStream_t stream, float* inverse, double* work) {
+	qrFactorPlain<float>(k, G, factor, stream);
+	if (inverse == nullptr || k > 128) return;
+	const unsigned kk = k * k;
+	if (work == nullptr || lsSolveMode() == LsSolve::InverseFp32) {
+		convert_kernel<float, float><<<ceilDiv(kk, 256), 256, 0, stream>>>(kk, nullptr, inverse, k);
+		launchCheck();
+		qrSolveGeneric<float>(k, factor, inverse, k, k, false, false, stream);
+		return;
+	}
+	double* Gd = work;                 // [k*k]
+	double* Fd = work + kk;            // [k*k + k]
+	double* Md = work + 2 * (size_t)kk + k;   // [k*k]
+	convert_kernel<float, double><<<ceilDiv(kk, 256), 256, 0, stream>>>(kk, G, Gd, 0);
+	qrFactorPlain<double>(k, Gd, Fd, stream);
+	convert_kernel<double, double><<<ceilDiv(kk, 256), 256, 0, stream>>>(kk, nullptr, Md, k);
+	launchCheck();
+	qrSolveGeneric<double>(k, Fd, Md, k, k, false, false, stream);
+	convert_kernel<double, float><<<ceilDiv(kk, 256), 256, 0, stream>>>(kk, Md, inverse, 0);
+	launchCheck();
+}
+
+// `inverse`: M as left by qrFactor<float> (nullptr: solve per right-hand side)
+template <>
+void qrSolveClamp<float>(unsigned k, const float* factor, float* R, size_t ldr, unsigned nrhs, bool transposed, cudaStream_t stream, float* inverse) {
+	if (inverse == nullptr || k > 128 || lsSolveMode() == LsSolve::Qr) {
 		qrSolveGeneric<float>(k, factor, R, ldr, nrhs, transposed, true, stream);
 		return;
 	}
-	// M = R^-1 Q^T: the factorisation applied to the identity, then one tiled product per side
-	CUDA_CHECK(cudaMemsetAsync(inverseScratch, 0, (size_t)k * k * sizeof(float), stream));
-	add_constraint_kernel<float><<<dim3(ceilDiv(k, 128), k), 128, 0, stream>>>(k, inverseScratch, 0.f, 1.f);
-	launchCheck();
-	qrSolveGeneric<float>(k, factor, inverseScratch, k, k, false, false, stream);
-	if (k <= 16) applyInverse<16>(k, inverseScratch, R, ldr, nrhs, transposed, stream);
-	else if (k <= 32) applyInverse<32>(k, inverseScratch, R, ldr, nrhs, transposed, stream);
-	else if (k <= 64) applyInverse<64>(k, inverseScratch, R, ldr, nrhs, transposed, stream);
-	else applyInverse<128>(k, inverseScratch, R, ldr, nrhs, transposed, stream);
+	if (k <= 16) applyInverse<16>(k, inverse, R, ldr, nrhs, transposed, stream);
+	else if (k <= 32) applyInverse<32>(k, inverse, R, ldr, nrhs, transposed, stream);
+	else if (k <= 64) applyInverse<64>(k, inverse, R, ldr, nrhs, transposed, stream);
+	else applyInverse<128>(k, inverse, R, ldr, nrhs, transposed, stream);
 }
 
 template <>
@@ -1233,6 +1328,7 @@ void splitTf32(unsigned rows, unsigned cols, const float* X, size_t ldx, float* 
 	template void sumSplits<T>(unsigned, unsigned, const T*, size_t, unsigned, size_t, T*, size_t, cudaStream_t, const unsigned char*, bool, const T*); \
 	template void clampNonNegative<T>(unsigned, unsigned, T*, size_t, cudaStream_t);                                                      \
 	template void absInPlace<T>(unsigned, unsigned, T*, size_t, cudaStream_t);                                                            \
+	template void absSquareSums<T>(unsigned, unsigned, const T*, size_t, double*, unsigned, cudaStream_t);                                \
 	template void finishColumnNorms<T>(unsigned, unsigned, const T*, T*, cudaStream_t, const T*, float, float*);                                                   \
 	template unsigned columnSquares<T>(unsigned, unsigned, const T*, size_t, T*, cudaStream_t);                                           \
 	template void scaleColumns<T>(unsigned, unsigned, T*, size_t, const T*, float*, float*, cudaStream_t);                                \
@@ -1241,7 +1337,6 @@ void splitTf32(unsigned rows, unsigned cols, const float* X, size_t ldx, float* 
 	template void addConstraint<T>(unsigned, T*, T, T, cudaStream_t);                                                                     \
 	template void smoothRight<T>(unsigned, unsigned, const T*, size_t, T*, size_t, T, cudaStream_t);                                      \
 	template void smoothLeft<T>(unsigned, unsigned, const T*, size_t, T*, size_t, T, cudaStream_t);                                       \
-	template void qrFactor<T>(unsigned, const T*, T*, cudaStream_t);                                                                      \
 
 NMF_INSTANTIATE(float)
 NMF_INSTANTIATE(double)

@@ -105,11 +105,13 @@ void smoothLeft(unsigned k, unsigned n, const T* H, size_t ldh, T* Y, size_t ldy
 // One thread block factorises G by Householder QR in shared memory (the reference's route:
 // geqrf/ormqr/trsm, Matrix.h:565-618) into `factor` (k*k + k values), then every column / row is
 // solved independently.
+// fp32 with `inverse` (k*k values) and `work` (3 k*k + k doubles), k <= 128: also leaves the explicit inverse M = R^-1 Q^T,
+// formed in fp64, for the tiled products of qrSolveClamp.
 template <typename T>
-void qrFactor(unsigned k, const T* G, T* factor, cudaStream_t stream);
+void qrFactor(unsigned k, const T* G, T* factor, cudaStream_t stream, T* inverse = nullptr, double* work = nullptr);
 template <typename T>
 void qrSolveClamp(unsigned k, const T* factor, T* R, size_t ldr, unsigned nrhs, bool transposed, cudaStream_t stream,
-                  T* inverseScratch = nullptr);   // k*k values: fp32 goes through the explicit inverse R^-1 Q^T and a tiled product
+                  T* inverse = nullptr);   // the M qrFactor left: fp32 then runs max(0, M R) resp. max(0, R M^T) as a tiled product
 
 // TF32 hi/lo split of a dense block: hi = rn_tf32(x), lo = x - hi
 void splitTf32(unsigned rows, unsigned cols, const float* X, size_t ldx, float* hi, float* lo, size_t ldo, cudaStream_t stream);
@@ -132,6 +134,10 @@ void finishStatsH(unsigned k, const float* stat, float center, float* B, float* 
 // |x| and max(0,x) variants for the k-means based initialisations (KMeansStrategy.cpp:31-40)
 template <typename T>
 void absInPlace(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream_t stream);
+
+// partial[2 b] = sum |x|, partial[2 b + 1] = sum x^2 over block b's share of the rows x cols matrix X (fp64; `blocks` blocks)
+template <typename T>
+void absSquareSums(unsigned rows, unsigned cols, const T* X, size_t ld, double* partial, unsigned blocks, cudaStream_t stream);
 
 }  // namespace kern
 }  // namespace b200

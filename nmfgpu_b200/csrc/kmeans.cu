@@ -113,29 +113,93 @@ __global__ void __launch_bounds__(256) centroid_kernel(unsigned rowLimit, unsign
 	centroids[(size_t)c * ldC + row] = sum;
 }
 
+// Column shards: the same sequential sums, continued from rank to rank.  `running` holds the sums over the members owned
+// by the ranks before this one (zeros on rank 0); this rank adds its own members in ascending sample index -- the exact
+// chain of additions a single GPU performs, so the centroids (and with them every later assignment) stay bit-identical
+// to the single-GPU run, which an all-reduce of per-rank sums would not give.
+template <typename T>
+__global__ void __launch_bounds__(256) centroid_accumulate_kernel(unsigned rowLimit, unsigned k, const T* __restrict__ data, size_t ldData,
+                                                                 T* __restrict__ running, size_t ldC, const unsigned* __restrict__ sorted,
+                                                                 const unsigned* __restrict__ entry, const unsigned* __restrict__ count) {
+	const unsigned row = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned c = blockIdx.y;
+	if (row >= rowLimit || c >= k) return;
+	const unsigned cnt = count[c];
+	const unsigned* ids = sorted + entry[c];
+	T sum = running[(size_t)c * ldC + row];
+	for (unsigned q = 0; q < cnt; ++q) sum += data[(size_t)ids[q] * ldData + row];
+	running[(size_t)c * ldC + row] = sum;
+}
+
+// the last rank of the chain: mean over the members of all ranks; empty clusters keep their previous centroid
+template <typename T>
+__global__ void __launch_bounds__(256) centroid_finish_kernel(unsigned rowLimit, unsigned k, const T* __restrict__ running, T* __restrict__ centroids,
+                                                             size_t ldC, const unsigned* __restrict__ globalCount) {
+	const unsigned row = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned c = blockIdx.y;
+	if (row >= rowLimit || c >= k) return;
+	const unsigned cnt = globalCount[c];
+	if (cnt == 0) return;
+	T sum = running[(size_t)c * ldC + row];
+	sum /= T(cnt);
+	centroids[(size_t)c * ldC + row] = sum;
+}
+
+// point-to-point transfers of the Communicator are counted in floats
+template <typename T>
+Communicator::Transfer transferOf(T* buffer, size_t count, int peer) {
+	return Communicator::Transfer{reinterpret_cast<float*>(buffer), count * (sizeof(T) / sizeof(float)), peer};
+}
+
 }  // namespace
 
 template <typename T>
 unsigned run(unsigned m, unsigned n, unsigned k, const T* data, size_t ldData, T* centroids, size_t ldCentroids, unsigned* membership,
              unsigned seed, unsigned maxIterations, double threshold, cudaStream_t stream, Communicator* comm, bool referenceRowCoverage) {
-	if (comm != nullptr && comm->worldSize() > 1)
-		throw EngineError(ResultType::ErrorInvalidArgument, "k-means initialisation is not available with column shards yet");
-	if (k == 0 || k > n) throw EngineError(ResultType::ErrorInvalidArgument, "cluster count must be in [1, columns]");
+	// Column shards (dist.h): rank g holds the samples [c0, c0 + n) of N; the centroids are replicated.  Seeding picks global
+	// sample indices, assignments are local, the centroid sums are chained through the ranks in rank order (see
+	// centroid_accumulate_kernel), the change count is summed: memberships and centroids are those of the single-GPU run.
+	const bool sharded = comm != nullptr && comm->worldSize() > 1;
+	const unsigned G = sharded ? (unsigned)comm->worldSize() : 1u, rank = sharded ? (unsigned)comm->rank() : 0u;
+	const unsigned N = sharded ? comm->globalColumns() : n, c0 = sharded ? comm->columnOffset() : 0u;
+	if (k == 0 || k > N) throw EngineError(ResultType::ErrorInvalidArgument, "cluster count must be in [1, columns]");
+	if (sharded) {
+		struct Shard {
+			unsigned offset, columns;
+		};
+		const Shard mine = {c0, n};
+		std::vector<Shard> shards(G);
+		comm->allGatherHost(&mine, sizeof(mine), shards.data());
+		unsigned next = 0;
+		for (const Shard& sh : shards) {   // "ascending sample index" must mean the same on one GPU and on G
+			if (sh.offset != next) throw EngineError(ResultType::ErrorInvalidArgument, "k-means over column shards needs contiguous shards in rank order");
+			next += sh.columns;
+		}
+		if (next != N) throw EngineError(ResultType::ErrorInvalidArgument, "the column shards of the ranks do not add up to the global column count");
+	}
 
 	// Phase 1: Forgy seeding (kMeans.cu:136-146)
-	std::vector<unsigned> order(n);
+	std::vector<unsigned> order(N);
 	std::iota(order.begin(), order.end(), 0u);
 	std::mt19937 generator(seed);
 	std::shuffle(order.begin(), order.end(), generator);
+	if (sharded) CUDA_CHECK(cudaMemsetAsync(centroids, 0, ldCentroids * (size_t)k * sizeof(T), stream));
 	for (unsigned c = 0; c < k; ++c)
-		CUDA_CHECK(cudaMemcpyAsync(centroids + (size_t)c * ldCentroids, data + (size_t)order[c] * ldData, (size_t)m * sizeof(T),
-		                           cudaMemcpyDeviceToDevice, stream));
+		if (order[c] >= c0 && order[c] - c0 < n)
+			CUDA_CHECK(cudaMemcpyAsync(centroids + (size_t)c * ldCentroids, data + (size_t)(order[c] - c0) * ldData, (size_t)m * sizeof(T),
+			                           cudaMemcpyDeviceToDevice, stream));
+	if (sharded) comm->allReduceSum(centroids, ldCentroids * (size_t)k, stream);   // every seed has one owner: x + 0 + ... + 0 is exact
 
-	DeviceBuffer<unsigned> changeCount, count, entry, sorted;
+	DeviceBuffer<unsigned> changeCount, count, entry, sorted, globalCount;
+	DeviceBuffer<T> running;
 	changeCount.allocate(1);
 	count.allocate(k);
 	entry.allocate(k);
-	sorted.allocate(n);
+	sorted.allocate(std::max(1u, n));
+	if (sharded) {
+		globalCount.allocate(k);
+		running.allocate(ldCentroids * (size_t)k);
+	}
 	// the reference starts from an uninitialised membership buffer; "no cluster" makes round 0 count every sample
 	CUDA_CHECK(cudaMemsetAsync(membership, 0xFF, (size_t)n * sizeof(unsigned), stream));
 
@@ -145,32 +209,68 @@ unsigned run(unsigned m, unsigned n, unsigned k, const T* data, size_t ldData, T
 		const unsigned blocks = std::max(1u, ceilDiv(m, 32) / 2u);
 		rowLimit = std::min<size_t>(m, (size_t)blocks * 64);
 	}
+	const dim3 centroidGrid(ceilDiv(rowLimit, 256), k);
+
+	auto assign = [&]() {
+		changeCount.zero(stream);
+		if (n > 0) assign_kernel<T><<<ceilDiv(n, 8), 256, 0, stream>>>(n, m, k, data, ldData, centroids, ldCentroids, membership, changeCount.get());
+		CUDA_CHECK(cudaGetLastError());
+	};
 
 	unsigned iteration = 0;
 	double fraction = 0.0;
 	unsigned changed = 0;
 	do {
-		changeCount.zero(stream);
-		assign_kernel<T><<<ceilDiv(n, 8), 256, 0, stream>>>(n, m, k, data, ldData, centroids, ldCentroids, membership, changeCount.get());
-		CUDA_CHECK(cudaGetLastError());
+		assign();
 		CUDA_CHECK(cudaMemcpyAsync(&changed, changeCount.get(), sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
 		CUDA_CHECK(cudaStreamSynchronize(stream));
-		fraction = changed / double(n);
+		if (sharded) changed = (unsigned)comm->allReduceSumHost((double)changed);
+		fraction = changed / double(N);
 		if (changed > 0) {
 			bucket_count_kernel<<<ceilDiv(k, 8), 256, 0, stream>>>(n, k, membership, count.get());
 			bucket_prefix_kernel<<<1, 32, 0, stream>>>(k, count.get(), entry.get());
 			bucket_scatter_kernel<<<ceilDiv(k, 8), 256, 0, stream>>>(n, k, membership, entry.get(), sorted.get());
-			dim3 grid(ceilDiv(rowLimit, 256), k);
-			centroid_kernel<T><<<grid, 256, 0, stream>>>(rowLimit, k, data, ldData, centroids, ldCentroids, sorted.get(), entry.get(), count.get());
-			CUDA_CHECK(cudaGetLastError());
+			if (!sharded) {
+				centroid_kernel<T><<<centroidGrid, 256, 0, stream>>>(rowLimit, k, data, ldData, centroids, ldCentroids, sorted.get(), entry.get(), count.get());
+				CUDA_CHECK(cudaGetLastError());
+			} else {
+				// members per cluster over all ranks
+				std::vector<unsigned> mine(k), all((size_t)k * G), total(k, 0u);
+				CUDA_CHECK(cudaMemcpyAsync(mine.data(), count.get(), (size_t)k * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+				CUDA_CHECK(cudaStreamSynchronize(stream));
+				comm->allGatherHost(mine.data(), (size_t)k * sizeof(unsigned), all.data());
+				for (unsigned g = 0; g < G; ++g)
+					for (unsigned c = 0; c < k; ++c) total[c] += all[(size_t)g * k + c];
+				CUDA_CHECK(cudaMemcpyAsync(globalCount.get(), total.data(), (size_t)k * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
+				// the chain: round r moves the running sums from rank r to rank r + 1 (every rank takes part in every round:
+				// the thread transport of dist.h is collective)
+				if (rank == 0) running.zero(stream);
+				const size_t words = ldCentroids * (size_t)k;
+				for (unsigned r = 0; r + 1 < G; ++r) {
+					std::vector<Communicator::Transfer> sends, recvs;
+					if (rank == r) {
+						centroid_accumulate_kernel<T><<<centroidGrid, 256, 0, stream>>>(rowLimit, k, data, ldData, running.get(), ldCentroids, sorted.get(),
+						                                                                entry.get(), count.get());
+						CUDA_CHECK(cudaGetLastError());
+						sends.push_back(transferOf(running.get(), words, (int)(r + 1)));
+					}
+					if (rank == r + 1) recvs.push_back(transferOf(running.get(), words, (int)r));
+					comm->exchange(sends, recvs, stream);
+				}
+				if (rank == G - 1) {
+					centroid_accumulate_kernel<T><<<centroidGrid, 256, 0, stream>>>(rowLimit, k, data, ldData, running.get(), ldCentroids, sorted.get(),
+					                                                                entry.get(), count.get());
+					centroid_finish_kernel<T><<<centroidGrid, 256, 0, stream>>>(rowLimit, k, running.get(), centroids, ldCentroids, globalCount.get());
+					CUDA_CHECK(cudaGetLastError());
+				} else {
+					CUDA_CHECK(cudaMemsetAsync(centroids, 0, words * sizeof(T), stream));
+				}
+				comm->allReduceSum(centroids, words, stream);   // broadcast of the last rank's centroids (the others add zeros)
+			}
 		}
 	} while (++iteration < maxIterations && fraction > threshold);
 
-	if (fraction > 0.0) {  // final assignment against the last centroids (kMeans.cu:269-277)
-		changeCount.zero(stream);
-		assign_kernel<T><<<ceilDiv(n, 8), 256, 0, stream>>>(n, m, k, data, ldData, centroids, ldCentroids, membership, changeCount.get());
-		CUDA_CHECK(cudaGetLastError());
-	}
+	if (fraction > 0.0) assign();  // final assignment against the last centroids (kMeans.cu:269-277)
 	CUDA_CHECK(cudaStreamSynchronize(stream));
 	return iteration;
 }

@@ -86,11 +86,6 @@ struct KParams {
 	alignas(64) CUtensorMap mapBhi;
 	alignas(64) CUtensorMap mapBlo;
 	float* out;
-	// W^T V over row blocks (dist.h): column r of the product belongs to rank r / colsPerRank and its partial goes into THAT
-	// rank's memory (peerOut[owner], NVLink peer stores), slot slotBase + s of the owner's slot array, at the owner's local
-	// column r - owner * colsPerRank.  Single GPU and V H^T: peerOut[0] = out, colsPerRank = 0xFFFFFFFF, slotBase = 0.
-	float* peerOut[8];
-	unsigned colsPerRank, slotBase;
 	unsigned long long* trace;   // optional timeline of CTA 0 (NMFGPU_TC_TRACE), nullptr otherwise
 	unsigned long long ldOut, slotStride, units;
 	unsigned rowsA, k, kp, tiles, stagesPerTile, flushStages, passes, grid;
@@ -560,10 +555,10 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 				const unsigned r = s.tile * PAIR_ROWS + (fwg + i * FLUSH_WGS) * TILE_ROWS + row;
 				if (r < p.rowsA) {
 					if (V_COLS_ARE_ROWS) {
-						// column r of N: kp contiguous values, stored into the memory of the rank that owns the column
-						const unsigned owner = r / p.colsPerRank;
-						float4* dst = reinterpret_cast<float4*>(p.peerOut[owner] + (size_t)(p.slotBase + s.slot) * p.slotStride +
-						                                        (size_t)(r - owner * p.colsPerRank) * p.ldOut);
+						// column r of N: kp contiguous values.  (Row blocks over several ranks: the partials stay local and
+						// fused::pushN sends their sum to the owners of the columns in whole 256-byte rows -- 16-byte stores
+						// at a 256-byte stride straight from here cost 50 us over NVLink, profiles/r02_notes.md.)
+						float4* dst = reinterpret_cast<float4*>(out + (size_t)r * p.ldOut);
 #pragma unroll
 						for (int c = 0; c < KPM / 4; ++c)
 							if (c * 4 < (int)kp) dst[c] = make_float4(sum[i][4 * c], sum[i][4 * c + 1], sum[i][4 * c + 2], sum[i][4 * c + 3]);
@@ -776,18 +771,9 @@ void configureKernels() {
 }
 
 template <int KPM, bool VC>
-void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, size_t ldOut, size_t slotStride, cudaStream_t stream,
-            const PeerRoute* route = nullptr) {
+void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, size_t ldOut, size_t slotStride, cudaStream_t stream) {
 	const size_t smem = smemBytes<KPM>();
 	KParams p;
-	for (int g = 0; g < 8; ++g) p.peerOut[g] = out;
-	p.colsPerRank = 0xFFFFFFFFu;
-	p.slotBase = 0;
-	if (route != nullptr && route->world > 1) {
-		for (unsigned g = 0; g < route->world && g < 8; ++g) p.peerOut[g] = route->base[g];
-		p.colsPerRank = route->colsPerRank;
-		p.slotBase = route->slotBase;
-	}
 	memcpy(&p.mapV, prod.mapV, 128);
 	memcpy(&p.mapBhi, prod.mapBhi, 128);
 	memcpy(&p.mapBlo, prod.mapBlo, 128);
@@ -973,9 +959,9 @@ void makePlan(Plan& plan, unsigned m, unsigned n, unsigned k, const float* V, si
 	makeMap(plan.vht.mapBlo, HtLo, n, k, ldHt, STAGE_K, plan.kp, true);
 }
 
-void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream, const PeerRoute* route) {
-	if (plan.kp <= 64) launch<64, true>(plan, plan.wtv, plan.n, Npart, ldn, slotStride, stream, route);
-	else launch<128, true>(plan, plan.wtv, plan.n, Npart, ldn, slotStride, stream, route);
+void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream) {
+	if (plan.kp <= 64) launch<64, true>(plan, plan.wtv, plan.n, Npart, ldn, slotStride, stream);
+	else launch<128, true>(plan, plan.wtv, plan.n, Npart, ldn, slotStride, stream);
 }
 
 const unsigned* timeoutCounter() {

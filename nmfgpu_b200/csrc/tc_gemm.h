@@ -88,18 +88,8 @@ void columnSums(Plan& plan, const float* W, unsigned rows, size_t ldW, float* ou
 // out[r] = sum of the first `cols` entries of row r of H (k x cols), r < plan.k
 void rowSums(Plan& plan, const float* H, unsigned cols, size_t ldH, float* out, cudaStream_t stream);
 
-// Where the partial products of W^T V go when the rows of V are spread over several ranks (dist.h): column r belongs to
-// rank r / colsPerRank; its partial is stored into base[owner] (that rank's slot array, mapped into this process) at slot
-// slotBase + s and local column r - owner * colsPerRank -- a reduce-scatter whose transfers leave the kernel tile by tile.
-struct PeerRoute {
-	unsigned world = 1;
-	unsigned colsPerRank = 0xFFFFFFFFu;
-	unsigned slotBase = 0;         // rank * (slots per rank)
-	float* base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-};
-
 // Npart + slot*slotStride (k x n, leading dimension ldn) receives the partial products of W^T V
-void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream, const PeerRoute* route = nullptr);
+void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cudaStream_t stream);
 
 // device address of the counter of tensor-core barrier waits that timed out (0 = healthy); the engine reads it with the
 // residual terms and turns a non-zero value into ErrorExternalLibrary instead of returning garbage with Success

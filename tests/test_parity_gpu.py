@@ -24,12 +24,18 @@ pytestmark = pytest.mark.gpu
 
 RES_TOL = 2e-5
 FAC_TOL = 2e-4
-# Residual tolerance per algorithm against the fp64 oracle.  The least-squares updates solve with the k x k Gram
-# matrix, so fp32 rounding anywhere upstream is amplified by its condition number: measured on the case below the
-# REFERENCE itself (cuBLAS + cuSOLVER fp32) is 5e-4 off the oracle for ALS (no regularisation) and 2e-5 for ACLS,
-# and our own result moves by 1e-2 (ALS) when only the summation order of the k x k QR changes.
-ALGO_RES_TOL = {"mu": RES_TOL, "nsnmf": 5 * RES_TOL, "gdcls": 5 * RES_TOL, "ahcls": 5 * RES_TOL, "acls": 2e-3, "als": 5e-2}
-ALGO_FAC_TOL = {"mu": FAC_TOL, "nsnmf": 5 * FAC_TOL, "gdcls": 5 * FAC_TOL, "ahcls": 5 * FAC_TOL, "acls": 5e-2, "als": 5e-1}
+# The least-squares updates solve with the k x k Gram matrix, so fp32 rounding anywhere upstream is amplified by its
+# condition number.  tools/ls_stability.py (profiles/r02_ls_stability.txt) measured, for this library and for the reference
+# build (cuBLAS + cuSOLVER fp32), the distance from the fp64 oracle on problems of different conditioning:
+#   * well posed (planted rank 20, k = 8): both within 1e-5 (residual) / 2e-4 (factors) for every algorithm -- the
+#     tolerances LS_RES_TOL / LS_FAC_TOL of test_every_algorithm_matches_oracle;
+#   * rank deficient (planted rank = k, the Gram matrix of the solution is singular; ALS has no regularisation): the
+#     REFERENCE is 5e-4 (ALS) / 9e-5 (ACLS) off, and so is this library since the explicit inverse is formed in fp64
+#     (3.6e-4 / 5.7e-5; formed in fp32 it was 3e-3 / 2e-4).  There the bound is max(2 e_ref, 1e-4), and without a
+#     reference run (golden traces) the loose RANK_DEFICIENT_* tolerances.
+LS_RES_TOL, LS_FAC_TOL = 5e-5, 5e-4
+RANK_DEFICIENT_RES_TOL = {"mu": RES_TOL, "nsnmf": 5 * RES_TOL, "gdcls": 5 * RES_TOL, "ahcls": 5 * RES_TOL, "acls": 1e-3, "als": 5e-3}
+RANK_DEFICIENT_FAC_TOL = {"mu": FAC_TOL, "nsnmf": 5 * FAC_TOL, "gdcls": 5 * FAC_TOL, "ahcls": 5 * FAC_TOL, "acls": 2e-2, "als": 1e-1}
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libnmfgpu64_ref.so")
 
@@ -93,14 +99,17 @@ def test_mu_cfg1_matches_oracle(L, precision):
 
 @pytest.mark.parametrize("algo", list(PARAMS))
 def test_every_algorithm_matches_oracle(L, algo):
-    V, W0, H0 = planted_inputs(700, 450, 12, seed=31)
+    """a well-posed problem (planted rank 20, k = 8): every algorithm within fp32 tolerance of the fp64 oracle"""
+    V, _, _ = planted_inputs(700, 450, 20, seed=41, noise=0.05)
+    W0, H0 = uniform_block(42, 700, 8), uniform_block(43, 8, 450)
     o = orc.run_nmf(algo, V, W0, H0, 30, params=PARAMS[algo])
     runs = _trace(L, algo, V, W0, H0, [10, 30], PARAMS[algo], "auto")
+    mult = algo in ("mu", "nsnmf")
     for r, idx in zip(runs, [0, 2]):
         e = abs(r["frobenius"] - o["frob"][idx]) / o["frob"][idx]
-        assert e <= ALGO_RES_TOL[algo], (algo, r["iterations"], e)
-    assert rel(runs[-1]["W"], o["W"]) <= ALGO_FAC_TOL[algo], algo
-    assert rel(runs[-1]["H"], o["H"]) <= ALGO_FAC_TOL[algo], algo
+        assert e <= (RES_TOL if mult else LS_RES_TOL), (algo, r["iterations"], e)
+    assert rel(runs[-1]["W"], o["W"]) <= (FAC_TOL if mult else LS_FAC_TOL), algo
+    assert rel(runs[-1]["H"], o["H"]) <= (FAC_TOL if mult else LS_FAC_TOL), algo
 
 
 def test_golden_traces(L):
@@ -111,8 +120,8 @@ def test_golden_traces(L):
         V, W0, H0 = planted_inputs(g["m"], g["n"], g["k"], seed=g["seed"])
         r = L.compute(V, g["k"], algorithm=algo, W0=W0, H0=H0, iterations=g["iterations"], params=PARAMS[algo])
         assert r["rc"] == ResultType.Success
-        assert abs(r["frobenius"] - g["frob"][-1]) / g["frob"][-1] <= ALGO_RES_TOL[algo], algo
-        np.testing.assert_allclose(np.abs(r["W"]).sum(axis=0), g["w_colsum"], rtol=max(2e-3, ALGO_FAC_TOL[algo]))
+        assert abs(r["frobenius"] - g["frob"][-1]) / g["frob"][-1] <= RANK_DEFICIENT_RES_TOL[algo], algo
+        np.testing.assert_allclose(np.abs(r["W"]).sum(axis=0), g["w_colsum"], rtol=max(2e-3, RANK_DEFICIENT_FAC_TOL[algo]))
         np.testing.assert_allclose(r["H"].sum(axis=1), g["h_rowsum"], rtol=2e-3)
 
 
@@ -431,8 +440,10 @@ def test_reference_other_algorithms_side_by_side(L, REF, algo):
     assert ref["rc"] == ResultType.Success and new["rc"] == ResultType.Success
     e_ref = abs(ref["frobenius"] - o["frob"][-1]) / o["frob"][-1]
     e_new = abs(new["frobenius"] - o["frob"][-1]) / o["frob"][-1]
-    assert e_ref <= max(20 * RES_TOL, ALGO_RES_TOL[algo]), (algo, e_ref)   # pins the oracle's restatement of this algorithm
-    assert e_new <= max(2 * e_ref, ALGO_RES_TOL[algo]), (algo, e_new, e_ref)
+    assert e_ref <= max(20 * RES_TOL, RANK_DEFICIENT_RES_TOL[algo]), (algo, e_ref)   # pins the oracle's restatement of this algorithm
+    assert e_new <= max(2 * e_ref, 1e-4), (algo, e_new, e_ref)
+    for key in ("W", "H"):
+        assert rel(new[key], o[key]) <= max(2 * rel(ref[key], o[key]), 1e-3), (algo, key)
 
 
 def test_reference_random_init_same_stream(L, REF):

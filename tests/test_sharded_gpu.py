@@ -197,3 +197,49 @@ def test_other_algorithms_over_shards(lib, algorithm, params):
         assert np.linalg.norm(W2 - W1) / np.linalg.norm(W1) <= 2e-4
         assert np.linalg.norm(H2 - H1[:, c0:c1]) / np.linalg.norm(H1[:, c0:c1]) <= 2e-4
         assert abs(f2 - f1) / f1 <= 2e-5
+
+
+@pytest.mark.parametrize("world,cuts", [(2, None), (3, [0, 130, 131, 500])])
+def test_kmeans_over_shards_is_bit_exact(lib, world, cuts):
+    """nmfgpu_compute_kmeans_single on column shards (csrc/kmeans.cu: global Forgy seeds, local assignments, centroid sums
+    chained through the ranks in sample order): memberships and centroids are the bits of the single-GPU run"""
+    rng = np.random.default_rng(17)
+    m, n, k = 1000, 500, 6              # 32 row blocks; (m = 1030: 33 blocks, the reference's odd-block quirk B-9) below
+    for rows in (m, 1030):
+        X = (rng.random((rows, k)).astype(np.float32)[:, rng.integers(0, k, n)] + 0.3 * rng.random((rows, n)).astype(np.float32))
+        one = lib.compute_kmeans(X, k, iterations=40, seed=4, threshold=0.0)
+        assert one["rc"] == 0
+
+        def body(rank, L, sync):
+            c0, c1 = (cuts[rank], cuts[rank + 1]) if cuts else shard_columns(n, world, rank)
+            assert L.lib.nmfgpu_b200_dist_set_shard(n, c0) == 0
+            r = L.compute_kmeans(np.asfortranarray(X[:, c0:c1]), k, iterations=40, seed=4, threshold=0.0)
+            return r, (c0, c1)
+
+        for r, (c0, c1) in _run_ranks(world, body):
+            assert r["rc"] == 0
+            np.testing.assert_array_equal(r["memberships"], one["memberships"][c0:c1])
+            np.testing.assert_array_equal(r["centroids"], one["centroids"])
+
+
+@pytest.mark.parametrize("algorithm,params", [("mu", {}), ("gdcls", {"lambda": 0.01}), ("ahcls", {"lambdaW": 0.01, "lambdaH": 0.01, "alphaW": 0.01, "alphaH": 0.01})])
+def test_kmeans_initialisation_over_shards(lib, algorithm, params):
+    """BASELINE configs[3] in small: k-means initialisation (KMeansAndRandomValues) of a column-sharded problem gives the
+    factorisation the single GPU gives from the same seed"""
+    m, n, k, iters = 2048, 1200, 16, 20
+    V, _, _ = dense_inputs(m, n, k, seed=21)
+    init = api.NmfInitializationMethod.KMeansAndRandomValues
+    one = lib.compute(V, k, algorithm=algorithm, init=init, iterations=iters, seed=6, params=params)
+    assert one["rc"] == 0
+
+    def body(rank, L, sync):
+        c0, c1 = shard_columns(n, 2, rank)
+        assert L.lib.nmfgpu_b200_dist_set_shard(n, c0) == 0
+        r = L.compute(np.asfortranarray(V[:, c0:c1]), k, algorithm=algorithm, init=init, iterations=iters, seed=6, params=params)
+        return r, (c0, c1)
+
+    for r, (c0, c1) in _run_ranks(2, body):
+        assert r["rc"] == 0
+        assert np.linalg.norm(r["W"] - one["W"]) / np.linalg.norm(one["W"]) <= 2e-4
+        assert np.linalg.norm(r["H"] - one["H"][:, c0:c1]) / np.linalg.norm(one["H"][:, c0:c1]) <= 2e-4
+        assert abs(r["frobenius"] - one["frobenius"]) / one["frobenius"] <= 2e-5
