@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 M, N, K = 100_000, 10_000, 64          # BASELINE.json configs[1]
 SEED_V, SEED_W, SEED_H = 42, 43, 44
-NVSMI_QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+NVSMI_QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
                "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
                "clocks_event_reasons.sw_power_cap")
 
@@ -51,6 +51,9 @@ def peaks():
 
 
 class ClockSampler:
+    """nvidia-smi in a loop (20 ms) from before the warm-up; stop(t0, t1) keeps the samples whose timestamps lie in
+    [t0, t1] (time.time() of this host), the window the caller was running the timed iterations in."""
+
     def __init__(self, index):
         self.proc = None
         try:
@@ -59,7 +62,8 @@ class ClockSampler:
         except OSError:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -72,14 +76,17 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                stamp = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t0 is not None and not (t0 <= stamp <= t1):
+                    continue
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[3:7]):
+            for name, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
@@ -138,10 +145,12 @@ def run_reference(args, rank, world, local):
         H0 = uniform_block(SEED_H, K, N)
         REF.compute(V, K, W0=W0, H0=H0, iterations=max(1, args.warmup))
         sampler = ClockSampler(0)
+        time.sleep(0.5)
+        w0 = time.time()
         t0 = time.perf_counter()
         r = REF.compute(V, K, W0=W0, H0=H0, iterations=args.steps)
         wall = time.perf_counter() - t0
-        clocks = sampler.stop()
+        clocks = sampler.stop(w0, time.time())
         assert r["rc"] == 0, r["rc"]
         # the same call from page-locked memory (what our own e2e_pinned leg gets)
         wall_pinned = None
@@ -186,6 +195,7 @@ def run_ours(args, rank, world, local):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    sampler = ClockSampler(local) if rank == 0 else None      # started first: nvidia-smi needs up to a second for its first line on an 8-GPU box
     L = api.Library()
     L.set_verbosity(api.Verbosity.NoOutput)
     assert L.initialize() == 0
@@ -219,16 +229,24 @@ def run_ours(args, rank, world, local):
     H0 = uniform_block(SEED_H, K, nloc, total_rows=K, col0=c0)
     s = api.Session(L, "mu", M, nloc, K, device_ptr=dev, ld_v=ld)
     s.set_factors(W0, H0)
-    sampler = ClockSampler(local) if rank == 0 else None      # started before the warm-up: nvidia-smi needs ~0.1 s to produce its first line
     s.iterate(args.warmup)                      # W >= 4 iterations also record the CUDA graph the timed batches replay
     s.iterate_with_error()                      # ... and the residual path (pinned buffers, the host combine) is warm
     s.synchronize()
     info0 = s.info()
     barrier()
+    wall0 = time.time()
     ms, f_timed = s.time_run(args.steps)        # CUDA events on the engine's stream around exactly K iterations, residual cadence included
     barrier()
-    clocks = sampler.stop() if sampler else None
     info1 = s.info()
+    # clocks under this load: the timed region lasts 7-35 ms at 20 steps, less than two nvidia-smi samples, so the same
+    # iterations keep running (untimed) until the sampling window is 0.4 s long
+    while time.time() - wall0 < 0.4:
+        s.iterate(10)
+        s.synchronize()
+    barrier()
+    clocks = sampler.stop(wall0, time.time()) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "the timed iterations and the same iterations continued to 0.4 s"
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -59,6 +59,10 @@ int nmfgpu_b200_session_create_f32(int algorithm, unsigned rows, unsigned column
                                    unsigned ld_v, int v_on_device, int constant_w, const nmfgpu_b200_named_value* params,
                                    unsigned num_params, nmfgpu_b200_session** out);
 int nmfgpu_b200_session_set_factors_f32(nmfgpu_b200_session* s, const float* w, unsigned ld_w, const float* h, unsigned ld_h);
+/* initial factors by one of the reference's strategies on the resident input (init_method: NmfInitializationMethod
+ * AllRandomValues, MeanColumns or a KMeans* value; seed: what the run loop's seed chain would pass); reports the wall-clock
+ * milliseconds of the initialisation (NULL to skip).  Column shards: k-means runs over all ranks' columns. */
+int nmfgpu_b200_session_initialize(nmfgpu_b200_session* s, int init_method, unsigned seed, float* milliseconds);
 int nmfgpu_b200_session_get_factors_f32(nmfgpu_b200_session* s, float* w, unsigned ld_w, float* h, unsigned ld_h);
 /* enqueue `iterations` iterations without residual evaluation; returns immediately */
 int nmfgpu_b200_session_iterate(nmfgpu_b200_session* s, unsigned iterations);

@@ -143,7 +143,7 @@ C_SYMBOLS = ["nmfgpu_initialize", "nmfgpu_finalize", "nmfgpu_version", "nmfgpu_s
 EXT_SYMBOLS = ["nmfgpu_b200_set_precision", "nmfgpu_b200_dist_unique_id", "nmfgpu_b200_dist_local_unique_id", "nmfgpu_b200_dist_init",
                "nmfgpu_b200_session_time_run",
                "nmfgpu_b200_dist_set_shard", "nmfgpu_b200_dist_finalize", "nmfgpu_b200_session_create_f32",
-               "nmfgpu_b200_session_set_factors_f32", "nmfgpu_b200_session_get_factors_f32",
+               "nmfgpu_b200_session_set_factors_f32", "nmfgpu_b200_session_get_factors_f32", "nmfgpu_b200_session_initialize",
                "nmfgpu_b200_session_iterate", "nmfgpu_b200_session_iterate_with_error",
                "nmfgpu_b200_session_time_iterations", "nmfgpu_b200_session_products_f32",
                "nmfgpu_b200_session_synchronize", "nmfgpu_b200_session_get_info", "nmfgpu_b200_session_destroy",
@@ -235,6 +235,7 @@ class Library:
                                                          POINTER(NamedValue), c_uint, POINTER(c_void_p)]
             L.nmfgpu_b200_session_set_factors_f32.argtypes = [c_void_p, c_void_p, c_uint, c_void_p, c_uint]
             L.nmfgpu_b200_session_get_factors_f32.argtypes = [c_void_p, c_void_p, c_uint, c_void_p, c_uint]
+            L.nmfgpu_b200_session_initialize.argtypes = [c_void_p, c_int, c_uint, POINTER(c_float)]
             L.nmfgpu_b200_session_iterate.argtypes = [c_void_p, c_uint]
             L.nmfgpu_b200_session_iterate_with_error.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double)]
             L.nmfgpu_b200_session_time_iterations.argtypes = [c_void_p, c_uint, POINTER(c_float)]
@@ -409,6 +410,14 @@ class Session:
         rc = self.L.lib.nmfgpu_b200_session_set_factors_f32(self.h, W.ctypes.data, self.m, H.ctypes.data, self.k)
         if rc != 0:
             raise RuntimeError("set_factors -> %d" % rc)
+
+    def initialize(self, init_method, seed):
+        """initial factors by one of the reference's strategies on the resident V; returns the milliseconds it took"""
+        ms = c_float()
+        rc = self.L.lib.nmfgpu_b200_session_initialize(self.h, init_method, seed, ctypes.byref(ms))
+        if rc != 0:
+            raise RuntimeError("session_initialize -> %d" % rc)
+        return ms.value
 
     def get_factors(self):
         W = np.zeros((self.m, self.k), dtype=np.float32, order="F")

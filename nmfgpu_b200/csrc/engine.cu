@@ -504,6 +504,7 @@ void Engine<T>::setupFused() {
 	m_ctlWords.zero(m_stream);
 	m_ctl.epoch = m_ctlWords.get();
 	m_ctl.error = m_ctlWords.get() + 1;
+	m_ctl.tickets = m_ctlWords.get() + 4;
 	m_hostFlags.allocate(2);
 	m_hostFlags.get()[0] = m_hostFlags.get()[1] = 0;
 	synchronize();
@@ -539,9 +540,9 @@ void Engine<T>::finishInitialisationFused() {
 	}
 	float* W = reinterpret_cast<float*>(m_W[m_wCur].get()) + m_r0;
 	kern::splitTf32(m_mr, k, W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, m_ldW, m_stream);
-	const unsigned blocks = fused::updateW(m_mr, k, nullptr, nullptr, W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, nullptr, 0, 0, nullptr, nullptr, 0.f,
-	                                       m_statPartW.get(), false, m_stream);
-	fused::reducePush(m_peers, m_lay.statW, m_lay.statLen, m_statPartW.get(), blocks, k * k + k, 0.f, m_stream);
+	const unsigned blocks = fused::updateW(m_peers, m_lay, 0.f, m_mr, k, nullptr, nullptr, nullptr, W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, nullptr, 0, 0,
+	                                       nullptr, 0.f, m_statPartW.get(), false, m_stream);
+	fused::reducePush(m_peers, m_lay.statW, m_lay.statLen, m_statPartW.get(), blocks, k * k + k, 0.f, fused::kNoSignal, m_ctl, 2, m_stream);
 	float* Hfull = reinterpret_cast<float*>(m_sym + m_lay.H);
 	const float* Hmine = reinterpret_cast<const float*>(m_H[m_hCur].get());
 	if (comm == nullptr) {
@@ -580,33 +581,40 @@ void Engine<T>::iterateMUFused(bool err) {
 	productWtVFused();
 	stamp("product W^T V");
 	if (several) {
-		fused::pushN(m_peers, m_lay, plan.kp, m_globalN, m_colsPerRank, m_ldH, m_Nlocal.get(), m_strideN, plan.wtv.slotCount, m_stream);
+		fused::pushN(m_peers, m_lay, m_ctl, plan.kp, m_globalN, m_colsPerRank, m_ldH, m_Nlocal.get(), m_strideN, plan.wtv.slotCount, m_stream);
 		stamp("partials to the owners");
 		m_launches += 1;
 	}
-	fused::prepH(m_peers, m_lay, m_ctl, k, plan.center, m_statSum.get(), G, m_inv.get(), plan.corrN, true, m_stream);
-	stamp("exchange, W statistics");
-	const unsigned blocksH = fused::updateH(m_peers, m_lay, k, m_c0, m_nOwn, m_colsPerRank, m_ldH, m_ldHtFull, several ? 1u : m_slotsPerRank,
+	const unsigned blocksH = fused::updateH(m_peers, m_lay, m_ctl, plan.center, k, m_c0, m_nOwn, m_colsPerRank, m_ldH, m_ldHtFull, several ? 1u : m_slotsPerRank,
 	                                        several ? nullptr : plan.wtv.slotCount, G, m_inv.get(), plan.corrN, (float)m_eps,
 	                                        err ? reinterpret_cast<float*>(m_partN.get()) : nullptr, m_statPartH.get(), m_stream);
 	stamp("update H");
-	fused::reducePush(m_peers, m_lay.statH, m_lay.statLen, m_statPartH.get(), blocksH, k * k + k, -1.f, m_stream);
-	fused::finishH(m_peers, m_lay, m_ctl, k, plan.center, B, plan.corrP, m_stream);
-	stamp("exchange, H statistics");
-	m_launches += 5;
+	fused::reducePush(m_peers, m_lay.statH, m_lay.statLen, m_statPartH.get(), blocksH, k * k + k, -1.f, m_lay.flagsH, m_ctl, 1, m_stream);
+	stamp("H statistics");
+	m_launches += 3;
+	if (err || m_cfg.constantW) {
+		// H H^T before the W update (the trace term), or without one: as a kernel of its own (it waits for the other ranks)
+		fused::finishH(m_peers, m_lay, m_ctl, k, plan.center, B, plan.corrP, m_stream);
+		m_launches += 1;
+	}
 	if (err) {
 		kern::traceKK<T>(k, m_B.get(), m_G.get(), m_partK.get(), m_stream);                     // tr(HH^T W^T W) MU.h:203-216
 		m_launches += 1;
 	}
 	// ---- W <- W o (V H^T) / (W (H H^T) + eps), unit columns (MU.h:200-248)
 	if (!m_cfg.constantW) {
-		tc::gemmVHt(plan, m_PpartR.get(), m_ldPr, m_stridePr, m_stream);
+		tc::Gate gate;
+		gate.flags = reinterpret_cast<const unsigned*>(m_sym + m_lay.flagsH);
+		gate.epoch = m_ctl.epoch;
+		gate.error = m_ctl.error;
+		gate.count = m_peers.world;
+		tc::gemmVHt(plan, m_PpartR.get(), m_ldPr, m_stridePr, m_stream, several ? &gate : nullptr);
 		stamp("product V H^T");
 		float* W = reinterpret_cast<float*>(m_W[m_wCur].get()) + m_r0;
-		const unsigned blocksW = fused::updateW(m_mr, k, B, m_inv.get(), W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, m_PpartR.get(), m_ldPr, m_stridePr,
-		                                        plan.vht.slotCount, plan.corrP, (float)m_eps, m_statPartW.get(), true, m_stream);
+		const unsigned blocksW = fused::updateW(m_peers, m_lay, plan.center, m_mr, k, B, plan.corrP, m_inv.get(), W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0,
+		                                        m_PpartR.get(), m_ldPr, m_stridePr, plan.vht.slotCount, (float)m_eps, m_statPartW.get(), true, m_stream);
 		stamp("update W");
-		fused::reducePush(m_peers, m_lay.statW, m_lay.statLen, m_statPartW.get(), blocksW, k * k + k, 1.f, m_stream);
+		fused::reducePush(m_peers, m_lay.statW, m_lay.statLen, m_statPartW.get(), blocksW, k * k + k, 1.f, fused::kNoSignal, m_ctl, 2, m_stream);
 		stamp("W statistics");
 		m_launches += 3;
 	}
@@ -621,8 +629,7 @@ void Engine<T>::storeFused(const MatrixDescription<T>& hostW, const MatrixDescri
 	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
 	synchronize();
 	if (comm != nullptr) comm->barrier();   // the statistics of every rank's last W update have landed
-	fused::prepH(m_peers, m_lay, m_ctl, k, m_tc->plan.center, m_statSum.get(), reinterpret_cast<float*>(m_Gsaved.get()), m_inv.get(), m_tc->plan.corrN, false,
-	             m_stream);
+	fused::prepH(m_peers, m_lay, k, m_tc->plan.center, m_statSum.get(), reinterpret_cast<float*>(m_Gsaved.get()), m_inv.get(), m_tc->plan.corrN, m_stream);
 	float* spare = reinterpret_cast<float*>(m_W[1 - m_wCur].get());
 	const float* W = reinterpret_cast<const float*>(m_W[m_wCur].get()) + m_r0;
 	if (comm == nullptr) {
@@ -1271,7 +1278,7 @@ void Engine<T>::debugProducts(T* wtv, T* vht, float* msWtV, float* msVHt, cudaEv
 			if (msWtV) CUDA_CHECK(cudaEventElapsedTime(msWtV, e0, e1));
 			if (wtv) {
 				float* sum = reinterpret_cast<float*>(m_H[1 - m_hCur].get());   // spare H buffer as the landing zone
-				fused::prepH(m_peers, m_lay, m_ctl, k, plan.center, m_statSum.get(), reinterpret_cast<float*>(m_Gsaved.get()), m_inv.get(), plan.corrN, false, m_stream);
+				fused::prepH(m_peers, m_lay, k, plan.center, m_statSum.get(), reinterpret_cast<float*>(m_Gsaved.get()), m_inv.get(), plan.corrN, m_stream);
 				fused::collectN(m_peers, m_lay, k, m_c0, m_nOwn, m_colsPerRank, m_ldH, m_slotsPerRank, plan.wtv.slotCount, m_inv.get(), plan.corrN, sum, m_ldH, m_stream);
 				CUDA_CHECK(cudaMemcpy2DAsync(wtv, (size_t)k * sizeof(T), sum, m_ldH * sizeof(T), (size_t)k * sizeof(T), n, cudaMemcpyDeviceToHost, m_stream));
 				synchronize();

@@ -31,13 +31,17 @@ __device__ __forceinline__ unsigned long long globalTimer() {
 	return t;
 }
 
-// one thread: tell every rank "epoch e of this rank is out", then wait until every rank has said the same.
-// A rank that never answers (it failed) must not hang the GPU: after 10 s the wait is abandoned and *error set; the
-// host turns that into ErrorExternalLibrary at its next synchronisation point.
-__device__ void signalAndWait(const Peers& peers, size_t flagOffset, unsigned epoch, unsigned* error) {
+// one thread: tell every rank "epoch e of this rank is out"
+__device__ void signalPeers(const Peers& peers, size_t flagOffset, unsigned epoch) {
 	__threadfence_system();
 	for (unsigned g = 0; g < peers.world; ++g)
 		storeReleaseSystem(reinterpret_cast<unsigned*>(peers.base[g] + flagOffset) + peers.rank, epoch);
+}
+
+// one thread: wait until every rank has signalled `epoch`.  A rank that never answers (it failed) must not hang the GPU:
+// after 10 s the wait is abandoned and *error set; the host turns that into ErrorExternalLibrary at its next
+// synchronisation point.
+__device__ void waitPeers(const Peers& peers, size_t flagOffset, unsigned epoch, unsigned* error) {
 	const unsigned* mine = reinterpret_cast<const unsigned*>(peers.base[peers.rank] + flagOffset);
 	const unsigned long long t0 = globalTimer();
 	for (unsigned g = 0; g < peers.world; ++g) {
@@ -53,28 +57,44 @@ __device__ void signalAndWait(const Peers& peers, size_t flagOffset, unsigned ep
 	__threadfence_system();
 }
 
+__device__ __forceinline__ unsigned currentEpoch(const Control& ctl) { return *reinterpret_cast<volatile const unsigned*>(ctl.epoch); }
+
+// Called by ALL threads of EVERY block of a 1-D grid after their (peer) stores: the block that finishes last tells every
+// rank -- the signal costs no launch of its own and leaves as soon as the data is out.  newEpoch: the iteration counter
+// advances with this signal (once per iteration, pushN).
+__device__ void lastBlockSignals(const Peers& peers, size_t flagOffset, const Control& ctl, unsigned ticket, bool newEpoch) {
+	__threadfence_system();   // this thread's stores are performed, at every rank, before its block takes a ticket
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned* t = ctl.tickets + ticket;
+		if (atomicAdd(t, 1u) == gridDim.x - 1) {
+			*t = 0;   // ready for the next launch (or graph replay)
+			unsigned e = currentEpoch(ctl);
+			if (newEpoch) {
+				e += 1u;
+				*reinterpret_cast<volatile unsigned*>(ctl.epoch) = e;
+			}
+			signalPeers(peers, flagOffset, e);
+		}
+	}
+}
+
 __device__ __forceinline__ float tf32Hi(float x) {
 	uint32_t u;
 	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
 	return __uint_as_float(u);
 }
 
-// ---- step 2 ------------------------------------------------------------------------------------------------------------
+// ---- W statistics -> column scales (outside the iteration: store, diagnostics; inside, updateH does this per block) -------
 // statSum = sum over the ranks of [W_un^T W_un, column sums of W_un, flag].  Unit columns (KernelNormalizeColumns.cu:52-58:
 // divide by the norm where the sum of squares is positive) are applied lazily: inv[c] = 1 / ||w_c||, so
 //   W^T W of the unit-column matrix  = statSum[i, j] * inv[i] * inv[j]
 //   centring term of W^T V           = center * column sum * inv
 // flag == 0 (initial factors, constant W): W is used as it is (the reference normalises only after a W update, MU.h:247).
-__global__ void __launch_bounds__(1024) prep_h_kernel(Peers peers, size_t flagsN, size_t statW, unsigned statLen, Control ctl, unsigned k, float center,
+__global__ void __launch_bounds__(1024) prep_h_kernel(Peers peers, size_t statW, unsigned statLen, unsigned k, float center,
                                                       float* __restrict__ statSum, float* __restrict__ G, float* __restrict__ inv,
-                                                      float* __restrict__ corrN, int signal) {
+                                                      float* __restrict__ corrN) {
 	__shared__ float invS[128];
-	if (signal && threadIdx.x == 0) {
-		const unsigned e = *ctl.epoch + 1u;
-		*ctl.epoch = e;
-		if (peers.world > 1) signalAndWait(peers, flagsN, e, ctl.error);
-	}
-	__syncthreads();
 	const unsigned count = k * k + k + 1;
 	const float* local = reinterpret_cast<const float*>(peers.base[peers.rank] + statW);
 	for (unsigned idx = threadIdx.x; idx < count; idx += blockDim.x) {
@@ -98,10 +118,11 @@ __global__ void __launch_bounds__(1024) prep_h_kernel(Peers peers, size_t flagsN
 	}
 }
 
-// ---- step 5 ------------------------------------------------------------------------------------------------------------
+// ---- H statistics -> H H^T and the centring term, as a kernel of its own: residual iterations (the trace term needs
+// H H^T before the W update) and a constant W (no W update that would do it per block) ---------------------------------------
 __global__ void __launch_bounds__(1024) finish_h_kernel(Peers peers, size_t flagsH, size_t statH, unsigned statLen, Control ctl, unsigned k, float center,
                                                         float* __restrict__ B, float* __restrict__ corrP) {
-	if (peers.world > 1 && threadIdx.x == 0) signalAndWait(peers, flagsH, *ctl.epoch, ctl.error);
+	if (peers.world > 1 && threadIdx.x == 0) waitPeers(peers, flagsH, currentEpoch(ctl), ctl.error);
 	__syncthreads();
 	const float* local = reinterpret_cast<const float*>(peers.base[peers.rank] + statH);
 	for (unsigned idx = threadIdx.x; idx < k * k + k; idx += blockDim.x) {
@@ -117,29 +138,35 @@ __global__ void __launch_bounds__(1024) finish_h_kernel(Peers peers, size_t flag
 // float4 per thread, a column (kp contiguous values) per group of threads, so the peer stores leave as whole 256-byte
 // rows.  (Stored straight from the tensor-core kernel -- one 16-byte piece per thread at a 256-byte stride -- the same
 // bytes cost 50 us over NVLink at 8 GPUs: W^T V 144 us against 93 us for the same launch without peers.)
-__global__ void __launch_bounds__(256) push_n_kernel(Peers peers, size_t oSlots, unsigned kp, unsigned N, unsigned colsPerRank, size_t ldh,
-                                                     const float* __restrict__ local, size_t localStride, const unsigned char* __restrict__ slotCount) {
+__global__ void __launch_bounds__(256) push_n_kernel(Peers peers, size_t oSlots, size_t flagsN, Control ctl, unsigned kp, unsigned N, unsigned colsPerRank,
+                                                     size_t ldh, const float* __restrict__ local, size_t localStride,
+                                                     const unsigned char* __restrict__ slotCount) {
 	const unsigned perCol = kp / 4;
 	const unsigned long long idx = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
 	const unsigned j = (unsigned)(idx / perCol), q = (unsigned)(idx % perCol);
-	if (j >= N) return;
-	const unsigned splits = slotCount[j >> 7];
-	const float* src = local + (size_t)j * ldh + 4 * q;
-	float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-	unsigned sl = 0;
-	for (; sl + 2 <= splits; sl += 2) {
-		const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sl * localStride));
-		const float4 y = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sl + 1) * localStride));
-		a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
-		b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
+	if (j < N) {
+		const unsigned splits = slotCount[j >> 7];
+		const float* src = local + (size_t)j * ldh + 4 * q;
+		float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+		unsigned sl = 0;
+		for (; sl + 4 <= splits; sl += 4) {   // four loads in flight: the sum of 5..15 slots is a chain of L2 latencies otherwise
+			const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sl * localStride));
+			const float4 y = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sl + 1) * localStride));
+			const float4 z = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sl + 2) * localStride));
+			const float4 w = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sl + 3) * localStride));
+			a.x += x.x + z.x; a.y += x.y + z.y; a.z += x.z + z.z; a.w += x.w + z.w;
+			b.x += y.x + w.x; b.y += y.y + w.y; b.z += y.z + w.z; b.w += y.w + w.w;
+		}
+		for (; sl < splits; ++sl) {
+			const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sl * localStride));
+			a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+		}
+		const unsigned owner = j / colsPerRank;
+		float* dst = reinterpret_cast<float*>(peers.base[owner] + oSlots) + ((size_t)peers.rank * colsPerRank + (j - owner * colsPerRank)) * ldh + 4 * q;
+		*reinterpret_cast<float4*>(dst) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 	}
-	if (sl < splits) {
-		const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sl * localStride));
-		a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
-	}
-	const unsigned owner = j / colsPerRank;
-	float* dst = reinterpret_cast<float*>(peers.base[owner] + oSlots) + ((size_t)peers.rank * colsPerRank + (j - owner * colsPerRank)) * ldh + 4 * q;
-	*reinterpret_cast<float4*>(dst) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+	// "my partials -- and, earlier in this stream, the statistics of my rows of W -- are out": a new iteration's first signal
+	lastBlockSignals(peers, flagsN, ctl, 0, true);
 }
 
 // ---- step 3 ------------------------------------------------------------------------------------------------------------
@@ -150,29 +177,82 @@ __global__ void __launch_bounds__(256) push_n_kernel(Peers peers, size_t oSlots,
 // then divide), the residual term and the stores to every rank are the epilogue; then the Gram matrix of the new panel.
 // slotCount == nullptr: one partial per rank (several ranks: fused::pushN has summed the slots).
 template <int KP, int COLS>
-__global__ void __launch_bounds__(COLS * 4) update_h_fused(Peers peers, size_t oH, size_t oHtHi, size_t oHtLo, size_t oSlots, unsigned k, unsigned c0,
-                                                          unsigned nOwn, size_t ldh, size_t ldht, unsigned slotsPerRank, size_t slotStride,
-                                                          const unsigned char* __restrict__ slotCount, const float* __restrict__ G,
-                                                          const float* __restrict__ inv, const float* __restrict__ corrN, float eps,
+__global__ void __launch_bounds__(COLS * 4) update_h_fused(Peers peers, size_t oH, size_t oHtHi, size_t oHtLo, size_t oSlots, size_t flagsN, size_t statW,
+                                                          unsigned statLen, Control ctl, float center, unsigned k, unsigned c0, unsigned nOwn, size_t ldh,
+                                                          size_t ldht, unsigned slotsPerRank, size_t slotStride, const unsigned char* __restrict__ slotCount,
+                                                          float* __restrict__ Gout, float* __restrict__ invOut, float* __restrict__ corrNout, float eps,
                                                           float* __restrict__ tracePartials, float* __restrict__ statPart) {
 	constexpr int NT = COLS * 4, RPT = KP / 16, LDJ = COLS + 4;
 	const unsigned jl0 = blockIdx.x * COLS;   // first column of the panel: local index, global index
 	const unsigned j0 = c0 + jl0;
-	const unsigned splits = slotCount != nullptr ? slotCount[j0 >> 7] : 1u;
+	const unsigned splits = (slotCount != nullptr && jl0 < nOwn) ? slotCount[j0 >> 7] : 1u;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
+	__shared__ float invS[128], corrS[128];
+	__shared__ float flagS;
 	float* Gs = reinterpret_cast<float*>(smem_raw);  // [KP t][KP r]: Gs[t*KP + r] = G[r + t*k]
 	float* Hs = Gs + KP * KP;                         // [KP t][LDJ]:  Hs[t*LDJ + j] = H[t, j0 + j]
 	const unsigned tid = threadIdx.x;
 	const float* Hloc = reinterpret_cast<const float*>(peers.base[peers.rank] + oH);
 	const float* Nloc = reinterpret_cast<const float*>(peers.base[peers.rank] + oSlots);
-	for (unsigned idx = tid; idx < KP * KP; idx += NT) {
-		const unsigned r = idx % KP, t = idx / KP;
-		Gs[idx] = (r < k && t < k) ? G[(size_t)t * k + r] : 0.f;
+	// every rank's partials of W^T V and the statistics of its rows of W have landed here
+	if (peers.world > 1) {
+		if (tid == 0) waitPeers(peers, flagsN, currentEpoch(ctl), ctl.error);
+		__syncthreads();
+	}
+	// Statistics of the UN-NORMALISED W, summed over the ranks in rank order (identical on every rank and in every block):
+	// Gram matrix, column sums, flag.  Unit columns (KernelNormalizeColumns.cu:52-58: divide by the norm where the sum of
+	// squares is positive) are applied lazily: inv[c] = 1 / ||w_c||, W^T W of the unit-column matrix = G[i, j] inv[i] inv[j],
+	// centring term of W^T V = center * column sum * inv.  flag == 0 (initial factors, constant W): W is used as it is
+	// (the reference normalises only after a W update, MU.h:247).
+	{
+		const float* stat = reinterpret_cast<const float*>(peers.base[peers.rank] + statW);
+		for (unsigned idx = tid; idx < KP * KP; idx += NT) {
+			const unsigned r = idx % KP, t = idx / KP;
+			float s = 0.f;
+			if (r < k && t < k)
+				for (unsigned g = 0; g < peers.world; ++g) s += __ldcg(stat + (size_t)g * statLen + (size_t)t * k + r);
+			Gs[idx] = s;
+		}
+		for (unsigned c = tid; c < k; c += NT) {
+			float s = 0.f;
+			for (unsigned g = 0; g < peers.world; ++g) s += __ldcg(stat + (size_t)g * statLen + (size_t)k * k + c);
+			corrS[c] = s;
+		}
+		if (tid == 0) {
+			float f = 0.f;
+			for (unsigned g = 0; g < peers.world; ++g) f += __ldcg(stat + (size_t)g * statLen + (size_t)k * k + k);
+			flagS = f;
+		}
 	}
 	for (unsigned idx = tid; idx < COLS * KP; idx += NT) {
 		const unsigned t = idx % KP, j = idx / KP;
 		Hs[t * LDJ + j] = (jl0 + j < nOwn && t < k) ? Hloc[(size_t)(j0 + j) * ldh + t] : 0.f;
 	}
+	__syncthreads();
+	for (unsigned c = tid; c < KP; c += NT) {
+		float v = 1.f, cs = 0.f;
+		if (c < k) {
+			const float d = Gs[c * KP + c];
+			v = (flagS > 0.5f && d > 0.f) ? 1.0f / sqrtf(d) : 1.0f;
+			cs = center * (corrS[c] * v);
+		}
+		invS[c] = v;
+		corrS[c] = cs;
+	}
+	__syncthreads();
+	for (unsigned idx = tid; idx < KP * KP; idx += NT) {
+		const unsigned r = idx % KP, t = idx / KP;
+		Gs[idx] = Gs[idx] * invS[r] * invS[t];
+	}
+	if (blockIdx.x == 0) {   // for the trace term, the W update and the store of the factors
+		for (unsigned c = tid; c < k; c += NT) {
+			invOut[c] = invS[c];
+			corrNout[c] = corrS[c];
+		}
+	}
+	__syncthreads();
+	if (blockIdx.x == 0)
+		for (unsigned idx = tid; idx < k * k; idx += NT) Gout[idx] = Gs[(idx / k) * KP + idx % k];
 	const unsigned rx = tid % 16, jx = tid / 16;      // rows rx*RPT.., columns jx*4..
 	float numv[RPT][4];
 #pragma unroll
@@ -234,11 +314,10 @@ __global__ void __launch_bounds__(COLS * 4) update_h_fused(Peers peers, size_t o
 #pragma unroll
 	for (int i = 0; i < RPT; ++i) {
 		const unsigned r = rx * RPT + i;
-		const float s = r < k ? inv[r] : 0.f, c = r < k ? corrN[r] : 0.f;
+		const float s = r < k ? invS[r] : 0.f, c = r < k ? corrS[r] : 0.f;
 #pragma unroll
 		for (int q = 0; q < 4; ++q) numv[i][q] = (jl0 + jx * 4 + q < nOwn) ? fmaf(s, numv[i][q], c) : 0.f;
 	}
-	__syncthreads();
 	float acc[RPT][4];
 #pragma unroll
 	for (int i = 0; i < RPT; ++i)
@@ -351,7 +430,7 @@ __global__ void __launch_bounds__(COLS * 4) update_h_fused(Peers peers, size_t o
 // ---- steps 4 and 8 -------------------------------------------------------------------------------------------------------
 // 32 entries x 8 block groups per CTA; every thread keeps four loads in flight; fixed summation order
 __global__ void __launch_bounds__(256) reduce_push_kernel(Peers peers, size_t dstOffset, unsigned statLen, const float* __restrict__ partials,
-                                                          unsigned blocks, unsigned count, float flag) {
+                                                          unsigned blocks, unsigned count, float flag, size_t signalFlags, Control ctl, unsigned ticket) {
 	__shared__ float red[8][33];
 	const unsigned lane = threadIdx.x % 32, grp = threadIdx.x / 32;
 	const unsigned x = blockIdx.x * 32 + lane;
@@ -374,6 +453,8 @@ __global__ void __launch_bounds__(256) reduce_push_kernel(Peers peers, size_t ds
 	}
 	if (flag >= 0.f && blockIdx.x == 0 && threadIdx.x == 0)
 		for (unsigned g = 0; g < peers.world; ++g) reinterpret_cast<float*>(peers.base[g] + dstOffset)[(size_t)peers.rank * statLen + count] = flag;
+	// H side: "my columns of H (the update kernel before this one) and their statistics are out"
+	if (signalFlags != kNoSignal && peers.world > 1) lastBlockSignals(peers, signalFlags, ctl, ticket, false);
 }
 
 // ---- step 7 ------------------------------------------------------------------------------------------------------------
@@ -383,12 +464,14 @@ __global__ void __launch_bounds__(256) reduce_push_kernel(Peers peers, size_t ds
 // TF32 split (what the next W^T V reads) and leaves them in the tile; then the Gram matrix and the column sums of the
 // new rows -- the statistics the next prepH turns into norms, W^T W and the centring term.
 template <int KP, bool UPDATE>
-__global__ void __launch_bounds__(256) update_w_fused(unsigned m, unsigned k, const float* __restrict__ B, const float* __restrict__ inv, float* __restrict__ W,
-                                                     size_t ldw, float* __restrict__ Whi, float* __restrict__ Wlo, const float* __restrict__ Ppart, size_t ldp,
-                                                     size_t slotStride, const unsigned char* __restrict__ slotCount, const float* __restrict__ corr,
-                                                     float eps, float* __restrict__ statPart) {
+__global__ void __launch_bounds__(256) update_w_fused(Peers peers, size_t statH, unsigned statLen, float center, unsigned m, unsigned k,
+                                                     float* __restrict__ Bout, float* __restrict__ corrPout, const float* __restrict__ inv,
+                                                     float* __restrict__ W, size_t ldw, float* __restrict__ Whi, float* __restrict__ Wlo,
+                                                     const float* __restrict__ Ppart, size_t ldp, size_t slotStride,
+                                                     const unsigned char* __restrict__ slotCount, float eps, float* __restrict__ statPart) {
 	constexpr int ROWS = 128, CPT = KP / 8, LDW = ROWS + 4, RPT = KP / 16;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
+	__shared__ float corrS[128];
 	float* Ws = reinterpret_cast<float*>(smem_raw);  // [KP t][LDW]: Ws[t*LDW + r] = W[i0 + r, t] (scaled)
 	float* Bs = Ws + KP * LDW;                        // [KP t][KP c]: Bs[t*KP + c] = B[t + c*k]
 	const unsigned tid = threadIdx.x;
@@ -404,11 +487,28 @@ __global__ void __launch_bounds__(256) update_w_fused(unsigned m, unsigned k, co
 	}
 	if (UPDATE) {
 		const unsigned splits = slotCount != nullptr ? slotCount[blockIdx.x] : 1u;
+		// H H^T and the centring term of V H^T from the statistics of every rank's columns of H, summed in rank order.  The
+		// gate in the tensor-core kernel BEFORE this one has waited for them, so they were complete when this kernel
+		// started: ordinary cached loads (782 blocks re-reading 16 KB each through L2 cost 30 us)
+		const float* stat = reinterpret_cast<const float*>(peers.base[peers.rank] + statH);
 		for (unsigned idx = tid; idx < KP * KP; idx += 256) {
 			const unsigned c = idx % KP, t = idx / KP;
-			Bs[idx] = (c < k && t < k) ? B[(size_t)c * k + t] : 0.f;
+			float s = 0.f;
+			if (c < k && t < k)
+				for (unsigned g = 0; g < peers.world; ++g) s += __ldg(stat + (size_t)g * statLen + (size_t)c * k + t);
+			Bs[idx] = s;
+		}
+		for (unsigned c = tid; c < KP; c += 256) {
+			float s = 0.f;
+			if (c < k)
+				for (unsigned g = 0; g < peers.world; ++g) s += __ldg(stat + (size_t)g * statLen + (size_t)k * k + c);
+			corrS[c] = center * s;
 		}
 		__syncthreads();
+		if (blockIdx.x == 0) {   // for the diagnostics (debugProducts) and the residual iterations
+			for (unsigned idx = tid; idx < k * k; idx += 256) Bout[idx] = Bs[(idx % k) * KP + idx / k];
+			for (unsigned c = tid; c < k; c += 256) corrPout[c] = corrS[c];
+		}
 		const unsigned tx = tid % 32, ty = tid / 32;      // rows tx*4.., columns ty*CPT..
 		float acc[4][CPT];
 #pragma unroll
@@ -443,7 +543,7 @@ __global__ void __launch_bounds__(256) update_w_fused(unsigned m, unsigned k, co
 		for (int j = 0; j < CPT; ++j) {
 			const unsigned c = ty * CPT + j;
 			if (c < k) {   // warp-uniform
-				const float base = corr != nullptr ? corr[c] : 0.f;
+				const float base = corrS[c];
 				float p[4] = {base, base, base, base};
 				if (r0 + 3 < m) {
 					for (unsigned sl = 0; sl < splits; ++sl) {
@@ -589,20 +689,20 @@ void configure() {
 	configureRank<128>();
 }
 
-void prepH(const Peers& peers, const Layout& lay, const Control& ctl, unsigned k, float center, float* statSum, float* G, float* inv, float* corrN,
-           bool signal, cudaStream_t stream) {
-	prep_h_kernel<<<1, 1024, 0, stream>>>(peers, lay.flagsN, lay.statW, lay.statLen, ctl, k, center, statSum, G, inv, corrN, signal ? 1 : 0);
+void prepH(const Peers& peers, const Layout& lay, unsigned k, float center, float* statSum, float* G, float* inv, float* corrN, cudaStream_t stream) {
+	prep_h_kernel<<<1, 1024, 0, stream>>>(peers, lay.statW, lay.statLen, k, center, statSum, G, inv, corrN);
 	launchCheck();
 }
 
 template <int KP, int COLS>
-static unsigned launchUpdateHCols(const Peers& peers, const Layout& lay, unsigned k, unsigned c0, unsigned nOwn, unsigned colsPerRank, size_t ldh, size_t ldht,
-                                  unsigned slotsPerRank, const unsigned char* slotCount, const float* G, const float* inv, const float* corrN, float eps,
-                                  float* tracePartials, float* statPart, cudaStream_t stream) {
-	const unsigned blocks = ceilDiv(nOwn, COLS);
-	update_h_fused<KP, COLS><<<blocks, COLS * 4, smemUpdateH<KP, COLS>(), stream>>>(peers, lay.H, lay.HtHi, lay.HtLo, lay.slots, k, c0, nOwn, ldh, ldht,
-	                                                                                 slotsPerRank, ldh * (size_t)colsPerRank, slotCount, G, inv, corrN, eps,
-	                                                                                 tracePartials, statPart);
+static unsigned launchUpdateHCols(const Peers& peers, const Layout& lay, const Control& ctl, float center, unsigned k, unsigned c0, unsigned nOwn,
+                                  unsigned colsPerRank, size_t ldh, size_t ldht, unsigned slotsPerRank, const unsigned char* slotCount, float* G, float* inv,
+                                  float* corrN, float eps, float* tracePartials, float* statPart, cudaStream_t stream) {
+	const unsigned blocks = std::max(1u, ceilDiv(nOwn, COLS));   // a rank without columns still derives G, inv and corrN (block 0)
+	update_h_fused<KP, COLS><<<blocks, COLS * 4, smemUpdateH<KP, COLS>(), stream>>>(peers, lay.H, lay.HtHi, lay.HtLo, lay.slots, lay.flagsN, lay.statW,
+	                                                                                 lay.statLen, ctl, center, k, c0, nOwn, ldh, ldht, slotsPerRank,
+	                                                                                 ldh * (size_t)colsPerRank, slotCount, G, inv, corrN, eps, tracePartials,
+	                                                                                 statPart);
 	launchCheck();
 	return blocks;
 }
@@ -619,11 +719,10 @@ unsigned panelColumnsH(unsigned nOwn) {
 }
 
 template <int KP>
-static unsigned launchUpdateH(const Peers& peers, const Layout& lay, unsigned k, unsigned c0, unsigned nOwn, unsigned colsPerRank, size_t ldh, size_t ldht,
-                              unsigned slotsPerRank, const unsigned char* slotCount, const float* G, const float* inv, const float* corrN, float eps,
-                              float* tracePartials, float* statPart, cudaStream_t stream) {
-	if (nOwn == 0) return 0;
-#define NMF_ARGS peers, lay, k, c0, nOwn, colsPerRank, ldh, ldht, slotsPerRank, slotCount, G, inv, corrN, eps, tracePartials, statPart, stream
+static unsigned launchUpdateH(const Peers& peers, const Layout& lay, const Control& ctl, float center, unsigned k, unsigned c0, unsigned nOwn,
+                              unsigned colsPerRank, size_t ldh, size_t ldht, unsigned slotsPerRank, const unsigned char* slotCount, float* G, float* inv,
+                              float* corrN, float eps, float* tracePartials, float* statPart, cudaStream_t stream) {
+#define NMF_ARGS peers, lay, ctl, center, k, c0, nOwn, colsPerRank, ldh, ldht, slotsPerRank, slotCount, G, inv, corrN, eps, tracePartials, statPart, stream
 	switch (panelColumnsH(nOwn)) {
 	case 64: return launchUpdateHCols<KP, 64>(NMF_ARGS);
 	case 32: return launchUpdateHCols<KP, 32>(NMF_ARGS);
@@ -632,10 +731,10 @@ static unsigned launchUpdateH(const Peers& peers, const Layout& lay, unsigned k,
 #undef NMF_ARGS
 }
 
-unsigned updateH(const Peers& peers, const Layout& lay, unsigned k, unsigned c0, unsigned nOwn, unsigned colsPerRank, size_t ldh, size_t ldht,
-                 unsigned slotsPerRank, const unsigned char* slotCount, const float* G, const float* inv, const float* corrN, float eps,
+unsigned updateH(const Peers& peers, const Layout& lay, const Control& ctl, float center, unsigned k, unsigned c0, unsigned nOwn, unsigned colsPerRank,
+                 size_t ldh, size_t ldht, unsigned slotsPerRank, const unsigned char* slotCount, float* G, float* inv, float* corrN, float eps,
                  float* tracePartials, float* statPart, cudaStream_t stream) {
-#define NMF_ARGS peers, lay, k, c0, nOwn, colsPerRank, ldh, ldht, slotsPerRank, slotCount, G, inv, corrN, eps, tracePartials, statPart, stream
+#define NMF_ARGS peers, lay, ctl, center, k, c0, nOwn, colsPerRank, ldh, ldht, slotsPerRank, slotCount, G, inv, corrN, eps, tracePartials, statPart, stream
 	if (k <= 16) return launchUpdateH<16>(NMF_ARGS);
 	if (k <= 32) return launchUpdateH<32>(NMF_ARGS);
 	if (k <= 64) return launchUpdateH<64>(NMF_ARGS);
@@ -644,17 +743,17 @@ unsigned updateH(const Peers& peers, const Layout& lay, unsigned k, unsigned c0,
 	throw EngineError(ResultType::ErrorInvalidArgument, "the fused MU kernels cover ranks up to 128");
 }
 
-void pushN(const Peers& peers, const Layout& lay, unsigned kp, unsigned N, unsigned colsPerRank, size_t ldh, const float* localSlots, size_t localStride,
-           const unsigned char* slotCount, cudaStream_t stream) {
+void pushN(const Peers& peers, const Layout& lay, const Control& ctl, unsigned kp, unsigned N, unsigned colsPerRank, size_t ldh, const float* localSlots,
+           size_t localStride, const unsigned char* slotCount, cudaStream_t stream) {
 	const unsigned long long threads = (unsigned long long)N * (kp / 4);
-	if (threads == 0) return;
-	push_n_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(peers, lay.slots, kp, N, colsPerRank, ldh, localSlots, localStride, slotCount);
+	push_n_kernel<<<(unsigned)std::max<unsigned long long>(1, (threads + 255) / 256), 256, 0, stream>>>(peers, lay.slots, lay.flagsN, ctl, kp, N, colsPerRank, ldh,
+	                                                                                                    localSlots, localStride, slotCount);
 	launchCheck();
 }
 
 void reducePush(const Peers& peers, size_t dstOffset, unsigned statLen, const float* partials, unsigned blocks, unsigned count, float flag,
-                cudaStream_t stream) {
-	reduce_push_kernel<<<ceilDiv(count, 32), 256, 0, stream>>>(peers, dstOffset, statLen, partials, blocks, count, flag);
+                size_t signalFlags, const Control& ctl, unsigned ticket, cudaStream_t stream) {
+	reduce_push_kernel<<<ceilDiv(count, 32), 256, 0, stream>>>(peers, dstOffset, statLen, partials, blocks, count, flag, signalFlags, ctl, ticket);
 	launchCheck();
 }
 
@@ -664,23 +763,25 @@ void finishH(const Peers& peers, const Layout& lay, const Control& ctl, unsigned
 }
 
 template <int KP>
-static unsigned launchUpdateW(unsigned rows, unsigned k, const float* B, const float* inv, float* W, size_t ldw, float* Whi, float* Wlo, const float* Ppart,
-                              size_t ldp, size_t slotStride, const unsigned char* slotCount, const float* corrP, float eps, float* statPart, bool update,
-                              cudaStream_t stream) {
+static unsigned launchUpdateW(const Peers& peers, const Layout& lay, float center, unsigned rows, unsigned k, float* B, float* corrP, const float* inv, float* W,
+                              size_t ldw, float* Whi, float* Wlo, const float* Ppart, size_t ldp, size_t slotStride, const unsigned char* slotCount, float eps,
+                              float* statPart, bool update, cudaStream_t stream) {
 	const unsigned blocks = ceilDiv(rows, 128);
 	if (blocks == 0) return 0;
 	if (update)
-		update_w_fused<KP, true><<<blocks, 256, smemUpdateW<KP>(), stream>>>(rows, k, B, inv, W, ldw, Whi, Wlo, Ppart, ldp, slotStride, slotCount, corrP, eps, statPart);
+		update_w_fused<KP, true><<<blocks, 256, smemUpdateW<KP>(), stream>>>(peers, lay.statH, lay.statLen, center, rows, k, B, corrP, inv, W, ldw, Whi, Wlo, Ppart,
+		                                                                     ldp, slotStride, slotCount, eps, statPart);
 	else
-		update_w_fused<KP, false><<<blocks, 256, smemUpdateW<KP>(), stream>>>(rows, k, B, inv, W, ldw, Whi, Wlo, Ppart, ldp, slotStride, slotCount, corrP, eps, statPart);
+		update_w_fused<KP, false><<<blocks, 256, smemUpdateW<KP>(), stream>>>(peers, lay.statH, lay.statLen, center, rows, k, B, corrP, inv, W, ldw, Whi, Wlo, Ppart,
+		                                                                      ldp, slotStride, slotCount, eps, statPart);
 	launchCheck();
 	return blocks;
 }
 
-unsigned updateW(unsigned rows, unsigned k, const float* B, const float* inv, float* W, size_t ldw, float* Whi, float* Wlo, const float* Ppart,
-                 size_t ldp, size_t slotStride, const unsigned char* slotCount, const float* corrP, float eps, float* statPart, bool update,
-                 cudaStream_t stream) {
-#define NMF_ARGS rows, k, B, inv, W, ldw, Whi, Wlo, Ppart, ldp, slotStride, slotCount, corrP, eps, statPart, update, stream
+unsigned updateW(const Peers& peers, const Layout& lay, float center, unsigned rows, unsigned k, float* B, float* corrP, const float* inv, float* W, size_t ldw,
+                 float* Whi, float* Wlo, const float* Ppart, size_t ldp, size_t slotStride, const unsigned char* slotCount, float eps, float* statPart,
+                 bool update, cudaStream_t stream) {
+#define NMF_ARGS peers, lay, center, rows, k, B, corrP, inv, W, ldw, Whi, Wlo, Ppart, ldp, slotStride, slotCount, eps, statPart, update, stream
 	if (k <= 16) return launchUpdateW<16>(NMF_ARGS);
 	if (k <= 32) return launchUpdateW<32>(NMF_ARGS);
 	if (k <= 64) return launchUpdateW<64>(NMF_ARGS);

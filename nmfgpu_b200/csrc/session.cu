@@ -3,6 +3,7 @@
 #include "../../include/nmfgpu_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -166,6 +167,45 @@ NMFGPU_EXPORT int nmfgpu_b200_session_set_factors_f32(nmfgpu_b200_session* s, co
 		s->engine->loadH(hd);
 		s->engine->finishInitialisation();
 		s->engine->synchronize();
+	});
+}
+
+// The reference's initialisation strategies (InitializationStrategy::create, source/init/*.cpp) on the resident V, with the
+// seeds host.cpp's run loop would hand them; wall-clock milliseconds of the whole initialisation (k-means synchronises).
+NMFGPU_EXPORT int nmfgpu_b200_session_initialize(nmfgpu_b200_session* s, int init_method, unsigned seed, float* milliseconds) {
+	if (s == nullptr) return static_cast<int>(ResultType::ErrorInvalidArgument);
+	return guarded([&] {
+		Engine<float>& e = *s->engine;
+		const NmfAlgorithm algo = e.config().algorithm;
+		const bool onlyW = algo == NmfAlgorithm::GDCLS || algo == NmfAlgorithm::ACLS || algo == NmfAlgorithm::AHCLS;   // GDCLS.h:147-157, AHCLS.h:158-168
+		e.synchronize();
+		const auto t0 = std::chrono::steady_clock::now();
+		switch (static_cast<NmfInitializationMethod>(init_method)) {
+		case NmfInitializationMethod::AllRandomValues:
+			e.randomW(seed);
+			if (!onlyW) e.randomH(seed);
+			break;
+		case NmfInitializationMethod::MeanColumns:
+			e.meanColumnsW(seed);
+			if (!onlyW) e.randomH(seed);
+			break;
+		case NmfInitializationMethod::KMeansAndRandomValues:
+			e.kmeansW(seed);
+			if (!onlyW) e.randomH(seed + 1);
+			break;
+		case NmfInitializationMethod::KMeansAndAbsoluteWTV:
+			e.kmeansW(seed);
+			if (!onlyW) e.hFromWtV(true);
+			break;
+		case NmfInitializationMethod::KMeansAndNonNegativeWTV:
+			e.kmeansW(seed);
+			if (!onlyW) e.hFromWtV(false);
+			break;
+		default: throw EngineError(ResultType::ErrorInvalidArgument, "session_initialize: AllRandomValues, MeanColumns or a k-means method");
+		}
+		e.finishInitialisation();
+		e.synchronize();
+		if (milliseconds) *milliseconds = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	});
 }
 

@@ -92,6 +92,12 @@ struct KParams {
 	unsigned chunks, chunkStages;   // reduction chunks (tc_gemm.h): `units` = tiles * chunkStages units per chunk
 	float center;   // subtracted from every element of V before the split (see tc_gemm.h)
 	unsigned prefetchStages;   // how many stages ahead of the TMA loads the V tiles are prefetched into L2
+	// Gate of the small operand (tc_gemm.h Gate): the B producer waits until gateFlags[0 .. gateCount) have all reached
+	// *gateEpoch before its first load -- the other ranks are still storing H^T into this GPU's memory when the kernel starts
+	const unsigned* gateFlags;
+	const unsigned* gateEpoch;
+	unsigned* gateError;
+	unsigned gateCount;
 };
 
 // ---- stream-K bookkeeping shared by host and device ---------------------------------------------------
@@ -357,6 +363,29 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 		// ===== B producer (hi and lo tiles of W resp. H^T) =====
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::HELPER_REGS));
 		if (lane == 0) {
+			if (p.gateCount != 0) {
+				// acquire at system scope (the flags and the data behind them were stored by other GPUs), then order the TMA
+				// reads -- async proxy -- behind it.  A rank that never signals must not hang the GPU: give up after 10 s.
+				const unsigned epoch = *reinterpret_cast<volatile const unsigned*>(p.gateEpoch);
+				unsigned long long t0 = 0;
+				for (unsigned g = 0; g < p.gateCount; ++g) {
+					unsigned spins = 0, seen;
+					for (;;) {
+						asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.gateFlags + g) : "memory");
+						if ((int)(seen - epoch) >= 0) break;
+						if ((++spins & 0x3FF) == 0) {
+							unsigned long long now;
+							asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+							if (t0 == 0) t0 = now;
+							else if (now - t0 > 10000000000ull) {
+								atomicExch(p.gateError, 1u);
+								break;
+							}
+						}
+					}
+				}
+				asm volatile("fence.proxy.async;" ::: "memory");
+			}
 			SegmentWalker walk(p, blockIdx.x);
 			Segment s;
 			RingPos b;
@@ -771,9 +800,14 @@ void configureKernels() {
 }
 
 template <int KPM, bool VC>
-void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, size_t ldOut, size_t slotStride, cudaStream_t stream) {
+void launch(const Plan& plan, const Product& prod, unsigned rowsA, float* out, size_t ldOut, size_t slotStride, cudaStream_t stream,
+            const Gate* gate = nullptr) {
 	const size_t smem = smemBytes<KPM>();
 	KParams p;
+	p.gateFlags = gate ? gate->flags : nullptr;
+	p.gateEpoch = gate ? gate->epoch : nullptr;
+	p.gateError = gate ? gate->error : nullptr;
+	p.gateCount = gate ? gate->count : 0u;
 	memcpy(&p.mapV, prod.mapV, 128);
 	memcpy(&p.mapBhi, prod.mapBhi, 128);
 	memcpy(&p.mapBlo, prod.mapBlo, 128);
@@ -970,9 +1004,9 @@ const unsigned* timeoutCounter() {
 	return static_cast<const unsigned*>(p);
 }
 
-void gemmVHt(const Plan& plan, float* Ppart, size_t ldp, size_t slotStride, cudaStream_t stream) {
-	if (plan.kp <= 64) launch<64, false>(plan, plan.vht, plan.m, Ppart, ldp, slotStride, stream);
-	else launch<128, false>(plan, plan.vht, plan.m, Ppart, ldp, slotStride, stream);
+void gemmVHt(const Plan& plan, float* Ppart, size_t ldp, size_t slotStride, cudaStream_t stream, const Gate* gate) {
+	if (plan.kp <= 64) launch<64, false>(plan, plan.vht, plan.m, Ppart, ldp, slotStride, stream, gate);
+	else launch<128, false>(plan, plan.vht, plan.m, Ppart, ldp, slotStride, stream, gate);
 }
 
 void splitTransposeH(unsigned k, unsigned n, const float* H, size_t ldh, float* hi, float* lo, size_t ldht, cudaStream_t stream) {

@@ -94,8 +94,17 @@ void gemmWtV(const Plan& plan, float* Npart, size_t ldn, size_t slotStride, cuda
 // device address of the counter of tensor-core barrier waits that timed out (0 = healthy); the engine reads it with the
 // residual terms and turns a non-zero value into ErrorExternalLibrary instead of returning garbage with Success
 const unsigned* timeoutCounter();
+// Row blocks over several ranks (dist.h): H^T is stored into this GPU's memory by the ranks that own its columns, and a
+// flag word per rank says up to which iteration.  With a gate the product waits INSIDE the kernel -- only the producer of
+// the H^T tiles, before its first load, while the V pipeline fills -- instead of behind a kernel that does nothing but wait.
+struct Gate {
+	const unsigned* flags = nullptr;   // device, [count]: last epoch every rank has signalled
+	const unsigned* epoch = nullptr;   // device: the epoch to wait for
+	unsigned* error = nullptr;         // device: set to 1 when a flag did not arrive within 10 s
+	unsigned count = 0;
+};
 // Ppart + slot*slotStride (m x k, leading dimension ldp)
-void gemmVHt(const Plan& plan, float* Ppart, size_t ldp, size_t slotStride, cudaStream_t stream);
+void gemmVHt(const Plan& plan, float* Ppart, size_t ldp, size_t slotStride, cudaStream_t stream, const Gate* gate = nullptr);
 
 // hi/lo TF32 split of H (k x n, column-major) written transposed: Ht[c * ldht + j] = H[c + j * ldh]
 void splitTransposeH(unsigned k, unsigned n, const float* H, size_t ldh, float* hi, float* lo, size_t ldht, cudaStream_t stream);

@@ -6,4 +6,4 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 timeout 600 $TR --master-port 29611 tools/dist_check.py > gpurun_out/b_dist_check_$N.log 2>&1; echo "dist_check rc=$?" >> gpurun_out/b_dist_check_$N.log
 timeout 600 $TR --master-port 29612 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/b_bench_$N.json 2> gpurun_out/b_bench_$N.err; echo "bench rc=$?" >> gpurun_out/b_bench_$N.err
 NMFGPU_PROFILE_ITERATION=1 timeout 600 $TR --master-port 29613 bench.py --gpus $N --steps 40 --warmup 5 > gpurun_out/b_profile_$N.json 2> gpurun_out/b_profile_$N.err
-grep -v "^$" gpurun_out/b_dist_check_$N.log | tail -12; cut -c1-900 gpurun_out/b_bench_$N.json; tail -5 gpurun_out/b_bench_$N.err; grep "iteration\]" gpurun_out/b_profile_$N.err | head -12
+grep -v "^$" gpurun_out/b_dist_check_$N.log | tail -8; cut -c1-330 gpurun_out/b_bench_$N.json; tail -3 gpurun_out/b_bench_$N.err; grep "iteration\]" gpurun_out/b_profile_$N.err | head -9
