@@ -111,6 +111,7 @@ public:
 	}
 
 	bool capturable() const override { return true; }
+	bool ranksMayShareDevice() const override { return false; }   // one process per GPU
 	void allReduceSum(float* buffer, size_t count, cudaStream_t stream) override {
 		if (m_world <= 1) return;
 		ncclCheck(api().allReduce(buffer, buffer, count, ncclFloat, ncclSum, m_comm, stream), "ncclAllReduce");
@@ -225,6 +226,7 @@ __global__ void sum_ranks_kernel(T* __restrict__ dst, const T* const* __restrict
 
 class LocalCommunicator : public Communicator {
 	std::shared_ptr<LocalGroup> m_group;
+	bool m_shared = false;   // two ranks on one device
 
 	template <typename T>
 	void allReduceImpl(T* buffer, size_t count, cudaStream_t stream) {
@@ -273,9 +275,13 @@ public:
 		allGatherHost(&dev, sizeof(dev), devices.data());
 		for (int d : devices)
 			if (d != dev && cudaDeviceEnablePeerAccess(d, 0) != cudaSuccess) cudaGetLastError();   // already enabled / same device
+		for (size_t a = 0; a < devices.size(); ++a)
+			for (size_t b = a + 1; b < devices.size(); ++b)
+				if (devices[a] == devices[b]) m_shared = true;
 	}
 
 	bool capturable() const override { return false; }
+	bool ranksMayShareDevice() const override { return m_shared; }
 	void allReduceSum(float* buffer, size_t count, cudaStream_t stream) override { allReduceImpl(buffer, count, stream); }
 	void allReduceSum(double* buffer, size_t count, cudaStream_t stream) override { allReduceImpl(buffer, count, stream); }
 

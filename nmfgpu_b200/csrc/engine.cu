@@ -505,6 +505,7 @@ void Engine<T>::setupFused() {
 	m_ctl.epoch = m_ctlWords.get();
 	m_ctl.error = m_ctlWords.get() + 1;
 	m_ctl.tickets = m_ctlWords.get() + 4;
+	m_ctl.waitInKernel = (comm != nullptr && comm->ranksMayShareDevice()) ? 0u : 1u;
 	m_hostFlags.allocate(2);
 	m_hostFlags.get()[0] = m_hostFlags.get()[1] = 0;
 	synchronize();
@@ -585,6 +586,10 @@ void Engine<T>::iterateMUFused(bool err) {
 		stamp("partials to the owners");
 		m_launches += 1;
 	}
+	if (several && m_ctl.waitInKernel == 0) {
+		fused::waitFor(m_peers, m_lay.flagsN, m_ctl, m_stream);
+		m_launches += 1;
+	}
 	const unsigned blocksH = fused::updateH(m_peers, m_lay, m_ctl, plan.center, k, m_c0, m_nOwn, m_colsPerRank, m_ldH, m_ldHtFull, several ? 1u : m_slotsPerRank,
 	                                        several ? nullptr : plan.wtv.slotCount, G, m_inv.get(), plan.corrN, (float)m_eps,
 	                                        err ? reinterpret_cast<float*>(m_partN.get()) : nullptr, m_statPartH.get(), m_stream);
@@ -608,7 +613,11 @@ void Engine<T>::iterateMUFused(bool err) {
 		gate.epoch = m_ctl.epoch;
 		gate.error = m_ctl.error;
 		gate.count = m_peers.world;
-		tc::gemmVHt(plan, m_PpartR.get(), m_ldPr, m_stridePr, m_stream, several ? &gate : nullptr);
+		if (several && m_ctl.waitInKernel == 0) {
+			fused::waitFor(m_peers, m_lay.flagsH, m_ctl, m_stream);
+			m_launches += 1;
+		}
+		tc::gemmVHt(plan, m_PpartR.get(), m_ldPr, m_stridePr, m_stream, (several && m_ctl.waitInKernel != 0) ? &gate : nullptr);
 		stamp("product V H^T");
 		float* W = reinterpret_cast<float*>(m_W[m_wCur].get()) + m_r0;
 		const unsigned blocksW = fused::updateW(m_peers, m_lay, plan.center, m_mr, k, B, plan.corrP, m_inv.get(), W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0,

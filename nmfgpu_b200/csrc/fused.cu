@@ -63,9 +63,10 @@ __device__ __forceinline__ unsigned currentEpoch(const Control& ctl) { return *r
 // rank -- the signal costs no launch of its own and leaves as soon as the data is out.  newEpoch: the iteration counter
 // advances with this signal (once per iteration, pushN).
 __device__ void lastBlockSignals(const Peers& peers, size_t flagOffset, const Control& ctl, unsigned ticket, bool newEpoch) {
-	__threadfence_system();   // this thread's stores are performed, at every rank, before its block takes a ticket
-	__syncthreads();
+	__syncthreads();   // every store of the block happens-before thread 0's fence: one system fence per block, not per thread
+	                   // (a membar.sys from each of 160 000 threads made pushN 34 us at 8 GPUs)
 	if (threadIdx.x == 0) {
+		__threadfence_system();   // cumulative: the block's stores are performed, at every rank, before the ticket is taken
 		unsigned* t = ctl.tickets + ticket;
 		if (atomicAdd(t, 1u) == gridDim.x - 1) {
 			*t = 0;   // ready for the next launch (or graph replay)
@@ -77,6 +78,26 @@ __device__ void lastBlockSignals(const Peers& peers, size_t flagOffset, const Co
 			signalPeers(peers, flagOffset, e);
 		}
 	}
+}
+
+// out[i] (+)= sum over the ranks, in rank order, of four consecutive statistics: one 16-byte load per rank, all of them in
+// flight at once (a scalar loop over 8 ranks x 4 160 entries per block was a chain of 33 L2 round trips, 25 us at 8 GPUs)
+template <bool CACHED>
+__device__ __forceinline__ float4 sumRanks4(const Peers& peers, const float* stat, unsigned statLen, unsigned index) {
+	float4 v[kMaxRanks];
+#pragma unroll
+	for (unsigned g = 0; g < kMaxRanks; ++g)
+		if (g < peers.world) {
+			const float4* p = reinterpret_cast<const float4*>(stat + (size_t)g * statLen + index);
+			v[g] = CACHED ? __ldg(p) : __ldcg(p);
+		}
+	float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+	for (unsigned g = 0; g < kMaxRanks; ++g)
+		if (g < peers.world) {
+			s.x += v[g].x; s.y += v[g].y; s.z += v[g].z; s.w += v[g].w;
+		}
+	return s;
 }
 
 __device__ __forceinline__ float tf32Hi(float x) {
@@ -131,6 +152,10 @@ __global__ void __launch_bounds__(1024) finish_h_kernel(Peers peers, size_t flag
 		if (idx < k * k) B[idx] = s;
 		else corrP[idx - k * k] = center * s;
 	}
+}
+
+__global__ void wait_kernel(Peers peers, size_t flagOffset, Control ctl) {
+	if (threadIdx.x == 0) waitPeers(peers, flagOffset, currentEpoch(ctl), ctl.error);
 }
 
 // ---- step 1b (several ranks) ---------------------------------------------------------------------------------------------
@@ -195,7 +220,7 @@ __global__ void __launch_bounds__(COLS * 4) update_h_fused(Peers peers, size_t o
 	const float* Hloc = reinterpret_cast<const float*>(peers.base[peers.rank] + oH);
 	const float* Nloc = reinterpret_cast<const float*>(peers.base[peers.rank] + oSlots);
 	// every rank's partials of W^T V and the statistics of its rows of W have landed here
-	if (peers.world > 1) {
+	if (peers.world > 1 && ctl.waitInKernel != 0) {
 		if (tid == 0) waitPeers(peers, flagsN, currentEpoch(ctl), ctl.error);
 		__syncthreads();
 	}
@@ -206,12 +231,21 @@ __global__ void __launch_bounds__(COLS * 4) update_h_fused(Peers peers, size_t o
 	// (the reference normalises only after a W update, MU.h:247).
 	{
 		const float* stat = reinterpret_cast<const float*>(peers.base[peers.rank] + statW);
-		for (unsigned idx = tid; idx < KP * KP; idx += NT) {
-			const unsigned r = idx % KP, t = idx / KP;
-			float s = 0.f;
-			if (r < k && t < k)
-				for (unsigned g = 0; g < peers.world; ++g) s += __ldcg(stat + (size_t)g * statLen + (size_t)t * k + r);
-			Gs[idx] = s;
+		if (k % 4 == 0) {
+			for (unsigned idx = tid; idx < KP * KP / 4; idx += NT) {
+				const unsigned r = (idx % (KP / 4)) * 4, t = idx / (KP / 4);
+				float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (r < k && t < k) s = sumRanks4<false>(peers, stat, statLen, t * k + r);
+				*reinterpret_cast<float4*>(Gs + t * KP + r) = s;
+			}
+		} else {
+			for (unsigned idx = tid; idx < KP * KP; idx += NT) {
+				const unsigned r = idx % KP, t = idx / KP;
+				float s = 0.f;
+				if (r < k && t < k)
+					for (unsigned g = 0; g < peers.world; ++g) s += __ldcg(stat + (size_t)g * statLen + (size_t)t * k + r);
+				Gs[idx] = s;
+			}
 		}
 		for (unsigned c = tid; c < k; c += NT) {
 			float s = 0.f;
@@ -457,150 +491,168 @@ __global__ void __launch_bounds__(256) reduce_push_kernel(Peers peers, size_t ds
 	if (signalFlags != kNoSignal && peers.world > 1) lastBlockSignals(peers, signalFlags, ctl, ticket, false);
 }
 
-// ---- step 7 ------------------------------------------------------------------------------------------------------------
-// A 128-row panel per block.  The tile is read with the column scale applied (unit columns of the previous update,
-// KernelNormalizeColumns.cu:52-58, without a pass of their own), D = W (H H^T) is a register-tiled product out of
-// shared memory (thread = 4 rows x KP/8 columns), the multiplicative update writes the new un-normalised rows and their
-// TF32 split (what the next W^T V reads) and leaves them in the tile; then the Gram matrix and the column sums of the
-// new rows -- the statistics the next prepH turns into norms, W^T W and the centring term.
+// ---- step 5 ------------------------------------------------------------------------------------------------------------
+// Every block walks 128-row panels blockIdx.x, blockIdx.x + gridDim.x, ... (the grid is sized to one wave, so 782 panels of
+// the 100 000-row problem are 391 blocks of two).  H H^T comes into shared memory once per block.  Per panel: the tile is
+// read with the column scale applied (unit columns of the previous update, KernelNormalizeColumns.cu:52-58, without a pass
+// of their own), D = W (H H^T) is a register-tiled product out of shared memory (thread = 4 rows x KP/8 columns), the
+// multiplicative update writes the new un-normalised rows and their TF32 split (what the next W^T V reads) and leaves them
+// in the tile; then the Gram matrix and the column sums of the new rows are ACCUMULATED in registers over the block's
+// panels -- the statistics the next updateH turns into norms, W^T W and the centring term; one partial per block.
 template <int KP, bool UPDATE>
-__global__ void __launch_bounds__(256) update_w_fused(Peers peers, size_t statH, unsigned statLen, float center, unsigned m, unsigned k,
+__global__ void __launch_bounds__(256, KP <= 64 ? 3 : 1) update_w_fused(Peers peers, size_t statH, unsigned statLen, float center, unsigned m, unsigned k,
                                                      float* __restrict__ Bout, float* __restrict__ corrPout, const float* __restrict__ inv,
                                                      float* __restrict__ W, size_t ldw, float* __restrict__ Whi, float* __restrict__ Wlo,
                                                      const float* __restrict__ Ppart, size_t ldp, size_t slotStride,
                                                      const unsigned char* __restrict__ slotCount, float eps, float* __restrict__ statPart) {
-	constexpr int ROWS = 128, CPT = KP / 8, LDW = ROWS + 4, RPT = KP / 16;
+	constexpr int ROWS = 128, CPT = KP / 8, LDW = ROWS + 4, RPT = KP / 16, CSUM = (KP + 7) / 8;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	__shared__ float corrS[128];
+	__shared__ float corrS[128], invS[128];
 	float* Ws = reinterpret_cast<float*>(smem_raw);  // [KP t][LDW]: Ws[t*LDW + r] = W[i0 + r, t] (scaled)
 	float* Bs = Ws + KP * LDW;                        // [KP t][KP c]: Bs[t*KP + c] = B[t + c*k]
-	const unsigned tid = threadIdx.x;
-	const unsigned i0 = blockIdx.x * ROWS;
-	for (unsigned idx = tid; idx < KP * ROWS; idx += 256) {
-		const unsigned r = idx % ROWS, t = idx / ROWS;
-		float v = 0.f;
-		if (i0 + r < m && t < k) {
-			v = W[(size_t)t * ldw + i0 + r];
-			if (UPDATE) v *= inv[t];
-		}
-		Ws[t * LDW + r] = v;
-	}
+	const unsigned tid = threadIdx.x, lane = tid % 32;
+	const unsigned panels = (m + ROWS - 1) / ROWS;
+	for (unsigned c = tid; c < KP; c += 256) invS[c] = (UPDATE && c < k) ? inv[c] : 1.f;
 	if (UPDATE) {
-		const unsigned splits = slotCount != nullptr ? slotCount[blockIdx.x] : 1u;
 		// H H^T and the centring term of V H^T from the statistics of every rank's columns of H, summed in rank order.  The
 		// gate in the tensor-core kernel BEFORE this one has waited for them, so they were complete when this kernel
-		// started: ordinary cached loads (782 blocks re-reading 16 KB each through L2 cost 30 us)
+		// started: ordinary cached loads
 		const float* stat = reinterpret_cast<const float*>(peers.base[peers.rank] + statH);
-		for (unsigned idx = tid; idx < KP * KP; idx += 256) {
-			const unsigned c = idx % KP, t = idx / KP;
-			float s = 0.f;
-			if (c < k && t < k)
-				for (unsigned g = 0; g < peers.world; ++g) s += __ldg(stat + (size_t)g * statLen + (size_t)c * k + t);
-			Bs[idx] = s;
+		if (k % 4 == 0) {   // (H H^T is symmetric bit for bit: both triangles are the same fma chains with the factors swapped)
+			for (unsigned idx = tid; idx < KP * KP / 4; idx += 256) {
+				const unsigned c = (idx % (KP / 4)) * 4, t = idx / (KP / 4);
+				float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (c < k && t < k) sum = sumRanks4<true>(peers, stat, statLen, t * k + c);
+				*reinterpret_cast<float4*>(Bs + t * KP + c) = sum;
+			}
+		} else {
+			for (unsigned idx = tid; idx < KP * KP; idx += 256) {
+				const unsigned c = idx % KP, t = idx / KP;
+				float sum = 0.f;
+				if (c < k && t < k)
+					for (unsigned g = 0; g < peers.world; ++g) sum += __ldg(stat + (size_t)g * statLen + (size_t)c * k + t);
+				Bs[idx] = sum;
+			}
 		}
 		for (unsigned c = tid; c < KP; c += 256) {
-			float s = 0.f;
+			float sum = 0.f;
 			if (c < k)
-				for (unsigned g = 0; g < peers.world; ++g) s += __ldg(stat + (size_t)g * statLen + (size_t)k * k + c);
-			corrS[c] = center * s;
-		}
-		__syncthreads();
-		if (blockIdx.x == 0) {   // for the diagnostics (debugProducts) and the residual iterations
-			for (unsigned idx = tid; idx < k * k; idx += 256) Bout[idx] = Bs[(idx % k) * KP + idx / k];
-			for (unsigned c = tid; c < k; c += 256) corrPout[c] = corrS[c];
-		}
-		const unsigned tx = tid % 32, ty = tid / 32;      // rows tx*4.., columns ty*CPT..
-		float acc[4][CPT];
-#pragma unroll
-		for (int i = 0; i < 4; ++i)
-#pragma unroll
-			for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-		for (int t = 0; t < KP; ++t) {
-			const float4 a = *reinterpret_cast<const float4*>(Ws + t * LDW + tx * 4);
-			float b[CPT];
-			if (CPT % 4 == 0) {
-#pragma unroll
-				for (int j = 0; j < CPT; j += 4) {
-					const float4 x = *reinterpret_cast<const float4*>(Bs + t * KP + ty * CPT + j);
-					b[j] = x.x; b[j + 1] = x.y; b[j + 2] = x.z; b[j + 3] = x.w;
-				}
-			} else {
-#pragma unroll
-				for (int j = 0; j < CPT; ++j) b[j] = Bs[t * KP + ty * CPT + j];
-			}
-#pragma unroll
-			for (int j = 0; j < CPT; ++j) {
-				acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
-				acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
-				acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
-				acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
-			}
-		}
-		__syncthreads();   // every thread is done reading the old tile: it can now be overwritten with the new values
-		const unsigned r0 = i0 + tx * 4;
-#pragma unroll
-		for (int j = 0; j < CPT; ++j) {
-			const unsigned c = ty * CPT + j;
-			if (c < k) {   // warp-uniform
-				const float base = corrS[c];
-				float p[4] = {base, base, base, base};
-				if (r0 + 3 < m) {
-					for (unsigned sl = 0; sl < splits; ++sl) {
-						const float4 x = __ldcg(reinterpret_cast<const float4*>(Ppart + sl * slotStride + (size_t)c * ldp + r0));
-						p[0] += x.x; p[1] += x.y; p[2] += x.z; p[3] += x.w;
-					}
-				} else {
-					for (unsigned sl = 0; sl < splits; ++sl)
-						for (int i = 0; i < 4; ++i)
-							if (r0 + i < m) p[i] += __ldcg(Ppart + sl * slotStride + (size_t)c * ldp + r0 + i);
-				}
-				const float4 w = *reinterpret_cast<const float4*>(Ws + c * LDW + tx * 4);
-				float wn[4];
-				wn[0] = w.x * p[0] / (acc[0][j] + eps);   // KernelMultiplyDivide.cu:42: multiply first, then divide
-				wn[1] = w.y * p[1] / (acc[1][j] + eps);
-				wn[2] = w.z * p[2] / (acc[2][j] + eps);
-				wn[3] = w.w * p[3] / (acc[3][j] + eps);
-				float hi[4];
-				if (r0 + 3 < m) {
-#pragma unroll
-					for (int i = 0; i < 4; ++i) hi[i] = tf32Hi(wn[i]);
-					*reinterpret_cast<float4*>(W + (size_t)c * ldw + r0) = make_float4(wn[0], wn[1], wn[2], wn[3]);
-					*reinterpret_cast<float4*>(Whi + (size_t)c * ldw + r0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-					*reinterpret_cast<float4*>(Wlo + (size_t)c * ldw + r0) = make_float4(wn[0] - hi[0], wn[1] - hi[1], wn[2] - hi[2], wn[3] - hi[3]);
-				} else {
-					for (int i = 0; i < 4; ++i) {
-						if (r0 + i < m) {
-							const float h = tf32Hi(wn[i]);
-							W[(size_t)c * ldw + r0 + i] = wn[i];
-							Whi[(size_t)c * ldw + r0 + i] = h;
-							Wlo[(size_t)c * ldw + r0 + i] = wn[i] - h;
-						} else {
-							wn[i] = 0.f;
-						}
-					}
-				}
-				*reinterpret_cast<float4*>(Ws + c * LDW + tx * 4) = make_float4(wn[0], wn[1], wn[2], wn[3]);
-			}
+				for (unsigned g = 0; g < peers.world; ++g) sum += __ldg(stat + (size_t)g * statLen + (size_t)k * k + c);
+			corrS[c] = center * sum;
 		}
 	}
 	__syncthreads();
-	// statistics of the rows now in the tile: Gram matrix (thread = columns a + 16 i x columns b + 16 q) and column sums
-	float* stat = statPart + (size_t)blockIdx.x * ((size_t)k * k + k);
-	{
-		const unsigned a = tid % 16, b = tid / 16;
-		float gr[RPT][RPT];
+	if (UPDATE && blockIdx.x == 0) {   // for the diagnostics (debugProducts) and the residual iterations
+		for (unsigned idx = tid; idx < k * k; idx += 256) Bout[idx] = Bs[(idx % k) * KP + idx / k];
+		for (unsigned c = tid; c < k; c += 256) corrPout[c] = corrS[c];
+	}
+	// statistics accumulated over the panels of this block: Gram entries (columns a + 16 i) x (columns b + 16 q), and per
+	// lane partial column sums of the columns warp + 8 j
+	const unsigned ga = tid % 16, gb = tid / 16;
+	float gr[RPT][RPT], csum[CSUM];
 #pragma unroll
-		for (int i = 0; i < RPT; ++i)
+	for (int i = 0; i < RPT; ++i)
 #pragma unroll
-			for (int q = 0; q < RPT; ++q) gr[i][q] = 0.f;
+		for (int q = 0; q < RPT; ++q) gr[i][q] = 0.f;
+#pragma unroll
+	for (int j = 0; j < CSUM; ++j) csum[j] = 0.f;
+
+	for (unsigned panel = blockIdx.x; panel < panels; panel += gridDim.x) {
+		const unsigned i0 = panel * ROWS;
+		__syncthreads();   // the previous panel's statistics are done with the tile
+		for (unsigned idx = tid; idx < KP * ROWS; idx += 256) {
+			const unsigned r = idx % ROWS, t = idx / ROWS;
+			float v = 0.f;
+			if (i0 + r < m && t < k) v = W[(size_t)t * ldw + i0 + r] * invS[t];
+			Ws[t * LDW + r] = v;
+		}
+		__syncthreads();
+		if (UPDATE) {
+			const unsigned splits = slotCount != nullptr ? slotCount[panel] : 1u;
+			const unsigned tx = tid % 32, ty = tid / 32;      // rows tx*4.., columns ty*CPT..
+			float acc[4][CPT];
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+#pragma unroll
+				for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+			for (int t = 0; t < KP; ++t) {
+				const float4 a = *reinterpret_cast<const float4*>(Ws + t * LDW + tx * 4);
+				float b[CPT];
+				if (CPT % 4 == 0) {
+#pragma unroll
+					for (int j = 0; j < CPT; j += 4) {
+						const float4 x = *reinterpret_cast<const float4*>(Bs + t * KP + ty * CPT + j);
+						b[j] = x.x; b[j + 1] = x.y; b[j + 2] = x.z; b[j + 3] = x.w;
+					}
+				} else {
+#pragma unroll
+					for (int j = 0; j < CPT; ++j) b[j] = Bs[t * KP + ty * CPT + j];
+				}
+#pragma unroll
+				for (int j = 0; j < CPT; ++j) {
+					acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
+					acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
+					acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
+					acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+				}
+			}
+			__syncthreads();   // every thread is done reading the old tile: it can now be overwritten with the new values
+			const unsigned r0 = i0 + tx * 4;
+#pragma unroll
+			for (int j = 0; j < CPT; ++j) {
+				const unsigned c = ty * CPT + j;
+				if (c < k) {   // warp-uniform
+					const float base = corrS[c];
+					float p[4] = {base, base, base, base};
+					if (r0 + 3 < m) {
+						for (unsigned sl = 0; sl < splits; ++sl) {
+							const float4 x = __ldcg(reinterpret_cast<const float4*>(Ppart + sl * slotStride + (size_t)c * ldp + r0));
+							p[0] += x.x; p[1] += x.y; p[2] += x.z; p[3] += x.w;
+						}
+					} else {
+						for (unsigned sl = 0; sl < splits; ++sl)
+							for (int i = 0; i < 4; ++i)
+								if (r0 + i < m) p[i] += __ldcg(Ppart + sl * slotStride + (size_t)c * ldp + r0 + i);
+					}
+					const float4 w = *reinterpret_cast<const float4*>(Ws + c * LDW + tx * 4);
+					float wn[4];
+					wn[0] = w.x * p[0] / (acc[0][j] + eps);   // KernelMultiplyDivide.cu:42: multiply first, then divide
+					wn[1] = w.y * p[1] / (acc[1][j] + eps);
+					wn[2] = w.z * p[2] / (acc[2][j] + eps);
+					wn[3] = w.w * p[3] / (acc[3][j] + eps);
+					float hi[4];
+					if (r0 + 3 < m) {
+#pragma unroll
+						for (int i = 0; i < 4; ++i) hi[i] = tf32Hi(wn[i]);
+						*reinterpret_cast<float4*>(W + (size_t)c * ldw + r0) = make_float4(wn[0], wn[1], wn[2], wn[3]);
+						*reinterpret_cast<float4*>(Whi + (size_t)c * ldw + r0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+						*reinterpret_cast<float4*>(Wlo + (size_t)c * ldw + r0) = make_float4(wn[0] - hi[0], wn[1] - hi[1], wn[2] - hi[2], wn[3] - hi[3]);
+					} else {
+						for (int i = 0; i < 4; ++i) {
+							if (r0 + i < m) {
+								const float h = tf32Hi(wn[i]);
+								W[(size_t)c * ldw + r0 + i] = wn[i];
+								Whi[(size_t)c * ldw + r0 + i] = h;
+								Wlo[(size_t)c * ldw + r0 + i] = wn[i] - h;
+							} else {
+								wn[i] = 0.f;
+							}
+						}
+					}
+					*reinterpret_cast<float4*>(Ws + c * LDW + tx * 4) = make_float4(wn[0], wn[1], wn[2], wn[3]);
+				}
+			}
+			__syncthreads();
+		}
+		// statistics of the rows now in the tile
 #pragma unroll 2
 		for (int r = 0; r < ROWS; r += 4) {
 			float4 av[RPT], bv[RPT];
 #pragma unroll
-			for (int i = 0; i < RPT; ++i) av[i] = *reinterpret_cast<const float4*>(Ws + (a + 16 * i) * LDW + r);
+			for (int i = 0; i < RPT; ++i) av[i] = *reinterpret_cast<const float4*>(Ws + (ga + 16 * i) * LDW + r);
 #pragma unroll
-			for (int q = 0; q < RPT; ++q) bv[q] = *reinterpret_cast<const float4*>(Ws + (b + 16 * q) * LDW + r);
+			for (int q = 0; q < RPT; ++q) bv[q] = *reinterpret_cast<const float4*>(Ws + (gb + 16 * q) * LDW + r);
 #pragma unroll
 			for (int i = 0; i < RPT; ++i)
 #pragma unroll
@@ -608,22 +660,29 @@ __global__ void __launch_bounds__(256) update_w_fused(Peers peers, size_t statH,
 					gr[i][q] = fmaf(av[i].w, bv[q].w, fmaf(av[i].z, bv[q].z, fmaf(av[i].y, bv[q].y, fmaf(av[i].x, bv[q].x, gr[i][q]))));
 		}
 #pragma unroll
-		for (int q = 0; q < RPT; ++q)
-#pragma unroll
-			for (int i = 0; i < RPT; ++i) {
-				const unsigned c1 = a + 16 * i, c2 = b + 16 * q;
-				if (c1 < k && c2 < k) stat[(size_t)c2 * k + c1] = gr[i][q];
+		for (int j = 0; j < CSUM; ++j) {
+			const unsigned c = tid / 32 + 8 * j;
+			if (c < KP) {
+				const float* col = Ws + c * LDW;
+				csum[j] += (col[lane] + col[lane + 32]) + (col[lane + 64] + col[lane + 96]);
 			}
-	}
-	{
-		const unsigned lane = tid % 32;
-		for (unsigned c = tid / 32; c < k; c += 8) {
-			const float* col = Ws + c * LDW;
-			float sum = (col[lane] + col[lane + 32]) + (col[lane + 64] + col[lane + 96]);
-#pragma unroll
-			for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-			if (lane == 0) stat[(size_t)k * k + c] = sum;
 		}
+	}
+	float* stat = statPart + (size_t)blockIdx.x * ((size_t)k * k + k);
+#pragma unroll
+	for (int q = 0; q < RPT; ++q)
+#pragma unroll
+		for (int i = 0; i < RPT; ++i) {
+			const unsigned c1 = ga + 16 * i, c2 = gb + 16 * q;
+			if (c1 < k && c2 < k) stat[(size_t)c2 * k + c1] = gr[i][q];
+		}
+#pragma unroll
+	for (int j = 0; j < CSUM; ++j) {
+		const unsigned c = tid / 32 + 8 * j;
+		float sum = csum[j];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+		if (lane == 0 && c < k) stat[(size_t)k * k + c] = sum;
 	}
 }
 
@@ -757,6 +816,12 @@ void reducePush(const Peers& peers, size_t dstOffset, unsigned statLen, const fl
 	launchCheck();
 }
 
+void waitFor(const Peers& peers, size_t flagOffset, const Control& ctl, cudaStream_t stream) {
+	if (peers.world <= 1) return;
+	wait_kernel<<<1, 32, 0, stream>>>(peers, flagOffset, ctl);
+	launchCheck();
+}
+
 void finishH(const Peers& peers, const Layout& lay, const Control& ctl, unsigned k, float center, float* B, float* corrP, cudaStream_t stream) {
 	finish_h_kernel<<<1, 1024, 0, stream>>>(peers, lay.flagsH, lay.statH, lay.statLen, ctl, k, center, B, corrP);
 	launchCheck();
@@ -766,8 +831,19 @@ template <int KP>
 static unsigned launchUpdateW(const Peers& peers, const Layout& lay, float center, unsigned rows, unsigned k, float* B, float* corrP, const float* inv, float* W,
                               size_t ldw, float* Whi, float* Wlo, const float* Ppart, size_t ldp, size_t slotStride, const unsigned char* slotCount, float eps,
                               float* statPart, bool update, cudaStream_t stream) {
-	const unsigned blocks = ceilDiv(rows, 128);
-	if (blocks == 0) return 0;
+	const unsigned panels = ceilDiv(rows, 128);
+	if (panels == 0) return 0;
+	// one wave: as many blocks as are resident at once (shared memory: 50 KB at k = 64, 4 per SM), each walking
+	// ceil(panels / blocks) panels and leaving ONE partial of the statistics
+	static int sms = 0;
+	if (sms == 0) {
+		int dev = 0;
+		CUDA_CHECK(cudaGetDevice(&dev));
+		CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	}
+	const unsigned perSm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / (smemUpdateW<KP>() + 2048)));
+	const unsigned resident = perSm * (unsigned)sms;
+	const unsigned blocks = ceilDiv(panels, ceilDiv(panels, resident));
 	if (update)
 		update_w_fused<KP, true><<<blocks, 256, smemUpdateW<KP>(), stream>>>(peers, lay.statH, lay.statLen, center, rows, k, B, corrP, inv, W, ldw, Whi, Wlo, Ppart,
 		                                                                     ldp, slotStride, slotCount, eps, statPart);

@@ -57,6 +57,10 @@ struct Control {
 	unsigned* epoch = nullptr;     // iteration counter of the protocol: advanced by the last block of pushN
 	unsigned* error = nullptr;     // set when a wait for another rank timed out
 	unsigned* tickets = nullptr;   // [4] grid-completion counters of the signalling kernels (pushN: 0, reducePush: 1, 2)
+	// 1: updateH and the H^T producer of V H^T wait for the other ranks themselves.  0: the ranks may share a GPU (thread
+	// transport of the tests) -- a kernel spinning on every SM would starve the kernels of the rank it waits for, so the
+	// engine launches waitFor (one block) in front of them instead
+	unsigned waitInKernel = 1;
 };
 constexpr size_t kNoSignal = ~(size_t)0;
 
@@ -70,6 +74,9 @@ void prepH(const Peers& peers, const Layout& lay, unsigned k, float center, floa
 // step 1b.  localSlots: [slots][ldh * N] partial products of this rank's row block (slotCount per 128-column tile)
 void pushN(const Peers& peers, const Layout& lay, const Control& ctl, unsigned kp, unsigned N, unsigned colsPerRank, size_t ldh, const float* localSlots,
            size_t localStride, const unsigned char* slotCount, cudaStream_t stream);
+
+// one block that waits until every rank has signalled the current epoch on the flag array at flagOffset (lay.flagsN / lay.flagsH)
+void waitFor(const Peers& peers, size_t flagOffset, const Control& ctl, cudaStream_t stream);
 
 // columns per block of updateH for a rank that owns nOwn columns (statPart needs max(1, ceil(nOwn / that)) * (k*k + k) floats)
 unsigned panelColumnsH(unsigned nOwn);

@@ -699,15 +699,15 @@ __global__ void __launch_bounds__(256) smooth_left_kernel(unsigned k, unsigned n
 // implied) followed by [k] tau.
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) qr_factor_kernel(unsigned k, const T* __restrict__ G, T* __restrict__ factor) {
+__global__ void __launch_bounds__(1024) qr_factor_kernel(unsigned k, const T* __restrict__ G, T* __restrict__ factor) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	T* a = reinterpret_cast<T*>(smem_raw);  // [k][k] column-major
 	T* tau = a + (size_t)k * k;
 	__shared__ T s_norm, s_tau, s_scale, s_beta;
-	const unsigned tid = threadIdx.x;
-	for (unsigned idx = tid; idx < k * k; idx += 256) a[idx] = G[idx];
+	const unsigned tid = threadIdx.x, threads = blockDim.x;
+	for (unsigned idx = tid; idx < k * k; idx += threads) a[idx] = G[idx];
 	__syncthreads();
-	const unsigned lane = tid % 32, warp = tid / 32;
+	const unsigned lane = tid % 32, warp = tid / 32, warps = threads / 32;
 	for (unsigned j = 0; j < k; ++j) {
 		T* col = a + (size_t)j * k;
 		if (warp == 0) {   // Householder vector of column j: one warp, shuffle reduction
@@ -734,13 +734,13 @@ __global__ void __launch_bounds__(256) qr_factor_kernel(unsigned k, const T* __r
 		}
 		__syncthreads();
 		if (s_norm != T(0)) {
-			for (unsigned i = j + 1 + tid; i < k; i += 256) col[i] *= s_scale;
+			for (unsigned i = j + 1 + tid; i < k; i += threads) col[i] *= s_scale;
 			__syncthreads();
 			if (tid == 0) col[j] = s_beta;
 			// apply the reflector (v_j = 1, v_i = col[i]) to the trailing columns: one warp per column, lanes along the
-			// rows (contiguous in shared memory), so all 256 threads work and no access is bank-conflicted
+			// rows (contiguous in shared memory), so every warp works and no access is bank-conflicted
 			const T tj = s_tau;
-			for (unsigned c = j + 1 + warp; c < k; c += 8) {
+			for (unsigned c = j + 1 + warp; c < k; c += warps) {
 				T* cc = a + (size_t)c * k;
 				T part = T(0);
 				for (unsigned i = j + lane; i < k; i += 32) part = fma(i == j ? T(1) : col[i], cc[i], part);
@@ -752,7 +752,61 @@ __global__ void __launch_bounds__(256) qr_factor_kernel(unsigned k, const T* __r
 		}
 		__syncthreads();
 	}
-	for (unsigned idx = tid; idx < k * k + k; idx += 256) factor[idx] = a[idx];
+	for (unsigned idx = tid; idx < k * k + k; idx += threads) factor[idx] = a[idx];
+}
+
+// M = R^-1 Q^T (k <= 128): one WARP per column of the identity, the vector spread over the lanes (entry i in lane i % 32,
+// register i / 32); the factor in shared memory.  (One thread per right-hand side walking the Householder vectors,
+// qr_solve_clamp_kernel, needs 0.98 ms for the 128 columns of the identity in fp64; this needs microseconds.)
+template <typename T>
+__global__ void __launch_bounds__(1024) qr_invert_kernel(unsigned k, const T* __restrict__ factor, T* __restrict__ M) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	T* f = reinterpret_cast<T*>(smem_raw);   // [k*k] R + Householder vectors, [k] tau
+	for (unsigned idx = threadIdx.x; idx < k * k + k; idx += blockDim.x) f[idx] = factor[idx];
+	__syncthreads();
+	const T* tau = f + (size_t)k * k;
+	const unsigned lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+	const unsigned c = blockIdx.x * (blockDim.x / 32) + warp;
+	if (c >= k) return;
+	T x[4];
+#pragma unroll
+	for (int i = 0; i < 4; ++i) x[i] = (lane + 32 * i == c) ? T(1) : T(0);
+	for (unsigned j = 0; j < k; ++j) {   // x <- Q^T x: reflector j has v_j = 1, v_i = f[j*k + i] for i > j
+		const T tj = tau[j];
+		if (tj == T(0)) continue;
+		const T* col = f + (size_t)j * k;
+		T v[4], part = T(0);
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const unsigned r = lane + 32 * i;
+			v[i] = r < k ? (r > j ? col[r] : (r == j ? T(1) : T(0))) : T(0);
+			part = fma(v[i], x[i], part);
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+		const T dot = part * tj;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) x[i] -= dot * v[i];
+	}
+	for (int j = (int)k - 1; j >= 0; --j) {   // back substitution, column oriented: x_j /= R_jj, then x_i -= R_ij x_j for i < j
+		const T* col = f + (size_t)j * k;
+		T mine = T(0);
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			if (i == j / 32) mine = x[i];
+		const T xj = __shfl_sync(0xffffffffu, mine, j % 32) / col[j];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const int r = (int)lane + 32 * i;
+			if (r == j) x[i] = xj;
+			else if (r < j) x[i] -= col[r] * xj;
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const unsigned r = lane + 32 * i;
+		if (r < k) M[(size_t)c * k + r] = x[i];
+	}
 }
 
 // one thread per right-hand side; the vector lives in shared memory (stride k+1, conflict free)
@@ -1218,7 +1272,16 @@ template <typename T>
 static void qrFactorPlain(unsigned k, const T* G, T* factor, cudaStream_t stream) {
 	const size_t smem = sizeof(T) * ((size_t)k * k + k);
 	allowSmem(qr_factor_kernel<T>, smem);
-	qr_factor_kernel<T><<<1, 256, smem, stream>>>(k, G, factor);
+	qr_factor_kernel<T><<<1, k > 32 ? 1024 : 256, smem, stream>>>(k, G, factor);   // a warp per trailing column: 32 warps at k = 128
+	launchCheck();
+}
+
+template <typename T>
+static void qrInvert(unsigned k, const T* factor, T* M, cudaStream_t stream) {
+	const size_t smem = sizeof(T) * ((size_t)k * k + k);
+	allowSmem(qr_invert_kernel<T>, smem);
+	const unsigned warps = k > 64 ? 32 : 16;
+	qr_invert_kernel<T><<<ceilDiv(k, warps), warps * 32, smem, stream>>>(k, factor, M);
 	launchCheck();
 }
 
@@ -1277,23 +1340,24 @@ void qrFactor<double>(unsigned k, const double* G, double* factor, cudaStream_t 
 // and ALS 2-4x further from the fp64 oracle than the reference's QR solve (profiles/r02_ls_stability.txt).
 template <>
 void qrFactor<float>(unsigned k, const float* G, float* factor, cudaStream_t stream, float* inverse, double* work) {
-	qrFactorPlain<float>(k, G, factor, stream);
-	if (inverse == nullptr || k > 128) return;
+	const LsSolve mode = lsSolveMode();
+	if (inverse == nullptr || k > 128 || mode == LsSolve::Qr) {   // the factor itself is what qrSolveClamp will walk
+		qrFactorPlain<float>(k, G, factor, stream);
+		return;
+	}
 	const unsigned kk = k * k;
-	if (work == nullptr || lsSolveMode() == LsSolve::InverseFp32) {
-		convert_kernel<float, float><<<ceilDiv(kk, 256), 256, 0, stream>>>(kk, nullptr, inverse, k);
-		launchCheck();
-		qrSolveGeneric<float>(k, factor, inverse, k, k, false, false, stream);
+	if (work == nullptr || mode == LsSolve::InverseFp32) {
+		qrFactorPlain<float>(k, G, factor, stream);
+		qrInvert<float>(k, factor, inverse, stream);
 		return;
 	}
 	double* Gd = work;                 // [k*k]
 	double* Fd = work + kk;            // [k*k + k]
 	double* Md = work + 2 * (size_t)kk + k;   // [k*k]
 	convert_kernel<float, double><<<ceilDiv(kk, 256), 256, 0, stream>>>(kk, G, Gd, 0);
-	qrFactorPlain<double>(k, Gd, Fd, stream);
-	convert_kernel<double, double><<<ceilDiv(kk, 256), 256, 0, stream>>>(kk, nullptr, Md, k);
 	launchCheck();
-	qrSolveGeneric<double>(k, Fd, Md, k, k, false, false, stream);
+	qrFactorPlain<double>(k, Gd, Fd, stream);
+	qrInvert<double>(k, Fd, Md, stream);
 	convert_kernel<double, float><<<ceilDiv(kk, 256), 256, 0, stream>>>(kk, Md, inverse, 0);
 	launchCheck();
 }
