@@ -232,6 +232,15 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	m_G.allocate((size_t)k * k);
 	m_Gsaved.allocate((size_t)k * k);
 	m_B.allocate((size_t)k * k);
+	{
+		// the k x k systems of the least-squares family are factorised in one block's shared memory (kernels.h qrFactor)
+		const NmfAlgorithm a = m_cfg.algorithm;
+		const bool ls = a == NmfAlgorithm::GDCLS || a == NmfAlgorithm::ALS || a == NmfAlgorithm::ACLS || a == NmfAlgorithm::AHCLS;
+		if (ls && ((size_t)k * k + k) * sizeof(T) + 64 > (size_t)227 * 1024)
+			throw EngineError(ResultType::ErrorInvalidArgument,
+			                  std::is_same<T, float>::value ? "GDCLS / ALS / ACLS / AHCLS support up to 240 features in single precision"
+			                                                : "GDCLS / ALS / ACLS / AHCLS support up to 169 features in double precision");
+	}
 	m_qr.allocate((size_t)k * k + k);
 	m_inverse.allocate((size_t)k * k);
 	if (std::is_same<T, float>::value) m_qrWork.allocate(3 * (size_t)k * k + k);
@@ -315,6 +324,8 @@ void Engine<T>::setup(const MatrixDescription<T>& V, bool vOnDevice) {
 	synchronize();
 	std::copy(m_hostSecond.get(), m_hostSecond.get() + n, m_vtvSorted.begin());
 	std::sort(m_vtvSorted.begin(), m_vtvSorted.end());
+	m_vtvSum = 0.0;
+	for (T v : m_vtvSorted) m_vtvSum += (double)v;
 	timer.mark("  tr(V^T V)");
 	if (m_fused) setupFused();
 	timer.mark("  row blocks, exchange buffer, plans");
@@ -461,6 +472,7 @@ void Engine<T>::setupFused() {
 	m_lay.flagsH = at; at = align(at + fused::kMaxRanks * sizeof(unsigned));
 	m_lay.statW = at; at = align(at + (size_t)G * m_lay.statLen * sizeof(float));
 	m_lay.statH = at; at = align(at + (size_t)G * m_lay.statLen * sizeof(float));
+	m_lay.trace = at; at = align(at + fused::kMaxRanks * sizeof(double));
 	m_lay.H = at; at = align(at + m_ldH * (size_t)N * sizeof(float));
 	m_lay.HtHi = at; at = align(at + m_ldHtFull * (size_t)k * sizeof(float));
 	m_lay.HtLo = at; at = align(at + m_ldHtFull * (size_t)k * sizeof(float));
@@ -508,6 +520,8 @@ void Engine<T>::setupFused() {
 	m_ctl.waitInKernel = (comm != nullptr && comm->ranksMayShareDevice()) ? 0u : 1u;
 	m_hostFlags.allocate(2);
 	m_hostFlags.get()[0] = m_hostFlags.get()[1] = 0;
+	m_hostTrace.allocate(fused::kMaxRanks);
+	m_vtvTotal = comm ? comm->allReduceSumHost(m_vtvSum) : m_vtvSum;
 	synchronize();
 }
 
@@ -594,6 +608,10 @@ void Engine<T>::iterateMUFused(bool err) {
 	                                        several ? nullptr : plan.wtv.slotCount, G, m_inv.get(), plan.corrN, (float)m_eps,
 	                                        err ? reinterpret_cast<float*>(m_partN.get()) : nullptr, m_statPartH.get(), m_stream);
 	stamp("update H");
+	if (err && several) {
+		fused::traceSumPush(m_peers, m_lay, reinterpret_cast<const float*>(m_partN.get()), m_nOwn, m_stream);
+		m_launches += 1;
+	}
 	fused::reducePush(m_peers, m_lay.statH, m_lay.statLen, m_statPartH.get(), blocksH, k * k + k, -1.f, m_lay.flagsH, m_ctl, 1, m_stream);
 	stamp("H statistics");
 	m_launches += 3;
@@ -1116,12 +1134,42 @@ template <typename T>
 void Engine<T>::resolveError(unsigned secondLen) {
 	const unsigned k = m_cfg.k;
 	const bool multi = m_cfg.comm && m_cfg.comm->worldSize() > 1;
-	CUDA_CHECK(cudaMemcpyAsync(m_hostSecond.get(), m_partN.get(), secondLen * sizeof(T), cudaMemcpyDeviceToHost, m_stream));
+	const double mn = m_cfg.comm ? (double)m_cfg.m * (double)m_cfg.comm->globalColumns() : (double)m_cfg.m * (double)m_cfg.n;
+	if (m_fused && m_peers.world > 1) {
+		// Row blocks: every rank holds the fp64 sums of all ranks' per-column terms (fused::traceSumPush; the wait in finishH
+		// made sure they have landed), so the residual needs no collective: sum of the column norms of V over all ranks
+		// - 2 (sums in rank order) + the k trace terms in the reference's order.  The same bits on every rank.
+		CUDA_CHECK(cudaMemcpyAsync(m_hostTrace.get(), m_sym + m_lay.trace, m_peers.world * sizeof(double), cudaMemcpyDeviceToHost, m_stream));
+		CUDA_CHECK(cudaMemcpyAsync(m_hostThird.get(), m_partK.get(), k * sizeof(T), cudaMemcpyDeviceToHost, m_stream));
+		checkDeviceFlags();   // synchronises the stream
+		T* third = m_hostThird.get();
+		std::sort(third, third + k);
+		double acc = m_vtvTotal;
+		for (unsigned g = 0; g < m_peers.world; ++g) acc -= 2.0 * m_hostTrace.get()[g];
+		for (unsigned j = 0; j < k; ++j) acc += third[j];
+		m_frobenius = std::sqrt(acc);
+		m_rmsd = m_frobenius / std::sqrt(mn);
+		return;
+	}
+	// the per-column terms arrive sorted: a radix sort on the device instead of a std::sort of n floats on the host
+	const bool deviceSort = secondLen >= 2048;
+	const T* secondSource = m_partN.get();
+	if (deviceSort) {
+		if (m_sortedSecond.count() < secondLen) m_sortedSecond.allocate(secondLen);
+		const size_t needed = kern::sortAscending<T>(m_partN.get(), m_sortedSecond.get(), secondLen, m_sortTemp.get(), m_sortTemp.count(), m_stream);
+		if (needed > m_sortTemp.count()) {
+			m_sortTemp.allocate(needed);
+			kern::sortAscending<T>(m_partN.get(), m_sortedSecond.get(), secondLen, m_sortTemp.get(), m_sortTemp.count(), m_stream);
+		}
+		secondSource = m_sortedSecond.get();
+		m_launches += 2;
+	}
+	CUDA_CHECK(cudaMemcpyAsync(m_hostSecond.get(), secondSource, secondLen * sizeof(T), cudaMemcpyDeviceToHost, m_stream));
 	CUDA_CHECK(cudaMemcpyAsync(m_hostThird.get(), m_partK.get(), k * sizeof(T), cudaMemcpyDeviceToHost, m_stream));
 	checkDeviceFlags();   // synchronises the stream
 	T* second = m_hostSecond.get();
 	T* third = m_hostThird.get();
-	std::sort(second, second + secondLen);
+	if (!deviceSort) std::sort(second, second + secondLen);
 	std::sort(third, third + k);
 	double acc = 0.0;
 	if (!multi) {
@@ -1147,7 +1195,6 @@ void Engine<T>::resolveError(unsigned secondLen) {
 		}
 	}
 	m_frobenius = std::sqrt(acc);
-	const double mn = m_cfg.comm ? (double)m_cfg.m * (double)m_cfg.comm->globalColumns() : (double)m_cfg.m * (double)m_cfg.n;
 	m_rmsd = m_frobenius / std::sqrt(mn);
 }
 

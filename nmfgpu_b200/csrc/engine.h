@@ -160,7 +160,10 @@ private:
 	DeviceBuffer<T> m_partN, m_partK;
 	PinnedBuffer<T> m_hostSecond, m_hostThird;
 	std::vector<T> m_vtvSorted;
-	double m_vtvSum = 0.0;
+	double m_vtvSum = 0.0, m_vtvTotal = 0.0;   // sum of the sorted column norms of V: own shard, all ranks
+	DeviceBuffer<T> m_sortedSecond;            // the per-column residual terms, sorted on the device before their D2H
+	DeviceBuffer<unsigned char> m_sortTemp;
+	PinnedBuffer<double> m_hostTrace;
 	double m_frobenius = 0.0, m_rmsd = 0.0;
 	double m_sparsityW = 0.0, m_sparsityH = 0.0;
 	DeviceBuffer<double> m_sparsityPartials;

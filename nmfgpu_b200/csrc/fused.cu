@@ -17,12 +17,15 @@ namespace {
 // A rank signals by storing its epoch into a flag word that lives in the RECEIVER's exchange buffer (so waiting spins on
 // local memory).  The data the flag announces was written by earlier kernels of the same stream (peer stores); the
 // kernel boundary plus the system fence order it before the flag.
-__device__ __forceinline__ void storeReleaseSystem(unsigned* p, unsigned v) {
-	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// Flags are written and polled with RELAXED system-scope accesses between explicit fences: a st.release.sys per peer is
+// a fence per peer, and each of them waits for the previous peer's store to be acknowledged over NVLink -- eight
+// sequential round trips, 16 of the 28 us the H-side signal took at 8 GPUs.  One fence, then eight independent stores.
+__device__ __forceinline__ void storeRelaxedSystem(unsigned* p, unsigned v) {
+	asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned loadAcquireSystem(const unsigned* p) {
+__device__ __forceinline__ unsigned loadRelaxedSystem(const unsigned* p) {
 	unsigned v;
-	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
 __device__ __forceinline__ unsigned long long globalTimer() {
@@ -33,9 +36,9 @@ __device__ __forceinline__ unsigned long long globalTimer() {
 
 // one thread: tell every rank "epoch e of this rank is out"
 __device__ void signalPeers(const Peers& peers, size_t flagOffset, unsigned epoch) {
-	__threadfence_system();
+	__threadfence_system();   // everything this rank stored (observed by this thread) is performed before any flag
 	for (unsigned g = 0; g < peers.world; ++g)
-		storeReleaseSystem(reinterpret_cast<unsigned*>(peers.base[g] + flagOffset) + peers.rank, epoch);
+		storeRelaxedSystem(reinterpret_cast<unsigned*>(peers.base[g] + flagOffset) + peers.rank, epoch);
 }
 
 // one thread: wait until every rank has signalled `epoch`.  A rank that never answers (it failed) must not hang the GPU:
@@ -47,14 +50,14 @@ __device__ void waitPeers(const Peers& peers, size_t flagOffset, unsigned epoch,
 	for (unsigned g = 0; g < peers.world; ++g) {
 		unsigned spins = 0;
 		// epochs only grow; "reached" must survive a wrap of the 32-bit counter
-		while ((int)(loadAcquireSystem(mine + g) - epoch) < 0) {
+		while ((int)(loadRelaxedSystem(mine + g) - epoch) < 0) {
 			if ((++spins & 0x3FF) == 0 && globalTimer() - t0 > 10000000000ull) {
 				atomicExch(error, 1u);
 				return;
 			}
 		}
 	}
-	__threadfence_system();
+	__threadfence_system();   // acquire: nothing after this is satisfied from before the flags were seen
 }
 
 __device__ __forceinline__ unsigned currentEpoch(const Control& ctl) { return *reinterpret_cast<volatile const unsigned*>(ctl.epoch); }
@@ -151,6 +154,23 @@ __global__ void __launch_bounds__(1024) finish_h_kernel(Peers peers, size_t flag
 		for (unsigned g = 0; g < peers.world; ++g) s += __ldcg(local + (size_t)g * statLen + idx);   // rank order: identical on every rank
 		if (idx < k * k) B[idx] = s;
 		else corrP[idx - k * k] = center * s;
+	}
+}
+
+// residual iterations over several ranks: the sum of the per-column terms of the own columns (fp64, fixed order) goes to
+// every rank, so that each of them can form the residual without a host-side collective
+__global__ void __launch_bounds__(1024) trace_sum_push_kernel(Peers peers, size_t oTrace, const float* __restrict__ tracePartials, unsigned count) {
+	__shared__ double red[32];
+	double a = 0.0;
+	for (unsigned i = threadIdx.x; i < count; i += 1024) a += (double)tracePartials[i];
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+	if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = a;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double total = 0.0;
+		for (int w = 0; w < 32; ++w) total += red[w];
+		for (unsigned g = 0; g < peers.world; ++g) reinterpret_cast<double*>(peers.base[g] + oTrace)[peers.rank] = total;
 	}
 }
 
@@ -813,6 +833,11 @@ void pushN(const Peers& peers, const Layout& lay, const Control& ctl, unsigned k
 void reducePush(const Peers& peers, size_t dstOffset, unsigned statLen, const float* partials, unsigned blocks, unsigned count, float flag,
                 size_t signalFlags, const Control& ctl, unsigned ticket, cudaStream_t stream) {
 	reduce_push_kernel<<<ceilDiv(count, 32), 256, 0, stream>>>(peers, dstOffset, statLen, partials, blocks, count, flag, signalFlags, ctl, ticket);
+	launchCheck();
+}
+
+void traceSumPush(const Peers& peers, const Layout& lay, const float* tracePartials, unsigned count, cudaStream_t stream) {
+	trace_sum_push_kernel<<<1, 1024, 0, stream>>>(peers, lay.trace, tracePartials, count);
 	launchCheck();
 }
 

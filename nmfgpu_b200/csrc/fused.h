@@ -45,6 +45,7 @@ struct Peers {
 struct Layout {
 	size_t flagsN = 0, flagsH = 0;   // kMaxRanks unsigned each: epoch of the last signal of every rank
 	size_t statW = 0, statH = 0;     // [world][statLen] floats: k*k Gram + k sums (+ 1 flag for W: 1 = columns get normalised)
+	size_t trace = 0;                // [world] doubles: every rank's sum of the per-column residual terms (residual iterations)
 	size_t H = 0, HtHi = 0, HtLo = 0;
 	size_t slots = 0;                // partial products of W^T V.  One rank: [slots][ldh * n], written by the tensor-core kernel;
 	                                 // several: [world][ldh * colsPerRank], one partial per rank for the own columns (pushN)
@@ -74,6 +75,10 @@ void prepH(const Peers& peers, const Layout& lay, unsigned k, float center, floa
 // step 1b.  localSlots: [slots][ldh * N] partial products of this rank's row block (slotCount per 128-column tile)
 void pushN(const Peers& peers, const Layout& lay, const Control& ctl, unsigned kp, unsigned N, unsigned colsPerRank, size_t ldh, const float* localSlots,
            size_t localStride, const unsigned char* slotCount, cudaStream_t stream);
+
+// residual iterations over several ranks, between updateH and the reducePush that signals: the fp64 sum of tracePartials
+// (count = own columns) stored to lay.trace[rank] on every rank
+void traceSumPush(const Peers& peers, const Layout& lay, const float* tracePartials, unsigned count, cudaStream_t stream);
 
 // one block that waits until every rank has signalled the current epoch on the flag array at flagOffset (lay.flagsN / lay.flagsH)
 void waitFor(const Peers& peers, size_t flagOffset, const Control& ctl, cudaStream_t stream);

@@ -135,6 +135,10 @@ void finishStatsH(unsigned k, const float* stat, float center, float* B, float* 
 template <typename T>
 void absInPlace(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream_t stream);
 
+// out <- in sorted ascending (radix sort).  Returns the scratch bytes needed; sorts only when temp holds that many.
+template <typename T>
+size_t sortAscending(const T* in, T* out, unsigned count, void* temp, size_t tempBytes, cudaStream_t stream);
+
 // partial[2 b] = sum |x|, partial[2 b + 1] = sum x^2 over block b's share of the rows x cols matrix X (fp64; `blocks` blocks)
 template <typename T>
 void absSquareSums(unsigned rows, unsigned cols, const T* X, size_t ld, double* partial, unsigned blocks, cudaStream_t stream);

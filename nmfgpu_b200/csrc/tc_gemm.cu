@@ -364,14 +364,14 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::HELPER_REGS));
 		if (lane == 0) {
 			if (p.gateCount != 0) {
-				// acquire at system scope (the flags and the data behind them were stored by other GPUs), then order the TMA
-				// reads -- async proxy -- behind it.  A rank that never signals must not hang the GPU: give up after 10 s.
+				// poll the flags (stored by other GPUs, like the data behind them), acquire at system scope once they are all
+				// there, then order the TMA reads -- async proxy -- behind it.  A rank that never signals must not hang the GPU: give up after 10 s.
 				const unsigned epoch = *reinterpret_cast<volatile const unsigned*>(p.gateEpoch);
 				unsigned long long t0 = 0;
 				for (unsigned g = 0; g < p.gateCount; ++g) {
 					unsigned spins = 0, seen;
 					for (;;) {
-						asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.gateFlags + g) : "memory");
+						asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.gateFlags + g) : "memory");
 						if ((int)(seen - epoch) >= 0) break;
 						if ((++spins & 0x3FF) == 0) {
 							unsigned long long now;
@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(Rings<KPM>::THREADS, 1) tc_stream_gemm(const _
 						}
 					}
 				}
+				asm volatile("fence.acq_rel.sys;" ::: "memory");   // one acquire fence after all flags (relaxed polls)
 				asm volatile("fence.proxy.async;" ::: "memory");
 			}
 			SegmentWalker walk(p, blockIdx.x);

@@ -501,3 +501,13 @@ def test_full_size_properties(L):
     rows = slice(70_000, 70_016)
     Vr = uniform_block(42, 16, n, total_rows=m, row0=70_000).astype(np.float64)
     assert rel(vht[rows, :], Vr @ H.astype(np.float64).T) <= 5e-7
+
+
+def test_ls_rank_limit_is_a_clear_error(L):
+    """the k x k systems of the least-squares family are factorised in one block's shared memory: ranks beyond that are
+    rejected up front with ErrorInvalidArgument (the reference's cuSOLVER path has no such limit)"""
+    V, W0, H0 = dense_inputs(600, 500, 250, seed=3)
+    r = L.compute(V, 250, algorithm="als", W0=W0, H0=H0, iterations=2)
+    assert r["rc"] == ResultType.ErrorInvalidArgument
+    r = L.compute(V, 250, algorithm="mu", W0=W0, H0=H0, iterations=2)          # MU has no such limit (SIMT path beyond k = 128)
+    assert r["rc"] == ResultType.Success

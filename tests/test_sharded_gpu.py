@@ -2,8 +2,11 @@
 
 The ranks are THREADS of this process (nmfgpu_b200_dist_local_unique_id, csrc/dist.h), all on cuda:0, so the test runs on a
 single-GPU box.  What executes is the product code: the same engine, the same kernels and the same exchange protocol as
-with one process per GPU -- peer stores into the other ranks' exchange buffers, flag words, the tcgen05 kernel routing
-its tiles to the owners -- only the transport of the setup-time collectives differs (memcpy instead of NCCL).
+with one process per GPU -- peer stores into the other ranks' exchange buffers, epoch flags, last-block signals.  Two things
+differ: the setup-time collectives go through memcpy instead of NCCL, and because the ranks share one GPU the waits for the
+other ranks run as one-block kernels of their own instead of inside the update / product kernels (a kernel spinning on every
+SM would starve the rank it waits for; csrc/dist.h ranksMayShareDevice).  The in-kernel waits are what tools/dist_check.py
+and bench.py --gpus N exercise with one process per GPU.
 """
 import ctypes
 import os
