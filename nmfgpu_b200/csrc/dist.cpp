@@ -291,7 +291,8 @@ public:
 		std::vector<const float*> all((size_t)m_world);
 		allGatherHost(&send, sizeof(send), all.data());
 		for (int g = 0; g < m_world; ++g)
-			CUDA_CHECK(cudaMemcpyAsync(recv + (size_t)g * countPerRank, all[(size_t)g], countPerRank * sizeof(float), cudaMemcpyDefault, stream));
+			if (all[(size_t)g] != recv + (size_t)g * countPerRank)   // in place: the own block is already where it belongs
+				CUDA_CHECK(cudaMemcpyAsync(recv + (size_t)g * countPerRank, all[(size_t)g], countPerRank * sizeof(float), cudaMemcpyDefault, stream));
 		CUDA_CHECK(cudaStreamSynchronize(stream));
 		m_group->barrier();
 		++m_calls;

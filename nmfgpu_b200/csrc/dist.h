@@ -43,9 +43,9 @@ public:
 
 	// whether the device collectives below may be recorded into a CUDA graph (the local transport synchronises inside them)
 	virtual bool capturable() const = 0;
-	// whether two ranks may share one GPU (the thread transport of the tests).  A kernel that waits for another rank while
-	// it occupies the SMs that rank's kernels need would then wait for ever, so the engine waits in one-block kernels of
-	// their own instead of inside the update / product kernels (engine.cu).
+	// whether two ranks may share one GPU (the thread transport of the tests).  A kernel that waits for another rank can
+	// then keep that rank's kernels from running, so the engine lets the ranks meet on the host before every such kernel
+	// (engine.cu m_hostLockstep).
 	virtual bool ranksMayShareDevice() const = 0;
 	// ---- device collectives, enqueued on `stream` (NCCL) or completed before returning (local)
 	virtual void allReduceSum(float* buffer, size_t count, cudaStream_t stream) = 0;

@@ -473,7 +473,7 @@ void Engine<T>::setupFused() {
 	m_lay.statW = at; at = align(at + (size_t)G * m_lay.statLen * sizeof(float));
 	m_lay.statH = at; at = align(at + (size_t)G * m_lay.statLen * sizeof(float));
 	m_lay.trace = at; at = align(at + fused::kMaxRanks * sizeof(double));
-	m_lay.H = at; at = align(at + m_ldH * (size_t)N * sizeof(float));
+	m_lay.H = at; at = align(at + m_ldH * (size_t)G * m_colsPerRank * sizeof(float));   // room for an in-place all-gather of the owners' blocks
 	m_lay.HtHi = at; at = align(at + m_ldHtFull * (size_t)k * sizeof(float));
 	m_lay.HtLo = at; at = align(at + m_ldHtFull * (size_t)k * sizeof(float));
 	// partial products of W^T V: one GPU -- the stream-K slots of the tensor-core kernel; several -- one partial per rank
@@ -517,7 +517,12 @@ void Engine<T>::setupFused() {
 	m_ctl.epoch = m_ctlWords.get();
 	m_ctl.error = m_ctlWords.get() + 1;
 	m_ctl.tickets = m_ctlWords.get() + 4;
-	m_ctl.waitInKernel = (comm != nullptr && comm->ranksMayShareDevice()) ? 0u : 1u;
+	m_wStatFlag = reinterpret_cast<float*>(m_ctlWords.get() + 16);
+	// Ranks that share a GPU (the thread transport of the tests): a kernel that waits for another rank's signal can keep
+	// that rank's kernels from being scheduled -- or from being submitted at all -- for as long as it spins.  There the
+	// ranks proceed in lockstep on the HOST at the two points of an iteration where they wait for each other (stream
+	// synchronise + barrier, no CUDA graphs); the in-kernel waits still run and find their flags already set.
+	m_hostLockstep = comm != nullptr && comm->ranksMayShareDevice();
 	m_hostFlags.allocate(2);
 	m_hostFlags.get()[0] = m_hostFlags.get()[1] = 0;
 	m_hostTrace.allocate(fused::kMaxRanks);
@@ -555,9 +560,10 @@ void Engine<T>::finishInitialisationFused() {
 	}
 	float* W = reinterpret_cast<float*>(m_W[m_wCur].get()) + m_r0;
 	kern::splitTf32(m_mr, k, W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, m_ldW, m_stream);
-	const unsigned blocks = fused::updateW(m_peers, m_lay, 0.f, m_mr, k, nullptr, nullptr, nullptr, W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, nullptr, 0, 0,
-	                                       nullptr, 0.f, m_statPartW.get(), false, m_stream);
-	fused::reducePush(m_peers, m_lay.statW, m_lay.statLen, m_statPartW.get(), blocks, k * k + k, 0.f, fused::kNoSignal, m_ctl, 2, m_stream);
+	m_wUpdated = false;
+	m_blocksW = fused::updateW(m_peers, m_lay, 0.f, m_mr, k, nullptr, nullptr, nullptr, W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0, nullptr, 0, 0,
+	                           nullptr, 0.f, m_statPartW.get(), m_wStatFlag, false, m_stream);
+	fused::reducePush(m_peers, m_lay.statW, m_lay.statLen, m_statPartW.get(), m_blocksW, k * k + k, 0.f, fused::kNoSignal, m_ctl, 2, m_stream);
 	float* Hfull = reinterpret_cast<float*>(m_sym + m_lay.H);
 	const float* Hmine = reinterpret_cast<const float*>(m_H[m_hCur].get());
 	if (comm == nullptr) {
@@ -596,13 +602,15 @@ void Engine<T>::iterateMUFused(bool err) {
 	productWtVFused();
 	stamp("product W^T V");
 	if (several) {
-		fused::pushN(m_peers, m_lay, m_ctl, plan.kp, m_globalN, m_colsPerRank, m_ldH, m_Nlocal.get(), m_strideN, plan.wtv.slotCount, m_stream);
+		// (the same launch sums and sends the statistics of the last W update: no launch of their own over several ranks)
+		fused::pushN(m_peers, m_lay, m_ctl, plan.kp, m_globalN, m_colsPerRank, m_ldH, m_Nlocal.get(), m_strideN, plan.wtv.slotCount, m_statPartW.get(), m_blocksW,
+		             k * k + k, m_wStatFlag, m_stream);
 		stamp("partials to the owners");
 		m_launches += 1;
 	}
-	if (several && m_ctl.waitInKernel == 0) {
-		fused::waitFor(m_peers, m_lay.flagsN, m_ctl, m_stream);
-		m_launches += 1;
+	if (several && m_hostLockstep) {
+		synchronize();
+		m_cfg.comm->barrier();
 	}
 	const unsigned blocksH = fused::updateH(m_peers, m_lay, m_ctl, plan.center, k, m_c0, m_nOwn, m_colsPerRank, m_ldH, m_ldHtFull, several ? 1u : m_slotsPerRank,
 	                                        several ? nullptr : plan.wtv.slotCount, G, m_inv.get(), plan.corrN, (float)m_eps,
@@ -615,6 +623,10 @@ void Engine<T>::iterateMUFused(bool err) {
 	fused::reducePush(m_peers, m_lay.statH, m_lay.statLen, m_statPartH.get(), blocksH, k * k + k, -1.f, m_lay.flagsH, m_ctl, 1, m_stream);
 	stamp("H statistics");
 	m_launches += 3;
+	if (several && m_hostLockstep) {
+		synchronize();
+		m_cfg.comm->barrier();
+	}
 	if (err || m_cfg.constantW) {
 		// H H^T before the W update (the trace term), or without one: as a kernel of its own (it waits for the other ranks)
 		fused::finishH(m_peers, m_lay, m_ctl, k, plan.center, B, plan.corrP, m_stream);
@@ -631,19 +643,19 @@ void Engine<T>::iterateMUFused(bool err) {
 		gate.epoch = m_ctl.epoch;
 		gate.error = m_ctl.error;
 		gate.count = m_peers.world;
-		if (several && m_ctl.waitInKernel == 0) {
-			fused::waitFor(m_peers, m_lay.flagsH, m_ctl, m_stream);
-			m_launches += 1;
-		}
-		tc::gemmVHt(plan, m_PpartR.get(), m_ldPr, m_stridePr, m_stream, (several && m_ctl.waitInKernel != 0) ? &gate : nullptr);
+		tc::gemmVHt(plan, m_PpartR.get(), m_ldPr, m_stridePr, m_stream, several ? &gate : nullptr);
 		stamp("product V H^T");
 		float* W = reinterpret_cast<float*>(m_W[m_wCur].get()) + m_r0;
-		const unsigned blocksW = fused::updateW(m_peers, m_lay, plan.center, m_mr, k, B, plan.corrP, m_inv.get(), W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0,
-		                                        m_PpartR.get(), m_ldPr, m_stridePr, plan.vht.slotCount, (float)m_eps, m_statPartW.get(), true, m_stream);
+		m_wUpdated = true;
+		m_blocksW = fused::updateW(m_peers, m_lay, plan.center, m_mr, k, B, plan.corrP, m_inv.get(), W, m_ldW, m_Whi.get() + m_r0, m_Wlo.get() + m_r0,
+		                           m_PpartR.get(), m_ldPr, m_stridePr, plan.vht.slotCount, (float)m_eps, m_statPartW.get(), m_wStatFlag, true, m_stream);
 		stamp("update W");
-		fused::reducePush(m_peers, m_lay.statW, m_lay.statLen, m_statPartW.get(), blocksW, k * k + k, 1.f, fused::kNoSignal, m_ctl, 2, m_stream);
-		stamp("W statistics");
-		m_launches += 3;
+		m_launches += 2;
+		if (!several) {   // several ranks: the next iteration's pushN does this
+			fused::reducePush(m_peers, m_lay.statW, m_lay.statLen, m_statPartW.get(), m_blocksW, k * k + k, 1.f, fused::kNoSignal, m_ctl, 2, m_stream);
+			stamp("W statistics");
+			m_launches += 1;
+		}
 	}
 	if (err) resolveError(m_nOwn);
 }
@@ -654,6 +666,15 @@ template <typename T>
 void Engine<T>::storeFused(const MatrixDescription<T>& hostW, const MatrixDescription<T>& hostH) {
 	Communicator* comm = (m_cfg.comm != nullptr && m_cfg.comm->worldSize() > 1) ? m_cfg.comm : nullptr;
 	const unsigned m = m_cfg.m, n = m_cfg.n, k = m_cfg.k;
+	if (comm != nullptr) {
+		// over several ranks the statistics of the last W update travel with the NEXT iteration's pushN: send them now
+		fused::reducePush(m_peers, m_lay.statW, m_lay.statLen, m_statPartW.get(), m_blocksW, k * k + k, m_wUpdated ? 1.f : 0.f, fused::kNoSignal, m_ctl, 2,
+		                  m_stream);
+		// and H: every rank keeps only its own columns current (fused.cu update_h_fused); in-place all-gather of the owners' blocks
+		float* Hall = reinterpret_cast<float*>(m_sym + m_lay.H);
+		const size_t block = m_ldH * (size_t)m_colsPerRank;
+		comm->allGather(Hall + block * m_peers.rank, Hall, block, m_stream);
+	}
 	synchronize();
 	if (comm != nullptr) comm->barrier();   // the statistics of every rank's last W update have landed
 	fused::prepH(m_peers, m_lay, k, m_tc->plan.center, m_statSum.get(), reinterpret_cast<float*>(m_Gsaved.get()), m_inv.get(), m_tc->plan.corrN, m_stream);
@@ -1221,7 +1242,7 @@ void Engine<T>::iterateNoError(unsigned count) {
 	}();
 	// (the in-stream profiler records events, which a capture cannot hold)
 	const bool collectivesOk = m_fused || m_cfg.comm == nullptr || m_cfg.comm->capturable();   // the fused iteration calls no collective
-	if (graphs && collectivesOk && count >= 4 && !m_profile && getenv("NMFGPU_TC_DEBUG") == nullptr) {
+	if (graphs && collectivesOk && !m_hostLockstep && count >= 4 && !m_profile && getenv("NMFGPU_TC_DEBUG") == nullptr) {
 		cudaGraphExec_t& exec = m_graphExec[m_wCur][m_hCur];
 		if (exec == nullptr) {
 			iterate(false);   // an eager pair first: lazily set kernel attributes must not happen inside the capture

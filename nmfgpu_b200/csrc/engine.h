@@ -198,6 +198,10 @@ private:
 	size_t m_ldVr = 0, m_ldHtFull = 0, m_ldPr = 0, m_stridePr = 0;
 	DeviceBuffer<float> m_Vr, m_Nlocal, m_PpartR, m_statSum, m_inv, m_statPartH, m_statPartW;
 	DeviceBuffer<unsigned> m_ctlWords;
+	float* m_wStatFlag = nullptr;      // device: 1 when m_statPartW describes an updated W (columns get normalised), 0 for the initial factors
+	unsigned m_blocksW = 0;            // block partials in m_statPartW
+	bool m_wUpdated = false;           // the host's copy of that flag
+	bool m_hostLockstep = false;       // ranks share a GPU (test transport): host barriers where the ranks wait for each other, no graphs
 	PinnedBuffer<unsigned> m_hostFlags;
 	const float* m_Vblock = nullptr;   // V[I, :]: m_Vr, or V itself on one GPU
 };

@@ -174,9 +174,8 @@ __global__ void __launch_bounds__(1024) trace_sum_push_kernel(Peers peers, size_
 	}
 }
 
-__global__ void wait_kernel(Peers peers, size_t flagOffset, Control ctl) {
-	if (threadIdx.x == 0) waitPeers(peers, flagOffset, currentEpoch(ctl), ctl.error);
-}
+__device__ void reduceAndPush(const Peers& peers, size_t dstOffset, unsigned statLen, const float* __restrict__ partials, unsigned blocks, unsigned count,
+                              float flag, unsigned bx);
 
 // ---- step 1b (several ranks) ---------------------------------------------------------------------------------------------
 // The partial product of the own row block, summed over its stream-K slots, goes to the rank that owns the columns: one
@@ -185,7 +184,16 @@ __global__ void wait_kernel(Peers peers, size_t flagOffset, Control ctl) {
 // bytes cost 50 us over NVLink at 8 GPUs: W^T V 144 us against 93 us for the same launch without peers.)
 __global__ void __launch_bounds__(256) push_n_kernel(Peers peers, size_t oSlots, size_t flagsN, Control ctl, unsigned kp, unsigned N, unsigned colsPerRank,
                                                      size_t ldh, const float* __restrict__ local, size_t localStride,
-                                                     const unsigned char* __restrict__ slotCount) {
+                                                     const unsigned char* __restrict__ slotCount, unsigned pushBlocks, size_t statW, unsigned statLen,
+                                                     const float* __restrict__ statPartials, unsigned statBlocks, unsigned statCount,
+                                                     const float* __restrict__ statFlag) {
+	if (blockIdx.x >= pushBlocks) {
+		// the CTAs behind the pushing ones: the statistics of this rank's rows of W (block partials of the last W update,
+		// or of the initial factors) summed and stored to every rank -- they travel with the same signal
+		reduceAndPush(peers, statW, statLen, statPartials, statBlocks, statCount, *statFlag, blockIdx.x - pushBlocks);
+		lastBlockSignals(peers, flagsN, ctl, 0, true);
+		return;
+	}
 	const unsigned perCol = kp / 4;
 	const unsigned long long idx = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
 	const unsigned j = (unsigned)(idx / perCol), q = (unsigned)(idx % perCol);
@@ -240,7 +248,7 @@ __global__ void __launch_bounds__(COLS * 4) update_h_fused(Peers peers, size_t o
 	const float* Hloc = reinterpret_cast<const float*>(peers.base[peers.rank] + oH);
 	const float* Nloc = reinterpret_cast<const float*>(peers.base[peers.rank] + oSlots);
 	// every rank's partials of W^T V and the statistics of its rows of W have landed here
-	if (peers.world > 1 && ctl.waitInKernel != 0) {
+	if (peers.world > 1) {
 		if (tid == 0) waitPeers(peers, flagsN, currentEpoch(ctl), ctl.error);
 		__syncthreads();
 	}
@@ -420,12 +428,15 @@ __global__ void __launch_bounds__(COLS * 4) update_h_fused(Peers peers, size_t o
 	}
 	__syncthreads();
 	// the new columns and their transposed TF32 split go to every rank: the all-gather of H is this kernel's epilogue
-	for (unsigned g = 0; g < peers.world; ++g) {
-		float* Hout = reinterpret_cast<float*>(peers.base[g] + oH);
+	{   // H itself is needed by its owner only (the next update of these columns); the other ranks read H^T hi/lo.  The
+		// store of the factors gathers H (engine.cu storeFused)
+		float* Hout = reinterpret_cast<float*>(peers.base[peers.rank] + oH);
 		for (unsigned idx = tid; idx < COLS * KP; idx += NT) {
 			const unsigned t = idx % KP, j = idx / KP;
 			if (jl0 + j < nOwn && t < k) Hout[(size_t)(j0 + j) * ldh + t] = Hs[t * LDJ + j];
 		}
+	}
+	for (unsigned g = 0; g < peers.world; ++g) {
 		float* HtHi = reinterpret_cast<float*>(peers.base[g] + oHtHi);
 		float* HtLo = reinterpret_cast<float*>(peers.base[g] + oHtLo);
 		for (unsigned idx = tid; idx < COLS * KP; idx += NT) {
@@ -481,13 +492,14 @@ __global__ void __launch_bounds__(COLS * 4) update_h_fused(Peers peers, size_t o
 	}
 }
 
-// ---- steps 4 and 8 -------------------------------------------------------------------------------------------------------
-// 32 entries x 8 block groups per CTA; every thread keeps four loads in flight; fixed summation order
-__global__ void __launch_bounds__(256) reduce_push_kernel(Peers peers, size_t dstOffset, unsigned statLen, const float* __restrict__ partials,
-                                                          unsigned blocks, unsigned count, float flag, size_t signalFlags, Control ctl, unsigned ticket) {
+// ---- steps 3 and 6 -------------------------------------------------------------------------------------------------------
+// 32 entries x 8 block groups per CTA (bx = index of the CTA among those that reduce); every thread keeps four loads in
+// flight; fixed summation order.  All threads of the CTA must call it.
+__device__ void reduceAndPush(const Peers& peers, size_t dstOffset, unsigned statLen, const float* __restrict__ partials, unsigned blocks, unsigned count,
+                              float flag, unsigned bx) {
 	__shared__ float red[8][33];
 	const unsigned lane = threadIdx.x % 32, grp = threadIdx.x / 32;
-	const unsigned x = blockIdx.x * 32 + lane;
+	const unsigned x = bx * 32 + lane;
 	float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 	if (x < count) {
 		unsigned b = grp;
@@ -505,8 +517,13 @@ __global__ void __launch_bounds__(256) reduce_push_kernel(Peers peers, size_t ds
 		const float v = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) + ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
 		for (unsigned g = 0; g < peers.world; ++g) reinterpret_cast<float*>(peers.base[g] + dstOffset)[(size_t)peers.rank * statLen + x] = v;
 	}
-	if (flag >= 0.f && blockIdx.x == 0 && threadIdx.x == 0)
+	if (flag >= 0.f && bx == 0 && threadIdx.x == 0)
 		for (unsigned g = 0; g < peers.world; ++g) reinterpret_cast<float*>(peers.base[g] + dstOffset)[(size_t)peers.rank * statLen + count] = flag;
+}
+
+__global__ void __launch_bounds__(256) reduce_push_kernel(Peers peers, size_t dstOffset, unsigned statLen, const float* __restrict__ partials,
+                                                          unsigned blocks, unsigned count, float flag, size_t signalFlags, Control ctl, unsigned ticket) {
+	reduceAndPush(peers, dstOffset, statLen, partials, blocks, count, flag, blockIdx.x);
 	// H side: "my columns of H (the update kernel before this one) and their statistics are out"
 	if (signalFlags != kNoSignal && peers.world > 1) lastBlockSignals(peers, signalFlags, ctl, ticket, false);
 }
@@ -524,8 +541,11 @@ __global__ void __launch_bounds__(256, KP <= 64 ? 3 : 1) update_w_fused(Peers pe
                                                      float* __restrict__ Bout, float* __restrict__ corrPout, const float* __restrict__ inv,
                                                      float* __restrict__ W, size_t ldw, float* __restrict__ Whi, float* __restrict__ Wlo,
                                                      const float* __restrict__ Ppart, size_t ldp, size_t slotStride,
-                                                     const unsigned char* __restrict__ slotCount, float eps, float* __restrict__ statPart) {
+                                                     const unsigned char* __restrict__ slotCount, float eps, float* __restrict__ statPart,
+                                                     float* __restrict__ statFlag) {
 	constexpr int ROWS = 128, CPT = KP / 8, LDW = ROWS + 4, RPT = KP / 16, CSUM = (KP + 7) / 8;
+	// 1: these statistics describe an updated W whose columns get normalised; 0: the initial factors, used as they are
+	if (blockIdx.x == 0 && threadIdx.x == 0 && statFlag != nullptr) *statFlag = UPDATE ? 1.f : 0.f;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	__shared__ float corrS[128], invS[128];
 	float* Ws = reinterpret_cast<float*>(smem_raw);  // [KP t][LDW]: Ws[t*LDW + r] = W[i0 + r, t] (scaled)
@@ -823,10 +843,13 @@ unsigned updateH(const Peers& peers, const Layout& lay, const Control& ctl, floa
 }
 
 void pushN(const Peers& peers, const Layout& lay, const Control& ctl, unsigned kp, unsigned N, unsigned colsPerRank, size_t ldh, const float* localSlots,
-           size_t localStride, const unsigned char* slotCount, cudaStream_t stream) {
+           size_t localStride, const unsigned char* slotCount, const float* statPartials, unsigned statBlocks, unsigned statCount, const float* statFlag,
+           cudaStream_t stream) {
 	const unsigned long long threads = (unsigned long long)N * (kp / 4);
-	push_n_kernel<<<(unsigned)std::max<unsigned long long>(1, (threads + 255) / 256), 256, 0, stream>>>(peers, lay.slots, lay.flagsN, ctl, kp, N, colsPerRank, ldh,
-	                                                                                                    localSlots, localStride, slotCount);
+	const unsigned pushBlocks = (unsigned)std::max<unsigned long long>(1, (threads + 255) / 256);
+	push_n_kernel<<<pushBlocks + ceilDiv(statCount, 32), 256, 0, stream>>>(peers, lay.slots, lay.flagsN, ctl, kp, N, colsPerRank, ldh, localSlots, localStride,
+	                                                                        slotCount, pushBlocks, lay.statW, lay.statLen, statPartials, statBlocks, statCount,
+	                                                                        statFlag);
 	launchCheck();
 }
 
@@ -841,12 +864,6 @@ void traceSumPush(const Peers& peers, const Layout& lay, const float* traceParti
 	launchCheck();
 }
 
-void waitFor(const Peers& peers, size_t flagOffset, const Control& ctl, cudaStream_t stream) {
-	if (peers.world <= 1) return;
-	wait_kernel<<<1, 32, 0, stream>>>(peers, flagOffset, ctl);
-	launchCheck();
-}
-
 void finishH(const Peers& peers, const Layout& lay, const Control& ctl, unsigned k, float center, float* B, float* corrP, cudaStream_t stream) {
 	finish_h_kernel<<<1, 1024, 0, stream>>>(peers, lay.flagsH, lay.statH, lay.statLen, ctl, k, center, B, corrP);
 	launchCheck();
@@ -855,7 +872,7 @@ void finishH(const Peers& peers, const Layout& lay, const Control& ctl, unsigned
 template <int KP>
 static unsigned launchUpdateW(const Peers& peers, const Layout& lay, float center, unsigned rows, unsigned k, float* B, float* corrP, const float* inv, float* W,
                               size_t ldw, float* Whi, float* Wlo, const float* Ppart, size_t ldp, size_t slotStride, const unsigned char* slotCount, float eps,
-                              float* statPart, bool update, cudaStream_t stream) {
+                              float* statPart, float* statFlag, bool update, cudaStream_t stream) {
 	const unsigned panels = ceilDiv(rows, 128);
 	if (panels == 0) return 0;
 	// one wave: as many blocks as are resident at once (shared memory: 50 KB at k = 64, 4 per SM), each walking
@@ -871,18 +888,18 @@ static unsigned launchUpdateW(const Peers& peers, const Layout& lay, float cente
 	const unsigned blocks = ceilDiv(panels, ceilDiv(panels, resident));
 	if (update)
 		update_w_fused<KP, true><<<blocks, 256, smemUpdateW<KP>(), stream>>>(peers, lay.statH, lay.statLen, center, rows, k, B, corrP, inv, W, ldw, Whi, Wlo, Ppart,
-		                                                                     ldp, slotStride, slotCount, eps, statPart);
+		                                                                     ldp, slotStride, slotCount, eps, statPart, statFlag);
 	else
 		update_w_fused<KP, false><<<blocks, 256, smemUpdateW<KP>(), stream>>>(peers, lay.statH, lay.statLen, center, rows, k, B, corrP, inv, W, ldw, Whi, Wlo, Ppart,
-		                                                                      ldp, slotStride, slotCount, eps, statPart);
+		                                                                      ldp, slotStride, slotCount, eps, statPart, statFlag);
 	launchCheck();
 	return blocks;
 }
 
 unsigned updateW(const Peers& peers, const Layout& lay, float center, unsigned rows, unsigned k, float* B, float* corrP, const float* inv, float* W, size_t ldw,
                  float* Whi, float* Wlo, const float* Ppart, size_t ldp, size_t slotStride, const unsigned char* slotCount, float eps, float* statPart,
-                 bool update, cudaStream_t stream) {
-#define NMF_ARGS peers, lay, center, rows, k, B, corrP, inv, W, ldw, Whi, Wlo, Ppart, ldp, slotStride, slotCount, eps, statPart, update, stream
+                 float* statFlag, bool update, cudaStream_t stream) {
+#define NMF_ARGS peers, lay, center, rows, k, B, corrP, inv, W, ldw, Whi, Wlo, Ppart, ldp, slotStride, slotCount, eps, statPart, statFlag, update, stream
 	if (k <= 16) return launchUpdateW<16>(NMF_ARGS);
 	if (k <= 32) return launchUpdateW<32>(NMF_ARGS);
 	if (k <= 64) return launchUpdateW<64>(NMF_ARGS);

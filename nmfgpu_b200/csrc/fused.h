@@ -1,15 +1,16 @@
 // fused.h -- the non-GEMM kernels of the MU iteration on the tensor-core path, one GPU or row blocks over several
-// (dist.h).  Together with the two tcgen05 products (tc_gemm.h) one iteration is SIX launches on one GPU, seven over several:
+// (dist.h).  Together with the two tcgen05 products (tc_gemm.h) one iteration is SIX launches, on one GPU and over several:
 //
 //   1  tc::gemmWtV        partial W_g^T V_g per stream-K slot
 //   1b pushN              (several ranks only) the slots summed, each column stored into the memory of the rank that owns it
-//                         (NVLink peer stores in whole 256-byte rows: the reduce-scatter); its last block signals "my
-//                         partials and the statistics of my rows of W are out"
+//                         (NVLink peer stores in whole 256-byte rows: the reduce-scatter); extra CTAs of the same launch sum
+//                         the block partials of the last W update and store this rank's W statistics to every rank (step 6
+//                         folded in); the last block signals "my partials and the statistics of my rows of W are out"
 //   2  updateH            every block: waits for every rank's signal, turns the statistics of the UN-NORMALISED W (Gram
 //                         matrix + column sums, summed over ranks) into the column scales 1/||w_c||, W^T W of the
 //                         unit-column matrix and the centring term of W^T V; then its panel of the own columns: adds up
 //                         the partials of all ranks, (W^T W) H, H <- H o N / (D + eps), residual term; the new columns
-//                         and their transposed TF32 split go to EVERY rank (peer stores: the all-gather is the epilogue);
+//                         stay here, their transposed TF32 split goes to EVERY rank (peer stores: the all-gather is the epilogue);
 //                         per-block Gram and row sums of the new columns
 //   3  reducePush         block partials -> this rank's H statistics, stored to every rank; last block signals "H is out"
 //   4  tc::gemmVHt        V_g H^T: the rank's own rows, no reduction across ranks.  Its B-operand producer waits for every
@@ -18,7 +19,7 @@
 //                         W_g <- (W_g/||.||) o P / ((W_g/||.||) (H H^T) + eps) with the column scale applied when W is READ,
 //                         so there is no normalisation pass (MU.h:247, KernelNormalizeColumns.cu); writes the new
 //                         un-normalised rows and their TF32 split; per-block Gram and column sums of the new rows
-//   6  reducePush         block partials -> this rank's W statistics, stored to every rank
+//   6  reducePush         (one rank only) block partials -> the W statistics
 //
 // Replaces, fused: cublasSsyrk/Ssymm G1, G2, G4, G5, multiplyDivide, normalizeColumns, traceMultiplication of the
 // reference's MU iteration (MU.h:164-248).  The Gram products are SIMT fp32 with fixed-order sums (exact, deterministic).
@@ -58,10 +59,6 @@ struct Control {
 	unsigned* epoch = nullptr;     // iteration counter of the protocol: advanced by the last block of pushN
 	unsigned* error = nullptr;     // set when a wait for another rank timed out
 	unsigned* tickets = nullptr;   // [4] grid-completion counters of the signalling kernels (pushN: 0, reducePush: 1, 2)
-	// 1: updateH and the H^T producer of V H^T wait for the other ranks themselves.  0: the ranks may share a GPU (thread
-	// transport of the tests) -- a kernel spinning on every SM would starve the kernels of the rank it waits for, so the
-	// engine launches waitFor (one block) in front of them instead
-	unsigned waitInKernel = 1;
 };
 constexpr size_t kNoSignal = ~(size_t)0;
 
@@ -72,16 +69,17 @@ void configure();
 // G (k x k), inv (k), corrN (k), statSum (k*k + k + 1 scratch) are local device buffers.
 void prepH(const Peers& peers, const Layout& lay, unsigned k, float center, float* statSum, float* G, float* inv, float* corrN, cudaStream_t stream);
 
-// step 1b.  localSlots: [slots][ldh * N] partial products of this rank's row block (slotCount per 128-column tile)
+// step 1b.  localSlots: [slots][ldh * N] partial products of this rank's row block (slotCount per 128-column tile).
+// Extra CTAs of the same launch do what reducePush does for the W statistics (statPartials: [statBlocks][statCount] block
+// partials of updateW, *statFlag the flag updateW left on the device) -- over several ranks the iteration has no separate
+// launch for them.
 void pushN(const Peers& peers, const Layout& lay, const Control& ctl, unsigned kp, unsigned N, unsigned colsPerRank, size_t ldh, const float* localSlots,
-           size_t localStride, const unsigned char* slotCount, cudaStream_t stream);
+           size_t localStride, const unsigned char* slotCount, const float* statPartials, unsigned statBlocks, unsigned statCount, const float* statFlag,
+           cudaStream_t stream);
 
 // residual iterations over several ranks, between updateH and the reducePush that signals: the fp64 sum of tracePartials
 // (count = own columns) stored to lay.trace[rank] on every rank
 void traceSumPush(const Peers& peers, const Layout& lay, const float* tracePartials, unsigned count, cudaStream_t stream);
-
-// one block that waits until every rank has signalled the current epoch on the flag array at flagOffset (lay.flagsN / lay.flagsH)
-void waitFor(const Peers& peers, size_t flagOffset, const Control& ctl, cudaStream_t stream);
 
 // columns per block of updateH for a rank that owns nOwn columns (statPart needs max(1, ceil(nOwn / that)) * (k*k + k) floats)
 unsigned panelColumnsH(unsigned nOwn);
@@ -107,9 +105,10 @@ void finishH(const Peers& peers, const Layout& lay, const Control& ctl, unsigned
 // step 5 on `rows` rows (W, Whi, Wlo point at the first of them; in place).  P: partial products of V H^T (ldp, slot stride,
 // slotCount per 128-row tile).  B (k x k) and corrP (k) are written by block 0.  update = false: no update, only the
 // statistics of W as it is (initial factors).  Returns the number of blocks (= partials in statPart, [blocks][k*k + k]).
+// statFlag (device, may be nullptr): set to 1 (update) / 0 (initial factors) for the launch that pushes these statistics.
 unsigned updateW(const Peers& peers, const Layout& lay, float center, unsigned rows, unsigned k, float* B, float* corrP, const float* inv, float* W, size_t ldw,
                  float* Whi, float* Wlo, const float* Ppart, size_t ldp, size_t slotStride, const unsigned char* slotCount, float eps, float* statPart,
-                 bool update, cudaStream_t stream);
+                 float* statFlag, bool update, cudaStream_t stream);
 
 // out[r + j * ldo] = inv[r] * (sum of all partials of W^T V) + corrN[r] for the own columns j (diagnostics: tests, bench)
 void collectN(const Peers& peers, const Layout& lay, unsigned k, unsigned c0, unsigned nOwn, unsigned colsPerRank, size_t ldh, unsigned slotsPerRank,

@@ -24,7 +24,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 # factors and residual of a sharded run against the single-GPU run of the same problem: the arithmetic is the same, only
 # the summation order of the partial products differs
-TOL_FACTOR, TOL_RESIDUAL = 5e-5, 5e-6
+TOL_FACTOR, TOL_RESIDUAL = 1e-5, 5e-6   # measured: 8e-7 / 3e-8
 
 
 def _single(L, algorithm, V, W0, H0, iters, params=None):
