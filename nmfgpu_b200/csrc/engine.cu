@@ -66,7 +66,9 @@ void uploadDense(T* dev, size_t ldDev, const T* host, size_t ldHost, unsigned ro
 	const size_t chunkBytes = 64u << 20;
 	const unsigned chunkCols = (unsigned)std::max<size_t>(1, chunkBytes / columnBytes);
 	const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-	const unsigned threads = std::max(2u, std::min(8u, hw / std::max(1u, ranksOnThisHost)));
+	// measured on the 16-thread host of a B200 box, 4 GB: 4 threads 188 ms per call, 8: 158, 12: 144, 16: 137, 24: 140 (profiles/r02_notes.md)
+	unsigned threads = std::max(2u, std::min(16u, hw / std::max(1u, ranksOnThisHost)));
+	if (const char* e = getenv("NMFGPU_UPLOAD_THREADS")) threads = std::max(1u, std::min(64u, (unsigned)atoi(e)));   // study knob
 	PinnedBuffer<T> staging[2];
 	cudaEvent_t drained[2] = {nullptr, nullptr};
 	for (int b = 0; b < 2; ++b) {
