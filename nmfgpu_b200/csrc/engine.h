@@ -104,7 +104,7 @@ public:
 
 private:
 	void iterateMU(bool err);
-	// MU on the tensor-core path, one GPU or row blocks over several (fused.h, dist.h): eight launches per iteration
+	// MU on the tensor-core path, one GPU or row blocks over several (fused.h, dist.h): six launches per iteration
 	bool decideFused();
 	void setupFused();
 	void finishInitialisationFused();

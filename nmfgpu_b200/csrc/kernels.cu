@@ -553,70 +553,6 @@ __global__ void scale_columns_kernel(unsigned m, unsigned k, T* __restrict__ W, 
 	}
 }
 
-// ---- row-owner multi-GPU dataflow (engine.cu): statistics of the un-normalised row block, scaled block, gathered W ----
-// stat = [W_un^T W_un (k x k, all-reduced), column sums of W_un (k)].  Unit columns: n_c = sqrt(stat[c,c]) where > 0
-// (KernelNormalizeColumns.cu:52-58), so W^T W of the normalised matrix is stat[i,j] / (n_i n_j).
-__global__ void finish_stats_kernel(unsigned k, const float* __restrict__ stat, float center, float* __restrict__ G, float* __restrict__ corrN) {
-	const unsigned i = threadIdx.x, j = blockIdx.x;
-	if (i >= k) return;
-	const float si = stat[(size_t)i * k + i], sj = stat[(size_t)j * k + j];
-	const float ni = si > 0.f ? sqrtf(si) : 1.f, nj = sj > 0.f ? sqrtf(sj) : 1.f;
-	G[(size_t)j * k + i] = stat[(size_t)j * k + i] / (ni * nj);
-	if (j == 0 && corrN != nullptr) corrN[i] = center * (stat[(size_t)k * k + i] / ni);
-}
-
-// stat[x] = sum over the ranks of gathered[g * stride + x], g ascending (what an all-reduce would deliver, in a fixed order)
-__global__ void sum_gathered_kernel(unsigned count, unsigned ranks, size_t stride, const float* __restrict__ gathered, float* __restrict__ stat) {
-	const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
-	if (x >= count) return;
-	float s = 0.f;
-	for (unsigned g = 0; g < ranks; ++g) s += gathered[(size_t)g * stride + x];
-	stat[x] = s;
-}
-
-// B = H H^T and the centring term of V H^T from the summed statistics [H_g H_g^T (k x k), row sums of H_g (k)]
-__global__ void finish_stats_h_kernel(unsigned k, const float* __restrict__ stat, float center, float* __restrict__ B, float* __restrict__ corrP) {
-	const unsigned i = threadIdx.x, j = blockIdx.x;
-	if (i >= k) return;
-	B[(size_t)j * k + i] = stat[(size_t)j * k + i];
-	if (j == 0) corrP[i] = center * stat[(size_t)k * k + i];
-}
-
-// block[c * ldb + r] = W[r, c] / n_c for the rows of this rank (zero beyond `rows`)
-__global__ void scale_pack_kernel(unsigned rows, unsigned rowsPadded, unsigned k, const float* __restrict__ W, size_t ldw, const float* __restrict__ stat,
-                                  float* __restrict__ block) {
-	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
-	const unsigned c = blockIdx.y;
-	if (r >= rowsPadded) return;
-	float v = 0.f;
-	if (r < rows) {
-		v = W[(size_t)c * ldw + r];
-		if (stat != nullptr) {   // nullptr: pack only, the unpack kernel scales
-			const float s = stat[(size_t)c * k + c];
-			if (s > 0.f) v = v / sqrtf(s);
-		}
-	}
-	block[(size_t)c * rowsPadded + r] = v;
-}
-
-// W, hi, lo (m x k, ld ldw) <- gathered[(g * k + c) * rowsPadded + r], global row = g * rowsPadded + r
-__global__ void unpack_split_kernel(unsigned m, unsigned k, unsigned rowsPadded, const float* __restrict__ gathered, float* __restrict__ W, size_t ldw,
-                                    float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ stat) {
-	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-	const unsigned c = blockIdx.y;
-	if (i >= m) return;
-	const unsigned g = i / rowsPadded, r = i - g * rowsPadded;
-	float v = gathered[((size_t)g * k + c) * rowsPadded + r];
-	if (stat != nullptr) {   // un-normalised blocks were gathered: unit columns here (KernelNormalizeColumns.cu:52-58)
-		const float s = stat[(size_t)c * k + c];
-		if (s > 0.f) v = v / sqrtf(s);
-	}
-	W[(size_t)c * ldw + i] = v;
-	const float h = tf32_hi(v);
-	hi[(size_t)c * ldw + i] = h;
-	lo[(size_t)c * ldw + i] = v - h;
-}
-
 __global__ void split_tf32_kernel(unsigned rows, unsigned cols, const float* __restrict__ X, size_t ldx, float* __restrict__ hi,
                                   float* __restrict__ lo, size_t ldo) {
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1208,34 +1144,6 @@ template <typename T>
 void scaleColumns(unsigned m, unsigned k, T* W, size_t ldw, const T* colSq, float* Whi, float* Wlo, cudaStream_t stream) {
 	dim3 grid(ceilDiv(m, 256), k);
 	scale_columns_kernel<T><<<grid, 256, 0, stream>>>(m, k, W, ldw, colSq, Whi, Wlo);
-	launchCheck();
-}
-
-void finishStats(unsigned k, const float* stat, float center, float* G, float* corrN, cudaStream_t stream) {
-	finish_stats_kernel<<<k, roundUp(k, 32), 0, stream>>>(k, stat, center, G, corrN);
-	launchCheck();
-}
-
-void scalePackRows(unsigned rows, unsigned rowsPadded, unsigned k, const float* W, size_t ldw, const float* stat, float* block, cudaStream_t stream) {
-	dim3 grid(ceilDiv(rowsPadded, 256), k);
-	scale_pack_kernel<<<grid, 256, 0, stream>>>(rows, rowsPadded, k, W, ldw, stat, block);
-	launchCheck();
-}
-
-void sumGathered(unsigned count, unsigned ranks, size_t stride, const float* gathered, float* stat, cudaStream_t stream) {
-	sum_gathered_kernel<<<ceilDiv(count, 256), 256, 0, stream>>>(count, ranks, stride, gathered, stat);
-	launchCheck();
-}
-
-void finishStatsH(unsigned k, const float* stat, float center, float* B, float* corrP, cudaStream_t stream) {
-	finish_stats_h_kernel<<<k, roundUp(k, 32), 0, stream>>>(k, stat, center, B, corrP);
-	launchCheck();
-}
-
-void unpackSplit(unsigned m, unsigned k, unsigned rowsPadded, const float* gathered, float* W, size_t ldw, float* hi, float* lo, cudaStream_t stream,
-                 const float* stat) {
-	dim3 grid(ceilDiv(m, 256), k);
-	unpack_split_kernel<<<grid, 256, 0, stream>>>(m, k, rowsPadded, gathered, W, ldw, hi, lo, stat);
 	launchCheck();
 }
 

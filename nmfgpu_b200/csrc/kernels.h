@@ -116,21 +116,6 @@ void qrSolveClamp(unsigned k, const T* factor, T* R, size_t ldr, unsigned nrhs, 
 // TF32 hi/lo split of a dense block: hi = rn_tf32(x), lo = x - hi
 void splitTf32(unsigned rows, unsigned cols, const float* X, size_t ldx, float* hi, float* lo, size_t ldo, cudaStream_t stream);
 
-// ---- row-owner multi-GPU dataflow (engine.cu, dist.h) ---------------------------------------------------
-// stat = [W_un^T W_un (k x k), column sums of W_un (k)] summed over all ranks:  G <- Gram of the unit-column matrix,
-// corrN <- center * column sums of the unit-column matrix (the centring term of W^T V, tc_gemm.h)
-void finishStats(unsigned k, const float* stat, float center, float* G, float* corrN, cudaStream_t stream);
-// block (k columns of rowsPadded values) <- this rank's rows of W scaled to unit columns (stat == nullptr: unscaled); zero beyond `rows`
-void scalePackRows(unsigned rows, unsigned rowsPadded, unsigned k, const float* W, size_t ldw, const float* stat, float* block, cudaStream_t stream);
-// W and its TF32 hi/lo split (m x k) <- the all-gathered blocks
-// (stat != nullptr: the gathered blocks are un-normalised and column c is divided by sqrt(stat[c, c]) here)
-void unpackSplit(unsigned m, unsigned k, unsigned rowsPadded, const float* gathered, float* W, size_t ldw, float* hi, float* lo, cudaStream_t stream,
-                 const float* stat = nullptr);
-// stat[x] = sum_g gathered[g * stride + x] in rank order: the all-gathered partial statistics of every rank added up locally
-void sumGathered(unsigned count, unsigned ranks, size_t stride, const float* gathered, float* stat, cudaStream_t stream);
-// B <- stat[0 .. k*k), corrP <- center * stat[k*k .. k*k + k): H H^T and the centring term of V H^T from the summed statistics
-void finishStatsH(unsigned k, const float* stat, float center, float* B, float* corrP, cudaStream_t stream);
-
 // |x| and max(0,x) variants for the k-means based initialisations (KMeansStrategy.cpp:31-40)
 template <typename T>
 void absInPlace(unsigned rows, unsigned cols, T* A, size_t lda, cudaStream_t stream);

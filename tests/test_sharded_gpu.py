@@ -2,11 +2,13 @@
 
 The ranks are THREADS of this process (nmfgpu_b200_dist_local_unique_id, csrc/dist.h), all on cuda:0, so the test runs on a
 single-GPU box.  What executes is the product code: the same engine, the same kernels and the same exchange protocol as
-with one process per GPU -- peer stores into the other ranks' exchange buffers, epoch flags, last-block signals.  Two things
-differ: the setup-time collectives go through memcpy instead of NCCL, and because the ranks share one GPU the waits for the
-other ranks run as one-block kernels of their own instead of inside the update / product kernels (a kernel spinning on every
-SM would starve the rank it waits for; csrc/dist.h ranksMayShareDevice).  The in-kernel waits are what tools/dist_check.py
-and bench.py --gpus N exercise with one process per GPU.
+with one process per GPU -- peer stores into the other ranks' exchange buffers, epoch flags, last-block signals, in-kernel
+waits.  Two things differ: the setup-time collectives go through memcpy instead of NCCL, and because the ranks share one GPU
+they meet on the host (stream synchronise + barrier) before every kernel that waits for another rank, and no CUDA graphs are
+used: a kernel spinning on the shared GPU can keep the rank it waits for from running at all (csrc/dist.h
+ranksMayShareDevice, csrc/engine.cu m_hostLockstep).  The waits still execute and find their flags set -- a flag that is
+never raised would hit the 10 s watchdog and fail the test.  Waits that really wait are what tools/dist_check.py and
+bench.py --gpus N exercise with one process per GPU.
 """
 import ctypes
 import os
