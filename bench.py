@@ -238,15 +238,15 @@ def run_ours(args, rank, world, local):
     ms, f_timed = s.time_run(args.steps)        # CUDA events on the engine's stream around exactly K iterations, residual cadence included
     barrier()
     info1 = s.info()
-    # clocks under this load: the timed region lasts 7-35 ms at 20 steps, less than two nvidia-smi samples, so the same
-    # iterations keep running (untimed) until the sampling window is 0.4 s long
-    while time.time() - wall0 < 0.4:
+    # clocks under this load: the timed region lasts 6-35 ms at 20 steps, less than two nvidia-smi samples, so the same
+    # iterations keep running (untimed) until the sampling window is 0.15 s long
+    while time.time() - wall0 < 0.15:
         s.iterate(10)
         s.synchronize()
     barrier()
     clocks = sampler.stop(wall0, time.time()) if sampler else None
     if clocks is not None:
-        clocks["window"] = "the timed iterations and the same iterations continued to 0.4 s"
+        clocks["window"] = "the timed iterations and the same iterations continued to 0.15 s"
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
