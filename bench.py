@@ -238,19 +238,22 @@ def run_ours(args, rank, world, local):
     ms, f_timed = s.time_run(args.steps)        # CUDA events on the engine's stream around exactly K iterations, residual cadence included
     barrier()
     info1 = s.info()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
     # clocks under this load: the timed region lasts 6-35 ms at 20 steps, less than two nvidia-smi samples, so the same
-    # iterations keep running (untimed) until the sampling window is 0.15 s long
-    while time.time() - wall0 < 0.15:
+    # iterations keep running (untimed) until the sampling window is about 0.15 s long.  The number of extra batches
+    # follows from the reduced time, so every rank runs the same number (the ranks of a sharded run iterate in lockstep:
+    # a rank that decided by its own clock to do one batch more would wait for signals that never come)
+    extra = int(np.ceil(max(0.0, 150.0 - ms) / max(ms / args.steps * 10.0, 1e-3)))
+    for _ in range(extra):
         s.iterate(10)
         s.synchronize()
     barrier()
     clocks = sampler.stop(wall0, time.time()) if sampler else None
     if clocks is not None:
-        clocks["window"] = "the timed iterations and the same iterations continued to 0.15 s"
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+        clocks["window"] = "the timed iterations and %d more of the same iterations (about 0.15 s in all)" % (10 * extra)
     launches = int(info1.kernel_launches - info0.kernel_launches)
     collectives = int(info1.collective_calls - info0.collective_calls)
     f_final, _ = s.iterate_with_error()
