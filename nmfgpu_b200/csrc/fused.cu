@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256) push_n_kernel(Peers peers, size_t oSlots,
 	lastBlockSignals(peers, flagsN, ctl, 0, true);
 }
 
-// ---- step 3 ------------------------------------------------------------------------------------------------------------
+// ---- step 2 ------------------------------------------------------------------------------------------------------------
 // A COLS-column panel of the own columns per block of 4 COLS threads (64 columns; 32 or 16 when the rank owns so few
 // columns that 64-wide panels would leave most SMs idle).  D = G H is a register-tiled product out of shared memory
 // (thread = KP/16 rows x 4 columns); the numerators are the partial products of all ranks and slots, fetched several
