@@ -5,6 +5,9 @@
 
 #include <cub/cub.cuh>
 
+#include <cstdint>
+#include <cstdlib>
+
 namespace nmfgpu {
 namespace b200 {
 namespace sparse {
@@ -87,8 +90,98 @@ void sortPositions(unsigned nnz, const unsigned* keys, unsigned keyCount, unsign
 
 // ---- products ------------------------------------------------------------------------------------------------
 // One warp per compressed row/column.  The 32 lanes load 32 (index, value) pairs at once and hand them round by
-// shuffle; lane l accumulates the output entries l, l + 32, ... (KQ of them), so every gather of an operand row is
-// KQ coalesced 128-byte requests.  Four entries are in flight per step to cover the L2 / HBM latency of the gathers.
+// shuffle; every gather of an operand row is ONE 16-byte load per lane (lane l holds the output entries 4 l .. 4 l + 3 in
+// fp32, 2 l, 2 l + 1 in fp64; k = 100: 25 lanes, 400 bytes, four 128-byte lines).  Four entries are in flight per step to
+// cover the L2 / HBM latency of the gathers; per output entry the FMAs run in stored order (deterministic, and the same
+// bits as the scalar variant below).  ncu on a quarter of configs[4] (profiles/r02_spmm_ncu_summary.json) showed the scalar
+// variant -- four 4-byte loads per lane and gather -- at 62-72 % issue-slot utilisation with the L2 at 42-48 %: instruction
+// bound before it is gather bound, hence one wide load instead of four.
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { using type = float4; static constexpr int N = 4; };
+template <> struct Vec16<double> { using type = double2; static constexpr int N = 2; };
+
+template <typename T, int VQ>
+__global__ void __launch_bounds__(256) spmm_gather_vec_kernel(unsigned numMajor, unsigned k, const int* __restrict__ ptrBegin,
+                                                              const int* __restrict__ ptrEnd, const int* __restrict__ idx, const T* __restrict__ val,
+                                                              const T* __restrict__ D, size_t ldd, T* __restrict__ out, size_t ldo) {
+	using V = typename Vec16<T>::type;
+	constexpr int E = Vec16<T>::N;
+	const unsigned r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+	const unsigned lane = threadIdx.x % 32;
+	if (r >= numMajor) return;
+	const unsigned vecs = (k + E - 1) / E;   // 16-byte pieces of an operand row (the rows are padded to 32 entries: always readable)
+	const int begin = ptrBegin[r], end = ptrEnd[r];
+	T acc[VQ][E];
+#pragma unroll
+	for (int q = 0; q < VQ; ++q)
+#pragma unroll
+		for (int e = 0; e < E; ++e) acc[q][e] = T(0);
+	auto load = [&](int jj, T (&d)[VQ][E]) {
+		const V* row = reinterpret_cast<const V*>(D + (size_t)jj * ldd);
+#pragma unroll
+		for (int q = 0; q < VQ; ++q) {
+			if (lane + 32 * q < vecs) {
+				const V x = row[lane + 32 * q];
+				const T* xe = reinterpret_cast<const T*>(&x);
+#pragma unroll
+				for (int e = 0; e < E; ++e) d[q][e] = xe[e];
+			} else {
+#pragma unroll
+				for (int e = 0; e < E; ++e) d[q][e] = T(0);
+			}
+		}
+	};
+	for (int base = begin; base < end; base += 32) {
+		const int e = base + (int)lane;
+		const int j = e < end ? idx[e] : 0;
+		const T v = e < end ? val[e] : T(0);
+		const int cnt = min(32, end - base);
+		int t = 0;
+		for (; t + 4 <= cnt; t += 4) {
+			T d[4][VQ][E], vv[4];
+#pragma unroll
+			for (int u = 0; u < 4; ++u) {
+				const int jj = __shfl_sync(0xffffffffu, j, t + u);
+				vv[u] = __shfl_sync(0xffffffffu, v, t + u);
+				load(jj, d[u]);
+			}
+#pragma unroll
+			for (int u = 0; u < 4; ++u)
+#pragma unroll
+				for (int q = 0; q < VQ; ++q)
+#pragma unroll
+					for (int x = 0; x < E; ++x) acc[q][x] = fma(vv[u], d[u][q][x], acc[q][x]);
+		}
+		for (; t < cnt; ++t) {
+			const int jj = __shfl_sync(0xffffffffu, j, t);
+			const T vv = __shfl_sync(0xffffffffu, v, t);
+			T d[VQ][E];
+			load(jj, d);
+#pragma unroll
+			for (int q = 0; q < VQ; ++q)
+#pragma unroll
+				for (int x = 0; x < E; ++x) acc[q][x] = fma(vv, d[q][x], acc[q][x]);
+		}
+	}
+	T* orow = out + (size_t)r * ldo;
+#pragma unroll
+	for (int q = 0; q < VQ; ++q) {
+		const unsigned e0 = (lane + 32 * q) * E;
+		if (e0 + E <= k) {
+			V x;
+			T* xe = reinterpret_cast<T*>(&x);
+#pragma unroll
+			for (int e = 0; e < E; ++e) xe[e] = acc[q][e];
+			*reinterpret_cast<V*>(orow + e0) = x;
+		} else {
+#pragma unroll
+			for (int e = 0; e < E; ++e)
+				if (e0 + e < k) orow[e0 + e] = acc[q][e];
+		}
+	}
+}
+
+// the scalar variant (NMFGPU_SPMM_SCALAR=1: A/B comparisons): lane l accumulates the output entries l, l + 32, ... (KQ of them)
 template <typename T, int KQ>
 __global__ void __launch_bounds__(256) spmm_gather_kernel(unsigned numMajor, unsigned k, const int* __restrict__ ptrBegin,
                                                           const int* __restrict__ ptrEnd, const int* __restrict__ idx, const T* __restrict__ val,
@@ -269,6 +362,19 @@ void spmmGather(unsigned numMajor, unsigned k, const int* ptrBegin, const int* p
 	if (numMajor == 0) return;
 	if (k > 128) throw EngineError(ResultType::ErrorInvalidArgument, "sparse products support at most 128 features");
 	const unsigned grid = ceilDiv(numMajor, 8);
+	static const bool scalar = [] {
+		const char* e = getenv("NMFGPU_SPMM_SCALAR");
+		return e != nullptr && atoi(e) != 0;
+	}();
+	const bool aligned = ldd % (16 / sizeof(T)) == 0 && ldo % (16 / sizeof(T)) == 0 && reinterpret_cast<uintptr_t>(D) % 16 == 0 &&
+	                     reinterpret_cast<uintptr_t>(out) % 16 == 0;
+	if (!scalar && aligned) {
+		const unsigned vecs = ceilDiv(k, (unsigned)(16 / sizeof(T)));
+		if (vecs <= 32) spmm_gather_vec_kernel<T, 1><<<grid, 256, 0, stream>>>(numMajor, k, ptrBegin, ptrEnd, idx, val, D, ldd, out, ldo);
+		else spmm_gather_vec_kernel<T, 2><<<grid, 256, 0, stream>>>(numMajor, k, ptrBegin, ptrEnd, idx, val, D, ldd, out, ldo);
+		CUDA_CHECK(cudaGetLastError());
+		return;
+	}
 	switch (ceilDiv(k, 32)) {
 	case 1: spmm_gather_kernel<T, 1><<<grid, 256, 0, stream>>>(numMajor, k, ptrBegin, ptrEnd, idx, val, D, ldd, out, ldo); break;
 	case 2: spmm_gather_kernel<T, 2><<<grid, 256, 0, stream>>>(numMajor, k, ptrBegin, ptrEnd, idx, val, D, ldd, out, ldo); break;
