@@ -119,3 +119,22 @@ def test_product_sources_never_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 text = open(os.path.join(base, f), errors="ignore").read()
                 assert not re.search(r"import\s+oracle|from\s+oracle|#include\s+[\"<][^\n]*oracle|liboracle|oracle\.binding|oracle/", text), os.path.join(base, f)
+
+
+def test_library_contains_the_blackwell_instructions(library_path):
+    """The built libnmfgpu64.so carries sm_100a code whose V-sized products are tcgen05 / TMA kernels: UTCHMMA
+    (tcgen05.mma), UTMALDG (TMA tensor load), LDTM / STTM (tcgen05.ld / st) in the SASS of tc_stream_gemm, and no cuBLAS
+    among its dependencies.  (What profiles/r02_sass_counts.txt records, checked on every build.)"""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", library_path], capture_output=True, text=True, timeout=600).stdout
+    assert "sm_100a" in sass
+    blocks = sass.split("Function : ")
+    gemm = [b for b in blocks if "tc_stream_gemm" in b.split("\n", 1)[0]]
+    assert len(gemm) == 4, [b.split("\n", 1)[0] for b in gemm]            # <64|128> x <W^T V | V H^T>
+    for b in gemm:
+        for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UTCBAR"):
+            assert mnemonic in b, (b.split("\n", 1)[0], mnemonic)
+    needed = subprocess.run(["readelf", "-d", library_path], capture_output=True, text=True).stdout
+    assert "cublas" not in needed.lower() and "cusolver" not in needed.lower() and "cusparse" not in needed.lower()
